@@ -1,0 +1,341 @@
+// bvh.cpp — binned-SAH BVH2 build on the host and breadth-first flattening (see bvh.h).
+#include "bvh.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <queue>
+
+namespace gort {
+namespace {
+
+struct BPrim {
+    double lo[3], hi[3], c[3];
+    int32_t type;  // 0 sphere, 1 triangle
+    int32_t idx;   // index into HostScene::spheres / ::tris
+};
+
+struct BNode {
+    double lo[3], hi[3];
+    int32_t left = -1, right = -1;  // tree-node indices; -1 => leaf
+    int32_t first = 0, count = 0;   // leaf: range in the prim permutation
+    int32_t type = 0;               // leaf: primitive type
+    int32_t depth = 0;
+};
+
+struct Box {
+    double lo[3], hi[3];
+    void reset() {
+        for (int a = 0; a < 3; a++) {
+            lo[a] = std::numeric_limits<double>::infinity();
+            hi[a] = -std::numeric_limits<double>::infinity();
+        }
+    }
+    void grow(const double* l, const double* h) {
+        for (int a = 0; a < 3; a++) {
+            lo[a] = std::min(lo[a], l[a]);
+            hi[a] = std::max(hi[a], h[a]);
+        }
+    }
+    void grow(const Box& b) { grow(b.lo, b.hi); }
+    double area() const {
+        double dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        if (dx < 0 || dy < 0 || dz < 0) return 0;
+        return 2.0 * (dx * dy + dy * dz + dz * dx);
+    }
+};
+
+constexpr int kBins = 16;
+
+struct Builder {
+    std::vector<BPrim> prims;
+    std::vector<BNode> nodes;
+    int max_depth = 0;
+
+    int make_leaf(int first, int count, int depth, const Box& b) {
+        BNode n;
+        memcpy(n.lo, b.lo, sizeof(n.lo));
+        memcpy(n.hi, b.hi, sizeof(n.hi));
+        n.first = first;
+        n.count = count;
+        n.type = prims[first].type;
+        n.depth = depth;
+        max_depth = std::max(max_depth, depth);
+        nodes.push_back(n);
+        return (int)nodes.size() - 1;
+    }
+
+    int build(int first, int count, int depth) {
+        Box b, cb;
+        b.reset();
+        cb.reset();
+        bool mixed = false;
+        for (int i = first; i < first + count; i++) {
+            b.grow(prims[i].lo, prims[i].hi);
+            cb.grow(prims[i].c, prims[i].c);
+            if (prims[i].type != prims[first].type) mixed = true;
+        }
+        int split = -1;  // prims [first, split) go left
+
+        if (count <= kMaxLeafPrims && mixed) {
+            // homogeneous leaves only: separate the types
+            auto mid = std::stable_partition(prims.begin() + first, prims.begin() + first + count,
+                                             [](const BPrim& p) { return p.type == 0; });
+            split = (int)(mid - prims.begin());
+        } else if (count == 1) {
+            return make_leaf(first, count, depth, b);
+        } else if (depth >= 32) {
+            // depth guard: balanced median split on the longest centroid axis
+            int axis = 0;
+            for (int a = 1; a < 3; a++)
+                if (cb.hi[a] - cb.lo[a] > cb.hi[axis] - cb.lo[axis]) axis = a;
+            if (count <= kMaxLeafPrims) return make_leaf(first, count, depth, b);
+            split = first + count / 2;
+            std::nth_element(prims.begin() + first, prims.begin() + split, prims.begin() + first + count,
+                             [axis](const BPrim& x, const BPrim& y) { return x.c[axis] < y.c[axis]; });
+        } else {
+            // binned SAH over the three axes
+            double best_cost = std::numeric_limits<double>::infinity();
+            int best_axis = -1, best_bin = -1;
+            const double parent_area = b.area();
+            for (int axis = 0; axis < 3; axis++) {
+                double cmin = cb.lo[axis], cmax = cb.hi[axis];
+                if (!(cmax > cmin)) continue;
+                Box bin_box[kBins];
+                int bin_cnt[kBins];
+                for (int k = 0; k < kBins; k++) {
+                    bin_box[k].reset();
+                    bin_cnt[k] = 0;
+                }
+                const double scale = kBins / (cmax - cmin);
+                for (int i = first; i < first + count; i++) {
+                    int k = std::min(kBins - 1, std::max(0, (int)((prims[i].c[axis] - cmin) * scale)));
+                    bin_cnt[k]++;
+                    bin_box[k].grow(prims[i].lo, prims[i].hi);
+                }
+                double right_area[kBins];
+                int right_cnt[kBins];
+                Box acc;
+                acc.reset();
+                int cnt = 0;
+                for (int k = kBins - 1; k > 0; k--) {
+                    acc.grow(bin_box[k]);
+                    cnt += bin_cnt[k];
+                    right_area[k] = acc.area();
+                    right_cnt[k] = cnt;
+                }
+                acc.reset();
+                cnt = 0;
+                for (int k = 0; k < kBins - 1; k++) {
+                    acc.grow(bin_box[k]);
+                    cnt += bin_cnt[k];
+                    if (cnt == 0 || right_cnt[k + 1] == 0) continue;
+                    double cost = acc.area() * cnt + right_area[k + 1] * right_cnt[k + 1];
+                    if (cost < best_cost) {
+                        best_cost = cost;
+                        best_axis = axis;
+                        best_bin = k;
+                    }
+                }
+            }
+            if (best_axis >= 0 && count <= kMaxLeafPrims) {
+                // leaf cost = count (one unit per primitive test); split cost = 1 (node) + SAH
+                double split_cost = 1.0 + (parent_area > 0 ? best_cost / parent_area : (double)count);
+                if (split_cost >= (double)count) return make_leaf(first, count, depth, b);
+            }
+            if (best_axis < 0) {
+                if (count <= kMaxLeafPrims) return make_leaf(first, count, depth, b);
+                split = first + count / 2;  // identical centroids: split by index
+            } else {
+                const double cmin = cb.lo[best_axis], cmax = cb.hi[best_axis];
+                const double scale = kBins / (cmax - cmin);
+                auto mid = std::partition(prims.begin() + first, prims.begin() + first + count, [&](const BPrim& p) {
+                    int k = std::min(kBins - 1, std::max(0, (int)((p.c[best_axis] - cmin) * scale)));
+                    return k <= best_bin;
+                });
+                split = (int)(mid - prims.begin());
+                if (split == first || split == first + count) split = first + count / 2;
+            }
+        }
+
+        BNode n;
+        memcpy(n.lo, b.lo, sizeof(n.lo));
+        memcpy(n.hi, b.hi, sizeof(n.hi));
+        n.depth = depth;
+        n.first = first;
+        n.count = count;
+        nodes.push_back(n);
+        int self = (int)nodes.size() - 1;
+        int l = build(first, split - first, depth + 1);
+        int r = build(split, first + count - split, depth + 1);
+        nodes[self].left = l;
+        nodes[self].right = r;
+        return self;
+    }
+};
+
+inline float round_down(double v) {
+    float f = (float)v;
+    if ((double)f > v) f = std::nextafterf(f, -std::numeric_limits<float>::infinity());
+    return f;
+}
+inline float round_up(double v) {
+    float f = (float)v;
+    if ((double)f < v) f = std::nextafterf(f, std::numeric_limits<float>::infinity());
+    return f;
+}
+inline float as_float(int32_t i) {
+    float f;
+    memcpy(&f, &i, 4);
+    return f;
+}
+
+}  // namespace
+
+void build_bvh(const HostScene& scene, FlatBvh& out) {
+    auto t0 = std::chrono::steady_clock::now();
+    out = FlatBvh();
+    Builder B;
+    const int nS = (int)scene.spheres.size(), nT = (int)scene.tris.size();
+    B.prims.reserve((size_t)nS + nT);
+    Box world;
+    world.reset();
+    for (int i = 0; i < nS; i++) {
+        const HostSphere& s = scene.spheres[i];
+        BPrim p;
+        double r = std::fabs(s.r);
+        for (int a = 0; a < 3; a++) {
+            p.lo[a] = s.c[a] - r;
+            p.hi[a] = s.c[a] + r;
+            p.c[a] = s.c[a];
+        }
+        p.type = 0;
+        p.idx = i;
+        B.prims.push_back(p);
+        world.grow(p.lo, p.hi);
+    }
+    for (int i = 0; i < nT; i++) {
+        const HostTriangle& t = scene.tris[i];
+        BPrim p;
+        for (int a = 0; a < 3; a++) {
+            p.lo[a] = std::min(t.v[0][a], std::min(t.v[1][a], t.v[2][a]));
+            p.hi[a] = std::max(t.v[0][a], std::max(t.v[1][a], t.v[2][a]));
+            p.c[a] = 0.5 * (p.lo[a] + p.hi[a]);
+        }
+        p.type = 1;
+        p.idx = i;
+        B.prims.push_back(p);
+        world.grow(p.lo, p.hi);
+    }
+    const int n = nS + nT;
+    if (n == 0) return;
+
+    B.nodes.reserve((size_t)n);
+    int root = B.build(0, n, 0);
+    // Aila-Laine nodes store the children's boxes in the parent, so a leaf root needs a wrapper.
+    if (B.nodes[root].left < 0) {
+        BNode w = B.nodes[root];
+        w.left = root;
+        w.right = -2;  // empty
+        w.depth = 0;
+        B.nodes.push_back(w);
+        root = (int)B.nodes.size() - 1;
+    }
+
+    // conservative padding for fp32 slab arithmetic (see DESIGN.md "BVH")
+    double extent = 0;
+    for (int a = 0; a < 3; a++) extent = std::max(extent, std::max(std::fabs(world.lo[a]), std::fabs(world.hi[a])));
+    const double pad = 4e-7 * std::max(1.0, extent);
+
+    // breadth-first numbering of inner nodes
+    std::vector<int32_t> flat_index(B.nodes.size(), -1);
+    std::vector<int32_t> order;
+    order.reserve(B.nodes.size());
+    {
+        std::queue<int32_t> q;
+        q.push(root);
+        while (!q.empty()) {
+            int32_t t = q.front();
+            q.pop();
+            flat_index[t] = (int32_t)order.size();
+            order.push_back(t);
+            const BNode& nd = B.nodes[t];
+            if (nd.left >= 0 && B.nodes[nd.left].left != -1) q.push(nd.left);
+            if (nd.right >= 0 && B.nodes[nd.right].left != -1) q.push(nd.right);
+        }
+    }
+    out.n_nodes = (int32_t)order.size();
+    out.nodes.resize((size_t)out.n_nodes * 4);
+    out.spheres.reserve(nS);
+    out.sphere_meta.reserve(nS);
+    out.tris.reserve((size_t)nT * 4);
+    out.max_depth = B.max_depth + 1;
+
+    auto emit_leaf = [&](const BNode& leaf) -> int32_t {
+        uint32_t start;
+        if (leaf.type == 0) {
+            start = (uint32_t)out.spheres.size();
+            for (int i = leaf.first; i < leaf.first + leaf.count; i++) {
+                const HostSphere& s = scene.spheres[B.prims[i].idx];
+                out.spheres.push_back(F4{(float)s.c[0], (float)s.c[1], (float)s.c[2], (float)s.r});
+                out.sphere_meta.push_back(I2{s.mat, s.order});
+            }
+        } else {
+            start = (uint32_t)(out.tris.size() / 4);
+            for (int i = leaf.first; i < leaf.first + leaf.count; i++) {
+                const HostTriangle& t = scene.tris[B.prims[i].idx];
+                double e1[3], e2[3], nrm[3];
+                for (int a = 0; a < 3; a++) {
+                    e1[a] = t.v[1][a] - t.v[0][a];
+                    e2[a] = t.v[2][a] - t.v[0][a];
+                }
+                // calculateNormal (triangle.go:30-34): normalize(e1 x e2), zero-safe (vector.go:61-67)
+                nrm[0] = e1[1] * e2[2] - e1[2] * e2[1];
+                nrm[1] = e1[2] * e2[0] - e1[0] * e2[2];
+                nrm[2] = e1[0] * e2[1] - e1[1] * e2[0];
+                double len = std::sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
+                if (len == 0) nrm[0] = nrm[1] = nrm[2] = 0;
+                else for (int a = 0; a < 3; a++) nrm[a] /= len;
+                out.tris.push_back(F4{(float)t.v[0][0], (float)t.v[0][1], (float)t.v[0][2], as_float(t.mat)});
+                out.tris.push_back(F4{(float)e1[0], (float)e1[1], (float)e1[2], as_float(t.order)});
+                out.tris.push_back(F4{(float)e2[0], (float)e2[1], (float)e2[2], 0.f});
+                out.tris.push_back(F4{(float)nrm[0], (float)nrm[1], (float)nrm[2], 0.f});
+            }
+        }
+        uint32_t v = (start & kLeafStartMask) | ((uint32_t)(leaf.count - 1) << kLeafCountShift) | ((uint32_t)leaf.type << kLeafTypeBit);
+        return (int32_t)~v;
+    };
+
+    const float inf = std::numeric_limits<float>::infinity();
+    for (int32_t fi = 0; fi < out.n_nodes; fi++) {
+        const BNode& nd = B.nodes[order[fi]];
+        float lo[2][3], hi[2][3];
+        int32_t child[2];
+        const int32_t kids[2] = {nd.left, nd.right};
+        for (int c = 0; c < 2; c++) {
+            if (kids[c] < 0) {  // empty slot
+                for (int a = 0; a < 3; a++) {
+                    lo[c][a] = inf;
+                    hi[c][a] = -inf;
+                }
+                child[c] = (int32_t)~0u;  // decodes as a 1-sphere leaf at 0 but its box is never hit
+                continue;
+            }
+            const BNode& k = B.nodes[kids[c]];
+            for (int a = 0; a < 3; a++) {
+                lo[c][a] = round_down(k.lo[a] - pad);
+                hi[c][a] = round_up(k.hi[a] + pad);
+            }
+            child[c] = (k.left == -1) ? emit_leaf(k) : flat_index[kids[c]];
+        }
+        out.nodes[(size_t)fi * 4 + 0] = F4{lo[0][0], hi[0][0], lo[0][1], hi[0][1]};
+        out.nodes[(size_t)fi * 4 + 1] = F4{lo[1][0], hi[1][0], lo[1][1], hi[1][1]};
+        out.nodes[(size_t)fi * 4 + 2] = F4{lo[0][2], hi[0][2], lo[1][2], hi[1][2]};
+        out.nodes[(size_t)fi * 4 + 3] = F4{as_float(child[0]), as_float(child[1]), 0.f, 0.f};
+    }
+    out.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+}  // namespace gort

@@ -1,0 +1,772 @@
+// capi.cu — the C ABI of libgort.so (include/gort.h): context, scene upload, frame render.
+// Replaces the body of ParallelRenderer.Render (/root/reference internal/renderer/renderer.go:67-126).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/gort.h"
+#include "bvh.h"
+#include "host_scene.h"
+#include "kernels.h"
+
+using namespace gort;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DeviceState {
+    int dev = -1;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    // scene (replicated on every device)
+    float4* d_nodes = nullptr;
+    float4* d_spheres = nullptr;
+    int2* d_meta = nullptr;
+    float4* d_tris = nullptr;
+    float4* d_mats = nullptr;
+    float4* d_lights = nullptr;
+    // per-frame buffers
+    unsigned long long* d_accum = nullptr;
+    size_t accum_tiles = 0;
+    unsigned int* d_counter = nullptr;
+    unsigned long long* d_stats = nullptr;
+    uint8_t* d_out = nullptr;  // frame (row-major) or slab (tile-major)
+    size_t out_bytes = 0;
+    uint8_t* d_gather = nullptr;  // lead device only: rank-major slabs of all devices
+    size_t gather_bytes = 0;
+    uint8_t* h_pinned = nullptr;
+    size_t pinned_bytes = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+struct gort_ctx {
+    std::vector<DeviceState> devs;
+    cudaStream_t user_stream = nullptr;
+    bool use_user_stream = false;
+    HostScene scene;
+    FlatBvh bvh;
+    bool has_scene = false;
+    std::string err;
+    double upload_ms = 0, bvh_ms = 0;
+    // last render (for gort_read_radiance)
+    int last_w = 0, last_h = 0, last_samples = 0, last_rank = 0, last_count = 1;
+    std::vector<int> last_local_tiles;  // per device
+};
+
+namespace {
+
+int fail(gort_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                                       \
+    do {                                                                                                          \
+        cudaError_t e__ = (expr);                                                                                 \
+        if (e__ != cudaSuccess)                                                                                   \
+            return fail(ctx, GORT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorName(e__) + " (" + cudaGetErrorString(e__) + ")"); \
+    } while (0)
+
+cudaStream_t stream_of(gort_ctx* ctx, int i) {
+    if (i == 0 && ctx->use_user_stream) return ctx->user_stream;
+    return ctx->devs[i].own_stream;
+}
+
+template <typename T>
+int ensure(gort_ctx* ctx, T*& ptr, size_t& have, size_t want_bytes) {
+    if (have >= want_bytes && ptr) return GORT_OK;
+    if (ptr) CUDA_TRY(ctx, cudaFree(ptr));
+    ptr = nullptr;
+    have = 0;
+    CUDA_TRY(ctx, cudaMalloc(&ptr, std::max<size_t>(want_bytes, 16)));
+    have = want_bytes;
+    return GORT_OK;
+}
+
+void free_scene(DeviceState& d) {
+    cudaSetDevice(d.dev);
+    cudaFree(d.d_nodes); cudaFree(d.d_spheres); cudaFree(d.d_meta); cudaFree(d.d_tris); cudaFree(d.d_mats); cudaFree(d.d_lights);
+    d.d_nodes = d.d_spheres = d.d_tris = d.d_mats = d.d_lights = nullptr;
+    d.d_meta = nullptr;
+}
+
+float as_float(int32_t i) {
+    float f;
+    memcpy(&f, &i, 4);
+    return f;
+}
+
+// Per-material constants the kernel needs, with every threshold ladder of the reference resolved
+// in float64 on the host: ambient/diffuse/specular ladders (renderer.go:236-243,262-273,282-287),
+// reflection/direct weights (renderer.go:193-223), Fresnel parameters (material.go:88,103,117;
+// material.go:180; advanced_materials.go:137,147).
+void pack_material(const HostMaterial& m, F4 out[4]) {
+    const bool metal_like = (m.type == GORT_MAT_METAL || m.type == GORT_MAT_SHINY || m.type == GORT_MAT_PERFECTMIRROR);
+    const double metallic = metal_like ? (m.type == GORT_MAT_PERFECTMIRROR ? 1.0 : m.metallic) : 0.0;  // GetMetallic
+    double color[3] = {m.color[0], m.color[1], m.color[2]};
+    if (m.type == GORT_MAT_DIELECTRIC) color[0] = color[1] = color[2] = 1.0;  // GetAlbedo / attenuation material.go:236,266
+    double ambient = 0.1;
+    if (metallic > 0.9) ambient = 0.05;
+    else if (metallic > 0.7) ambient = 0.07;
+    else if (metallic > 0.5) ambient = 0.08;
+    double kd = 0.25;
+    if (metallic > 0.95) kd = 0.05;
+    else if (metallic > 0.9) kd = 0.08;
+    else if (metallic > 0.8) kd = 0.12;
+    else if (metallic > 0.7) kd = 0.15;
+    else if (metallic > 0.5) kd = 0.2;
+    double wr = 1.0, wd = 1.0;
+    if (metallic > 0.95) { wr = 0.85; wd = 0.15; }
+    else if (metallic > 0.9) { wr = 0.8; wd = 0.2; }
+    else if (metallic > 0.8) { wr = 0.75; wd = 0.25; }
+    else if (metallic > 0.7) { wr = 0.7; wd = 0.3; }
+    else if (metallic > 0.5) { wr = 0.6; wd = 0.4; }
+    else if (metallic > 0.2) { wr = 0.4; wd = 0.6; }
+    double spec_power = 0.0;  // 0 => no specular term (metallic <= 0.5)
+    if (metallic > 0.5) {
+        spec_power = 32.0;
+        if (metallic > 0.9) spec_power = 64.0;
+        else if (metallic > 0.8) spec_power = 48.0;
+    }
+    const double ior = m.ior;
+    const double f0 = std::pow((ior - 1.0) / (ior + 1.0), 2.0);
+    double fs = 0.0, mf = -1.0;
+    if (m.type == GORT_MAT_METAL) {
+        fs = 0.6 + m.metallic * 0.4;
+        if (m.metallic > 0.8) mf = 0.4 + m.metallic * 0.5;
+    } else if (m.type == GORT_MAT_SHINY) {
+        fs = 0.4 + m.specular * 0.4;
+    } else if (m.type == GORT_MAT_PERFECTMIRROR) {
+        fs = 0.9;
+    }
+    out[0] = F4{as_float(m.type), (float)color[0], (float)color[1], (float)color[2]};
+    out[1] = F4{(float)m.roughness, (float)metallic, (float)m.specular, (float)ior};
+    out[2] = F4{(float)ambient, (float)kd, (float)wr, (float)wd};
+    out[3] = F4{(float)spec_power, (float)f0, (float)fs, (float)mf};
+}
+
+int upload_scene(gort_ctx* ctx) {
+    const double t0 = now_ms();
+    build_bvh(ctx->scene, ctx->bvh);
+    ctx->bvh_ms = ctx->bvh.build_ms;
+    const HostScene& hs = ctx->scene;
+    std::vector<F4> mats(hs.mats.size() * 4);
+    for (size_t i = 0; i < hs.mats.size(); i++) pack_material(hs.mats[i], &mats[4 * i]);
+    std::vector<F4> lights(hs.lights.size() * 2);
+    for (size_t i = 0; i < hs.lights.size(); i++) {
+        const HostLight& l = hs.lights[i];
+        lights[2 * i] = F4{(float)l.pos[0], (float)l.pos[1], (float)l.pos[2], (float)l.intensity};
+        lights[2 * i + 1] = F4{(float)l.color[0], (float)l.color[1], (float)l.color[2], 0.f};
+    }
+    const FlatBvh& b = ctx->bvh;
+    for (size_t i = 0; i < ctx->devs.size(); i++) {
+        DeviceState& d = ctx->devs[i];
+        CUDA_TRY(ctx, cudaSetDevice(d.dev));
+        free_scene(d);
+        cudaStream_t st = stream_of(ctx, (int)i);
+        auto up = [&](auto*& dst, const void* src, size_t bytes) -> cudaError_t {
+            cudaError_t e = cudaMalloc(&dst, std::max<size_t>(bytes, 16));
+            if (e != cudaSuccess) return e;
+            if (bytes) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+            return e;
+        };
+        CUDA_TRY(ctx, up(d.d_nodes, b.nodes.data(), b.nodes.size() * sizeof(F4)));
+        CUDA_TRY(ctx, up(d.d_spheres, b.spheres.data(), b.spheres.size() * sizeof(F4)));
+        CUDA_TRY(ctx, up(d.d_meta, b.sphere_meta.data(), b.sphere_meta.size() * sizeof(I2)));
+        CUDA_TRY(ctx, up(d.d_tris, b.tris.data(), b.tris.size() * sizeof(F4)));
+        CUDA_TRY(ctx, up(d.d_mats, mats.data(), mats.size() * sizeof(F4)));
+        CUDA_TRY(ctx, up(d.d_lights, lights.data(), lights.size() * sizeof(F4)));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));  // host vectors go out of scope: the copies must be done
+    }
+    ctx->has_scene = true;
+    ctx->upload_ms = now_ms() - t0 - ctx->bvh_ms;
+    return GORT_OK;
+}
+
+DevCamera make_camera(const HostScene& s, int mode) {
+    DevCamera c;
+    c.ox = (float)s.cam_pos[0]; c.oy = (float)s.cam_pos[1]; c.oz = (float)s.cam_pos[2];
+    if (mode == GORT_CAMERA_LOOKAT) {
+        // extension: classic look-at pinhole (vertical fov in degrees), upright image
+        const double kPi = 3.14159265358979323846;
+        const double hh = std::tan(s.cam_fov * kPi / 180.0 / 2.0);
+        const double vh = 2.0 * hh, vw = vh * s.cam_aspect;
+        auto norm = [](double* v) {
+            double l = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+            if (l == 0) { v[0] = v[1] = v[2] = 0; return; }
+            v[0] /= l; v[1] /= l; v[2] /= l;
+        };
+        double w[3] = {s.cam_pos[0] - s.cam_look_at[0], s.cam_pos[1] - s.cam_look_at[1], s.cam_pos[2] - s.cam_look_at[2]};
+        norm(w);
+        double u[3] = {s.cam_up[1] * w[2] - s.cam_up[2] * w[1], s.cam_up[2] * w[0] - s.cam_up[0] * w[2], s.cam_up[0] * w[1] - s.cam_up[1] * w[0]};
+        norm(u);
+        double v[3] = {w[1] * u[2] - w[2] * u[1], w[2] * u[0] - w[0] * u[2], w[0] * u[1] - w[1] * u[0]};
+        double H[3], V[3], ll[3];
+        for (int a = 0; a < 3; a++) {
+            H[a] = u[a] * vw;
+            V[a] = v[a] * vh;
+            ll[a] = -H[a] / 2 - V[a] / 2 - w[a];
+        }
+        // dir = ll + u*H + (1-v)*V  (row 0 = top of the view)
+        c.llx = (float)(ll[0] + V[0]); c.lly = (float)(ll[1] + V[1]); c.llz = (float)(ll[2] + V[2]);
+        c.hx = (float)H[0]; c.hy = (float)H[1]; c.hz = (float)H[2];
+        c.vx = (float)-V[0]; c.vy = (float)-V[1]; c.vz = (float)-V[2];
+        return c;
+    }
+    // getRay (renderer.go:377-390): viewport height 2, width 2*aspect, focal length 1, looking down -Z
+    const double vw = 2.0 * s.cam_aspect;
+    c.llx = (float)(-vw / 2.0); c.lly = -1.0f; c.llz = -1.0f;
+    c.hx = (float)vw; c.hy = 0.f; c.hz = 0.f;
+    c.vx = 0.f; c.vy = 2.0f; c.vz = 0.f;
+    return c;
+}
+
+int local_tile_count(int n_tiles, int rank, int count) { return rank < n_tiles ? (n_tiles - rank + count - 1) / count : 0; }
+
+int validate(gort_ctx* ctx, const gort_render_params* p) {
+    if (!ctx) return GORT_ERR_INVALID;
+    if (!p) return fail(ctx, GORT_ERR_INVALID, "params is NULL");
+    if (p->abi_version != GORT_ABI_VERSION) return fail(ctx, GORT_ERR_INVALID, "gort_render_params.abi_version mismatch");
+    if (!ctx->has_scene) return fail(ctx, GORT_ERR_NO_SCENE, "no scene uploaded");
+    if (p->width <= 0 || p->height <= 0) return fail(ctx, GORT_ERR_INVALID, "width/height must be positive");
+    if ((int64_t)p->width * p->height > (int64_t)1 << 28) return fail(ctx, GORT_ERR_INVALID, "image too large");
+    if (p->samples <= 0 || p->samples > 65535) return fail(ctx, GORT_ERR_INVALID, "samples must be in 1..65535");
+    if (p->max_depth < 0 || p->max_depth > (1 << 20)) return fail(ctx, GORT_ERR_INVALID, "max_depth out of range");
+    const int sc = p->shard_count <= 0 ? 1 : p->shard_count;
+    if (p->shard_rank < 0 || p->shard_rank >= sc) return fail(ctx, GORT_ERR_INVALID, "shard_rank out of range");
+    if (p->camera_mode != GORT_CAMERA_REFERENCE && p->camera_mode != GORT_CAMERA_LOOKAT) return fail(ctx, GORT_ERR_INVALID, "camera_mode");
+    return GORT_OK;
+}
+
+// Enqueue one device's share of the frame: zero accumulators, trace, resolve into d.d_out.
+// eff_rank/eff_count: the tiles this device owns.  slab_mode: tile-major slab vs row-major frame.
+// out_override: write the resolved pixels there instead of d.d_out (device pointer on this device).
+int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_rank, int eff_count, int slab_mode, uint8_t* out_override,
+                   size_t slab_bytes) {
+    DeviceState& d = ctx->devs[di];
+    CUDA_TRY(ctx, cudaSetDevice(d.dev));
+    cudaStream_t st = stream_of(ctx, di);
+    const int tiles_x = (p->width + kTile - 1) / kTile, tiles_y = (p->height + kTile - 1) / kTile;
+    const int n_tiles = tiles_x * tiles_y;
+    const int n_local = local_tile_count(n_tiles, eff_rank, eff_count);
+    ctx->last_local_tiles[di] = n_local;
+
+    size_t accum_have = d.accum_tiles * kTilePixels * 3 * sizeof(unsigned long long);
+    const size_t accum_want = (size_t)n_local * kTilePixels * 3 * sizeof(unsigned long long);
+    if (int rc = ensure(ctx, d.d_accum, accum_have, accum_want)) return rc;
+    d.accum_tiles = accum_have / (kTilePixels * 3 * sizeof(unsigned long long));
+
+    uint8_t* out = out_override;
+    if (!out) {
+        const size_t want = slab_mode ? slab_bytes : (size_t)p->width * p->height * 4;
+        if (int rc = ensure(ctx, d.d_out, d.out_bytes, want)) return rc;
+        out = d.d_out;
+    }
+
+    CUDA_TRY(ctx, cudaEventRecord(d.ev[0], st));
+    if (accum_want) CUDA_TRY(ctx, cudaMemsetAsync(d.d_accum, 0, accum_want, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(d.d_counter, 0, sizeof(unsigned int), st));
+    if (p->collect_stats) CUDA_TRY(ctx, cudaMemsetAsync(d.d_stats, 0, kStatCount * sizeof(unsigned long long), st));
+    if (slab_mode && slab_bytes > (size_t)n_local * kTilePixels * 4)
+        CUDA_TRY(ctx, cudaMemsetAsync(out + (size_t)n_local * kTilePixels * 4, 0, slab_bytes - (size_t)n_local * kTilePixels * 4, st));
+
+    TraceParams tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.scene.nodes = d.d_nodes; tp.scene.spheres = d.d_spheres; tp.scene.sphere_meta = d.d_meta; tp.scene.tris = d.d_tris;
+    tp.scene.mats = d.d_mats; tp.scene.lights = d.d_lights;
+    tp.scene.n_nodes = ctx->bvh.n_nodes; tp.scene.n_lights = (int)ctx->scene.lights.size();
+    tp.cam = make_camera(ctx->scene, p->camera_mode);
+    tp.width = p->width; tp.height = p->height; tp.samples = p->samples; tp.max_depth = p->max_depth;
+    tp.jitter = p->anti_aliasing ? 1 : 0; tp.recursive = p->recursive_reflections ? 1 : 0; tp.soft = p->soft_shadows ? 1 : 0;
+    tp.tiles_x = tiles_x; tp.tiles_y = tiles_y;
+    tp.shard_rank = eff_rank; tp.shard_count = eff_count; tp.n_local_tiles = n_local;
+    // work units: (sample batch, tile, 8x4 block); aim for >= 8 units per resident warp
+    const long long blocks = (long long)n_local * 32;
+    const long long target_units = 8LL * d.sm_count * 2 * 8;
+    const long long min_batches = blocks > 0 ? (target_units + blocks - 1) / blocks : 1;
+    int spu = (int)std::max<long long>(1, std::min<long long>(16, p->samples / std::max<long long>(1, min_batches)));
+    tp.samples_per_unit = spu;
+    tp.n_batches = (p->samples + spu - 1) / spu;
+    tp.n_units = (uint32_t)(blocks * tp.n_batches);
+    tp.accum = d.d_accum; tp.work_counter = d.d_counter; tp.stats = p->collect_stats ? d.d_stats : nullptr;
+    const uint32_t k0 = (uint32_t)p->seed, k1 = (uint32_t)(p->seed >> 32);
+    for (int r = 0; r < 10; r++) {
+        tp.rk[2 * r] = k0 + (uint32_t)r * 0x9E3779B9u;
+        tp.rk[2 * r + 1] = k1 + (uint32_t)r * 0xBB67AE85u;
+    }
+    tp.fog_enabled = ctx->scene.fog_enabled;
+    tp.fog_density = (float)ctx->scene.fog_density;
+    tp.fog_r = (float)ctx->scene.fog_color[0]; tp.fog_g = (float)ctx->scene.fog_color[1]; tp.fog_b = (float)ctx->scene.fog_color[2];
+    CUDA_TRY(ctx, launch_trace(tp, p->collect_stats != 0, d.sm_count, st));
+    CUDA_TRY(ctx, cudaEventRecord(d.ev[1], st));
+
+    ResolveParams rp;
+    rp.accum = d.d_accum; rp.n_local_tiles = n_local; rp.shard_rank = eff_rank; rp.shard_count = eff_count;
+    rp.tiles_x = tiles_x; rp.width = p->width; rp.height = p->height; rp.samples = p->samples;
+    rp.out = out; rp.slab_mode = slab_mode;
+    CUDA_TRY(ctx, launch_resolve(rp, st));
+    CUDA_TRY(ctx, cudaEventRecord(d.ev[2], st));
+    return GORT_OK;
+}
+
+int collect_stats(gort_ctx* ctx, const gort_render_params* p, gort_stats* s, double t_start_ms, int n_devs_used) {
+    if (!s) return GORT_OK;
+    memset(s, 0, sizeof(*s));
+    s->n_devices = n_devs_used;
+    s->upload_ms = ctx->upload_ms;
+    s->bvh_build_ms = ctx->bvh_ms;
+    s->bvh_nodes = (uint64_t)ctx->bvh.n_nodes;
+    s->bvh_bytes = ctx->bvh.nodes.size() * sizeof(F4) + ctx->bvh.spheres.size() * sizeof(F4) + ctx->bvh.sphere_meta.size() * sizeof(I2) +
+                   ctx->bvh.tris.size() * sizeof(F4);
+    unsigned long long tot[kStatCount] = {0};
+    int64_t pixels = 0;
+    const int tiles_x = (p->width + kTile - 1) / kTile;
+    for (int i = 0; i < n_devs_used; i++) {
+        DeviceState& d = ctx->devs[i];
+        CUDA_TRY(ctx, cudaSetDevice(d.dev));
+        CUDA_TRY(ctx, cudaEventSynchronize(d.ev[2]));
+        float a = 0, b = 0;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&a, d.ev[0], d.ev[1]));
+        CUDA_TRY(ctx, cudaEventElapsedTime(&b, d.ev[1], d.ev[2]));
+        s->device_ms[i] = a + b;
+        if (i == 0) { s->trace_ms = a; s->resolve_ms = b; }
+        s->kernel_ms = std::max(s->kernel_ms, (double)(a + b));
+        s->n_tiles += ctx->last_local_tiles[i];
+        if (p->collect_stats) {
+            unsigned long long h[kStatCount];
+            CUDA_TRY(ctx, cudaMemcpy(h, d.d_stats, sizeof(h), cudaMemcpyDeviceToHost));
+            for (int k = 0; k < kStatCount; k++) tot[k] += h[k];
+        }
+    }
+    // pixels actually covered by the rendered tiles
+    {
+        const int eff_count = ctx->last_count * n_devs_used;
+        const int tiles_y = (p->height + kTile - 1) / kTile;
+        for (int i = 0; i < n_devs_used; i++) {
+            const int eff_rank = ctx->last_rank + i * ctx->last_count;
+            for (int t = eff_rank; t < tiles_x * tiles_y; t += eff_count) {
+                const int tx = t % tiles_x, ty = t / tiles_x;
+                pixels += (int64_t)std::min(kTile, p->width - tx * kTile) * std::min(kTile, p->height - ty * kTile);
+            }
+        }
+    }
+    s->primary_rays = (uint64_t)pixels * (uint64_t)p->samples;
+    if (p->collect_stats) {
+        s->closest_queries = tot[kStatClosest]; s->shadow_queries = tot[kStatShadow]; s->nodes_visited = tot[kStatNodes];
+        s->sphere_tests = tot[kStatSphereTests]; s->sphere_hits = tot[kStatSphereHits];
+        s->tri_tests = tot[kStatTriTests]; s->tri_hits = tot[kStatTriHits];
+        s->tri_rejects[0] = tot[kStatTriRejA]; s->tri_rejects[1] = tot[kStatTriRejU]; s->tri_rejects[2] = tot[kStatTriRejV]; s->tri_rejects[3] = tot[kStatTriRejT];
+        s->shaded_hits = tot[kStatShaded]; s->rng_blocks = tot[kStatRngBlocks]; s->light_evals = tot[kStatLightEvals];
+        s->soft_shadow_rays = tot[kStatSoftRays]; s->diffuse_evals = tot[kStatDiffuse]; s->specular_evals = tot[kStatSpec];
+        // SURVEY §8d operation costs (FMA = 2 flops): ray generation 12, AABB slab 24 (two per node),
+        // sphere 23 miss / 47 hit, triangle 20/30/46/52 staged rejects / 92 accept, 30 per (hit, light)
+        // set-up, 36 per soft-shadow direction, 50 per diffuse term, 45 per specular term, ~70 per
+        // scatter, 20 per pixel of tone-map.
+        s->algorithmic_flops = 12.0 * (double)s->primary_rays + 48.0 * (double)s->nodes_visited +
+                               23.0 * (double)(s->sphere_tests - s->sphere_hits) + 47.0 * (double)s->sphere_hits +
+                               20.0 * (double)s->tri_rejects[0] + 30.0 * (double)s->tri_rejects[1] + 46.0 * (double)s->tri_rejects[2] +
+                               52.0 * (double)s->tri_rejects[3] + 92.0 * (double)s->tri_hits + 30.0 * (double)s->light_evals +
+                               36.0 * (double)s->soft_shadow_rays + 50.0 * (double)s->diffuse_evals + 45.0 * (double)s->specular_evals +
+                               70.0 * (double)s->shaded_hits + 20.0 * (double)pixels;
+    }
+    s->total_ms = now_ms() - t_start_ms;
+    return GORT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gort_abi_version(void) { return (int)GORT_ABI_VERSION; }
+
+int gort_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? 0 : GORT_ERR_CUDA;
+    }
+    return n;
+}
+
+int gort_create(const int* device_ids, int n_devices, gort_ctx** out) {
+    if (!out) return fail(nullptr, GORT_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (n_devices <= 0 || n_devices > GORT_MAX_DEVICES) return fail(nullptr, GORT_ERR_INVALID, "n_devices must be in 1..8");
+    const int avail = gort_device_count();
+    if (avail <= 0) return fail(nullptr, GORT_ERR_NO_DEVICE, "no CUDA device available (libgort has no CPU fallback): " + g_create_error);
+    gort_ctx* ctx = new gort_ctx();
+    ctx->devs.resize(n_devices);
+    ctx->last_local_tiles.assign(n_devices, 0);
+    auto bail = [&](int code, const std::string& msg) {
+        g_create_error = msg;
+        gort_destroy(ctx);
+        return code;
+    };
+    for (int i = 0; i < n_devices; i++) {
+        DeviceState& d = ctx->devs[i];
+        d.dev = device_ids ? device_ids[i] : i;
+        if (d.dev < 0 || d.dev >= avail) return bail(GORT_ERR_INVALID, "device id out of range");
+        cudaError_t e = cudaSetDevice(d.dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.dev);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.own_stream, cudaStreamNonBlocking);
+        for (int k = 0; k < 4 && e == cudaSuccess; k++) e = cudaEventCreate(&d.ev[k]);
+        if (e == cudaSuccess) e = cudaMalloc(&d.d_counter, 16);
+        if (e == cudaSuccess) e = cudaMalloc(&d.d_stats, kStatCount * sizeof(unsigned long long));
+        if (e != cudaSuccess) return bail(GORT_ERR_CUDA, std::string("device init: ") + cudaGetErrorString(e));
+    }
+    if (n_devices > 1) {  // direct NVLink copies for the slab gather
+        for (int i = 1; i < n_devices; i++) {
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, ctx->devs[0].dev, ctx->devs[i].dev);
+            if (can) {
+                cudaSetDevice(ctx->devs[0].dev);
+                cudaDeviceEnablePeerAccess(ctx->devs[i].dev, 0);
+                cudaSetDevice(ctx->devs[i].dev);
+                cudaDeviceEnablePeerAccess(ctx->devs[0].dev, 0);
+                cudaGetLastError();
+            }
+        }
+    }
+    *out = ctx;
+    return GORT_OK;
+}
+
+void gort_destroy(gort_ctx* ctx) {
+    if (!ctx) return;
+    for (DeviceState& d : ctx->devs) {
+        if (d.dev < 0) continue;
+        cudaSetDevice(d.dev);
+        if (d.own_stream) cudaStreamSynchronize(d.own_stream);
+        free_scene(d);
+        cudaFree(d.d_accum); cudaFree(d.d_counter); cudaFree(d.d_stats); cudaFree(d.d_out); cudaFree(d.d_gather);
+        if (d.h_pinned) cudaFreeHost(d.h_pinned);
+        for (auto& e : d.ev)
+            if (e) cudaEventDestroy(e);
+        if (d.own_stream) cudaStreamDestroy(d.own_stream);
+    }
+    delete ctx;
+}
+
+const char* gort_last_error(const gort_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int gort_set_stream(gort_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return GORT_ERR_INVALID;
+    ctx->user_stream = (cudaStream_t)cuda_stream;
+    ctx->use_user_stream = cuda_stream != nullptr;
+    return GORT_OK;
+}
+
+int gort_scene_upload(gort_ctx* ctx, const gort_scene_desc* desc) {
+    if (!ctx) return GORT_ERR_INVALID;
+    if (!desc) return fail(ctx, GORT_ERR_INVALID, "desc is NULL");
+    HostScene hs;
+    std::string err = scene_from_desc(*desc, hs);
+    if (!err.empty()) return fail(ctx, GORT_ERR_INVALID, err);
+    ctx->scene = std::move(hs);
+    return upload_scene(ctx);
+}
+
+int gort_scene_load_json(gort_ctx* ctx, const char* json_text, size_t json_len, uint32_t options) {
+    if (!ctx) return GORT_ERR_INVALID;
+    if (!json_text) return fail(ctx, GORT_ERR_INVALID, "json_text is NULL");
+    HostScene hs;
+    std::string err = scene_from_json(json_text, json_len, options, hs);
+    if (!err.empty()) return fail(ctx, GORT_ERR_PARSE, err);
+    ctx->scene = std::move(hs);
+    return upload_scene(ctx);
+}
+
+int gort_scene_load_file(gort_ctx* ctx, const char* path, uint32_t options) {
+    if (!ctx) return GORT_ERR_INVALID;
+    if (!path) return fail(ctx, GORT_ERR_INVALID, "path is NULL");
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return fail(ctx, GORT_ERR_IO, std::string("error reading file: ") + path);  // scene.go:46-49
+    std::stringstream ss;
+    ss << f.rdbuf();
+    const std::string text = ss.str();
+    return gort_scene_load_json(ctx, text.data(), text.size(), options);
+}
+
+int gort_scene_counts(const gort_ctx* ctx, int32_t* n_spheres, int32_t* n_triangles, int32_t* n_materials, int32_t* n_lights,
+                      int32_t* n_hittables) {
+    if (!ctx || !ctx->has_scene) return GORT_ERR_NO_SCENE;
+    if (n_spheres) *n_spheres = (int32_t)ctx->scene.spheres.size();
+    if (n_triangles) *n_triangles = (int32_t)ctx->scene.tris.size();
+    if (n_materials) *n_materials = (int32_t)ctx->scene.mats.size();
+    if (n_lights) *n_lights = (int32_t)ctx->scene.lights.size();
+    if (n_hittables) *n_hittables = ctx->scene.n_hittables;
+    return GORT_OK;
+}
+
+int gort_scene_get_triangle(const gort_ctx* ctx, int32_t i, double* v9, int32_t* material) {
+    if (!ctx || !ctx->has_scene) return GORT_ERR_NO_SCENE;
+    if (i < 0 || i >= (int32_t)ctx->scene.tris.size() || !v9) return GORT_ERR_INVALID;
+    memcpy(v9, ctx->scene.tris[i].v, 9 * sizeof(double));
+    if (material) *material = ctx->scene.tris[i].mat;
+    return GORT_OK;
+}
+
+int gort_scene_get_material(const gort_ctx* ctx, int32_t i, int32_t* type, double* out7) {
+    if (!ctx || !ctx->has_scene) return GORT_ERR_NO_SCENE;
+    if (i < 0 || i >= (int32_t)ctx->scene.mats.size() || !out7) return GORT_ERR_INVALID;
+    const HostMaterial& m = ctx->scene.mats[i];
+    if (type) *type = m.type;
+    out7[0] = m.color[0]; out7[1] = m.color[1]; out7[2] = m.color[2];
+    out7[3] = m.roughness; out7[4] = m.metallic; out7[5] = m.specular; out7[6] = m.ior;
+    return GORT_OK;
+}
+
+size_t gort_shard_slab_bytes(int32_t width, int32_t height, int32_t shard_count) {
+    if (width <= 0 || height <= 0) return 0;
+    if (shard_count <= 0) shard_count = 1;
+    const int64_t n_tiles = (int64_t)((width + kTile - 1) / kTile) * ((height + kTile - 1) / kTile);
+    return (size_t)((n_tiles + shard_count - 1) / shard_count) * kTilePixels * 4;
+}
+
+int gort_render_shard_device(gort_ctx* ctx, const gort_render_params* p, void* d_slab, size_t slab_bytes, gort_stats* stats_out) {
+    const double t0 = now_ms();
+    if (int rc = validate(ctx, p)) return rc;
+    const int sc = p->shard_count <= 0 ? 1 : p->shard_count;
+    if (!d_slab || slab_bytes != gort_shard_slab_bytes(p->width, p->height, sc)) return fail(ctx, GORT_ERR_INVALID, "slab pointer/size mismatch");
+    ctx->last_w = p->width; ctx->last_h = p->height; ctx->last_samples = p->samples; ctx->last_rank = p->shard_rank; ctx->last_count = sc;
+    if (int rc = enqueue_device(ctx, 0, p, p->shard_rank, sc, 1, (uint8_t*)d_slab, slab_bytes)) return rc;
+    if (stats_out) return collect_stats(ctx, p, stats_out, t0, 1);
+    return GORT_OK;
+}
+
+int gort_unswizzle_device(gort_ctx* ctx, const void* d_slabs, int32_t shard_count, int32_t width, int32_t height, void* d_rgba,
+                          size_t rgba_bytes) {
+    if (!ctx) return GORT_ERR_INVALID;
+    if (!d_slabs || !d_rgba || shard_count <= 0 || width <= 0 || height <= 0 || rgba_bytes != (size_t)width * height * 4)
+        return fail(ctx, GORT_ERR_INVALID, "gort_unswizzle_device: bad arguments");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->devs[0].dev));
+    CUDA_TRY(ctx, launch_unswizzle((const uint8_t*)d_slabs, shard_count, width, height, (uint8_t*)d_rgba, stream_of(ctx, 0)));
+    return GORT_OK;
+}
+
+// Frame into device memory of the lead device (row-major).  n_devices > 1: every device renders its
+// interleaved tiles into a slab, slabs are gathered to the lead device over NVLink and unswizzled.
+static int render_frame_device(gort_ctx* ctx, const gort_render_params* p, uint8_t* d_rgba, double t0, gort_stats* stats_out, bool sync) {
+    const int nd = (int)ctx->devs.size();
+    const int sc = p->shard_count <= 0 ? 1 : p->shard_count;
+    ctx->last_w = p->width; ctx->last_h = p->height; ctx->last_samples = p->samples; ctx->last_rank = p->shard_rank; ctx->last_count = sc;
+    if (nd == 1) {
+        if (int rc = enqueue_device(ctx, 0, p, p->shard_rank, sc, 0, d_rgba, 0)) return rc;
+    } else {
+        if (sc != 1) return fail(ctx, GORT_ERR_INVALID, "a multi-device ctx renders whole frames (shard_count must be 1)");
+        const size_t slab = gort_shard_slab_bytes(p->width, p->height, nd);
+        DeviceState& lead = ctx->devs[0];
+        CUDA_TRY(ctx, cudaSetDevice(lead.dev));
+        if (int rc = ensure(ctx, lead.d_gather, lead.gather_bytes, slab * nd)) return rc;
+        for (int i = 0; i < nd; i++) {
+            uint8_t* dst = (i == 0) ? lead.d_gather : nullptr;  // lead device resolves straight into the gather buffer
+            if (int rc = enqueue_device(ctx, i, p, i, nd, 1, dst, slab)) return rc;
+        }
+        CUDA_TRY(ctx, cudaSetDevice(lead.dev));
+        cudaStream_t st0 = stream_of(ctx, 0);
+        for (int i = 1; i < nd; i++) {
+            CUDA_TRY(ctx, cudaStreamWaitEvent(st0, ctx->devs[i].ev[2], 0));
+            CUDA_TRY(ctx, cudaMemcpyPeerAsync(lead.d_gather + slab * i, lead.dev, ctx->devs[i].d_out, ctx->devs[i].dev, slab, st0));
+        }
+        CUDA_TRY(ctx, launch_unswizzle(lead.d_gather, nd, p->width, p->height, d_rgba, st0));
+        CUDA_TRY(ctx, cudaEventRecord(lead.ev[3], st0));
+    }
+    if (stats_out || sync) {
+        CUDA_TRY(ctx, cudaSetDevice(ctx->devs[0].dev));
+        CUDA_TRY(ctx, cudaStreamSynchronize(stream_of(ctx, 0)));
+    }
+    if (stats_out) {
+        if (int rc = collect_stats(ctx, p, stats_out, t0, nd)) return rc;
+        if (nd > 1) {
+            float g = 0;
+            CUDA_TRY(ctx, cudaSetDevice(ctx->devs[0].dev));
+            CUDA_TRY(ctx, cudaEventElapsedTime(&g, ctx->devs[0].ev[0], ctx->devs[0].ev[3]));
+            stats_out->kernel_ms = std::max(stats_out->kernel_ms, (double)g);
+            stats_out->resolve_ms = g - stats_out->trace_ms;
+        }
+    }
+    return GORT_OK;
+}
+
+int gort_render_device(gort_ctx* ctx, const gort_render_params* p, void* d_rgba, size_t rgba_bytes, gort_stats* stats_out) {
+    const double t0 = now_ms();
+    if (int rc = validate(ctx, p)) return rc;
+    if (!d_rgba || rgba_bytes != (size_t)p->width * p->height * 4) return fail(ctx, GORT_ERR_INVALID, "d_rgba pointer/size mismatch");
+    return render_frame_device(ctx, p, (uint8_t*)d_rgba, t0, stats_out, false);
+}
+
+int gort_render(gort_ctx* ctx, const gort_render_params* p, uint8_t* rgba_out, size_t rgba_bytes, gort_stats* stats_out) {
+    const double t0 = now_ms();
+    if (int rc = validate(ctx, p)) return rc;
+    const size_t frame_bytes = (size_t)p->width * p->height * 4;
+    if (!rgba_out || rgba_bytes != frame_bytes) return fail(ctx, GORT_ERR_INVALID, "rgba_out pointer/size mismatch (want width*height*4)");
+    DeviceState& lead = ctx->devs[0];
+    CUDA_TRY(ctx, cudaSetDevice(lead.dev));
+    const int sc = p->shard_count <= 0 ? 1 : p->shard_count;
+    cudaStream_t st0 = stream_of(ctx, 0);
+    if (sc == 1) {
+        if (lead.pinned_bytes < frame_bytes) {
+            if (lead.h_pinned) CUDA_TRY(ctx, cudaFreeHost(lead.h_pinned));
+            lead.h_pinned = nullptr; lead.pinned_bytes = 0;
+            CUDA_TRY(ctx, cudaMallocHost(&lead.h_pinned, frame_bytes));
+            lead.pinned_bytes = frame_bytes;
+        }
+        if (ctx->devs.size() == 1) {
+            if (int rc = render_frame_device(ctx, p, nullptr, t0, nullptr, false)) return rc;  // into lead.d_out
+        } else {
+            if (int rc = ensure(ctx, lead.d_out, lead.out_bytes, std::max(frame_bytes, gort_shard_slab_bytes(p->width, p->height, (int)ctx->devs.size())))) return rc;
+            // lead.d_out doubles as the frame; its own slab goes straight into d_gather
+            if (int rc = render_frame_device(ctx, p, lead.d_out, t0, nullptr, false)) return rc;
+        }
+        CUDA_TRY(ctx, cudaSetDevice(lead.dev));
+        CUDA_TRY(ctx, cudaMemcpyAsync(lead.h_pinned, lead.d_out, frame_bytes, cudaMemcpyDeviceToHost, st0));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st0));
+        memcpy(rgba_out, lead.h_pinned, frame_bytes);
+    } else {
+        // process-level shard with a host destination: render the slab, copy back, write own tiles only
+        if (ctx->devs.size() != 1) return fail(ctx, GORT_ERR_INVALID, "a multi-device ctx renders whole frames (shard_count must be 1)");
+        const size_t slab = gort_shard_slab_bytes(p->width, p->height, sc);
+        if (lead.pinned_bytes < slab) {
+            if (lead.h_pinned) CUDA_TRY(ctx, cudaFreeHost(lead.h_pinned));
+            lead.h_pinned = nullptr; lead.pinned_bytes = 0;
+            CUDA_TRY(ctx, cudaMallocHost(&lead.h_pinned, slab));
+            lead.pinned_bytes = slab;
+        }
+        ctx->last_w = p->width; ctx->last_h = p->height; ctx->last_samples = p->samples; ctx->last_rank = p->shard_rank; ctx->last_count = sc;
+        if (int rc = enqueue_device(ctx, 0, p, p->shard_rank, sc, 1, nullptr, slab)) return rc;
+        CUDA_TRY(ctx, cudaMemcpyAsync(lead.h_pinned, lead.d_out, slab, cudaMemcpyDeviceToHost, st0));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st0));
+        const int tiles_x = (p->width + kTile - 1) / kTile, tiles_y = (p->height + kTile - 1) / kTile;
+        int j = 0;
+        for (int t = p->shard_rank; t < tiles_x * tiles_y; t += sc, j++) {
+            const int tx = t % tiles_x, ty = t / tiles_x;
+            const int w = std::min(kTile, p->width - tx * kTile), h = std::min(kTile, p->height - ty * kTile);
+            for (int ly = 0; ly < h; ly++)
+                memcpy(rgba_out + ((size_t)(ty * kTile + ly) * p->width + tx * kTile) * 4, lead.h_pinned + ((size_t)j * kTilePixels + ly * kTile) * 4, (size_t)w * 4);
+        }
+    }
+    if (stats_out) {
+        if (int rc = collect_stats(ctx, p, stats_out, t0, (int)ctx->devs.size())) return rc;
+        if (ctx->devs.size() > 1) {
+            float g = 0;
+            CUDA_TRY(ctx, cudaSetDevice(lead.dev));
+            CUDA_TRY(ctx, cudaEventElapsedTime(&g, lead.ev[0], lead.ev[3]));
+            stats_out->kernel_ms = std::max(stats_out->kernel_ms, (double)g);
+            stats_out->resolve_ms = g - stats_out->trace_ms;
+        }
+        stats_out->total_ms = now_ms() - t0;
+    }
+    return GORT_OK;
+}
+
+int gort_read_radiance(gort_ctx* ctx, double* out, size_t bytes) {
+    if (!ctx) return GORT_ERR_INVALID;
+    if (ctx->last_w <= 0) return fail(ctx, GORT_ERR_INVALID, "no frame rendered yet");
+    const int W = ctx->last_w, H = ctx->last_h;
+    if (!out || bytes != (size_t)W * H * 3 * sizeof(double)) return fail(ctx, GORT_ERR_INVALID, "radiance buffer size mismatch");
+    const int nd = (int)ctx->devs.size();
+    const int tiles_x = (W + kTile - 1) / kTile;
+    const double inv = 1.0 / ((double)(1u << kAccumFracBits) * (double)ctx->last_samples);
+    for (int i = 0; i < nd; i++) {
+        DeviceState& d = ctx->devs[i];
+        const int n_local = ctx->last_local_tiles[i];
+        if (n_local == 0) continue;
+        CUDA_TRY(ctx, cudaSetDevice(d.dev));
+        CUDA_TRY(ctx, cudaStreamSynchronize(stream_of(ctx, i)));
+        std::vector<long long> h((size_t)n_local * kTilePixels * 3);
+        CUDA_TRY(ctx, cudaMemcpy(h.data(), d.d_accum, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        const int eff_count = ctx->last_count * nd, eff_rank = ctx->last_rank + i * ctx->last_count;
+        for (int lt = 0; lt < n_local; lt++) {
+            const int gt = eff_rank + lt * eff_count;
+            const int tx = gt % tiles_x, ty = gt / tiles_x;
+            for (int p = 0; p < kTilePixels; p++) {
+                const int x = tx * kTile + (p & (kTile - 1)), y = ty * kTile + p / kTile;
+                if (x >= W || y >= H) continue;
+                for (int c = 0; c < 3; c++) out[((size_t)y * W + x) * 3 + c] = (double)h[((size_t)lt * kTilePixels + p) * 3 + c] * inv;
+            }
+        }
+    }
+    return GORT_OK;
+}
+
+int gort_trace_rays(gort_ctx* ctx, int32_t n, const double* origins3, const double* directions3, double t_min, double t_max,
+                    int32_t any_hit, double* out_t, int32_t* out_order) {
+    if (!ctx) return GORT_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, GORT_ERR_NO_SCENE, "no scene uploaded");
+    if (n < 0 || (n > 0 && (!origins3 || !directions3 || !out_t || !out_order))) return fail(ctx, GORT_ERR_INVALID, "gort_trace_rays: bad arguments");
+    if (n == 0) return GORT_OK;
+    DeviceState& d = ctx->devs[0];
+    CUDA_TRY(ctx, cudaSetDevice(d.dev));
+    cudaStream_t st = stream_of(ctx, 0);
+    std::vector<float> ho(3 * (size_t)n), hd(3 * (size_t)n);
+    for (size_t i = 0; i < 3 * (size_t)n; i++) {
+        ho[i] = (float)origins3[i];
+        hd[i] = (float)directions3[i];
+    }
+    float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr;
+    int* d_ord = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&d_o, ho.size() * 4));
+    CUDA_TRY(ctx, cudaMalloc(&d_d, hd.size() * 4));
+    CUDA_TRY(ctx, cudaMalloc(&d_t, (size_t)n * 4));
+    CUDA_TRY(ctx, cudaMalloc(&d_ord, (size_t)n * 4));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_o, ho.data(), ho.size() * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_d, hd.data(), hd.size() * 4, cudaMemcpyHostToDevice, st));
+    SceneView sv;
+    sv.nodes = d.d_nodes; sv.spheres = d.d_spheres; sv.sphere_meta = d.d_meta; sv.tris = d.d_tris; sv.mats = d.d_mats; sv.lights = d.d_lights;
+    sv.n_nodes = ctx->bvh.n_nodes; sv.n_lights = (int)ctx->scene.lights.size();
+    const float tmax_f = std::isinf(t_max) ? INFINITY : (float)t_max;
+    CUDA_TRY(ctx, launch_trace_rays(sv, n, d_o, d_d, (float)t_min, tmax_f, any_hit, d_t, d_ord, st));
+    std::vector<float> ht(n);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ht.data(), d_t, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_order, d_ord, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    for (int i = 0; i < n; i++) out_t[i] = ht[i];
+    cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_ord);
+    return GORT_OK;
+}
+
+int gort_measure_fp32_peak(gort_ctx* ctx, double* tflops_out, double* ms_out) {
+    if (!ctx || !tflops_out) return GORT_ERR_INVALID;
+    DeviceState& d = ctx->devs[0];
+    CUDA_TRY(ctx, cudaSetDevice(d.dev));
+    cudaStream_t st = stream_of(ctx, 0);
+    float* sink = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&sink, 16));
+    const int blocks = d.sm_count * 8, threads = 256, iters = 8192;
+    CUDA_TRY(ctx, launch_ffma_peak(sink, 256, blocks, threads, st));  // warm-up
+    double best = 1e30;
+    for (int rep = 0; rep < 3; rep++) {
+        CUDA_TRY(ctx, cudaEventRecord(d.ev[0], st));
+        CUDA_TRY(ctx, launch_ffma_peak(sink, iters, blocks, threads, st));
+        CUDA_TRY(ctx, cudaEventRecord(d.ev[1], st));
+        CUDA_TRY(ctx, cudaEventSynchronize(d.ev[1]));
+        float ms = 0;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms, d.ev[0], d.ev[1]));
+        best = std::min(best, (double)ms);
+    }
+    cudaFree(sink);
+    const double flops = (double)blocks * threads * (double)iters * 64.0 * 2.0;
+    *tflops_out = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return GORT_OK;
+}
+
+}  // extern "C"

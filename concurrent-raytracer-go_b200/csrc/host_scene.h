@@ -1,0 +1,69 @@
+// host_scene.h — host-side scene model of libgort (float64, reference scan order) and the flat
+// device layout produced from it.  Mirrors what scene.GetHittables()/GetLights() hand to Render
+// (/root/reference internal/scene/scene.go:59-98) after createMaterial (:104-148) and createCube
+// (:150-190).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/gort.h"
+
+namespace gort {
+
+struct HostMaterial {
+    int32_t type = GORT_MAT_LAMBERTIAN;
+    double color[3] = {0, 0, 0};
+    double roughness = 0, metallic = 0, specular = 0, ior = 1.5;
+};
+
+struct HostSphere {
+    double c[3];
+    double r;
+    int32_t mat;
+    int32_t order;  // position in the reference's flattened linear scan
+};
+
+struct HostTriangle {
+    double v[3][3];
+    int32_t mat;
+    int32_t order;
+};
+
+struct HostLight {
+    double pos[3], color[3], intensity;
+};
+
+struct HostScene {
+    double cam_pos[3] = {0, 0, 0}, cam_look_at[3] = {0, 0, 0}, cam_up[3] = {0, 1, 0};
+    double cam_fov = 60, cam_aspect = 1;
+    std::vector<HostMaterial> mats;
+    std::vector<HostSphere> spheres;
+    std::vector<HostTriangle> tris;
+    std::vector<HostLight> lights;
+    int32_t n_hittables = 0;  // len(scene.GetHittables()): spheres + meshes
+    int32_t fog_enabled = 0;
+    double fog_density = 0, fog_color[3] = {0, 0, 0};
+
+    int32_t next_order() const { return (int32_t)(spheres.size() + tris.size()); }
+};
+
+// gort_scene_desc -> HostScene (validates indices and sizes). Returns "" or an error message.
+std::string scene_from_desc(const gort_scene_desc& d, HostScene& out);
+
+// Host mirror of scene.LoadFromFile + GetHittables for the reference's JSON schema
+// (scene.go:12-39): returns "" or an error message.  options: bit0 prisms, bit1 fog.
+std::string scene_from_json(const char* text, size_t len, uint32_t options, HostScene& out);
+
+// createMaterial's defaults and constructor clamps (scene.go:104-148; material.go:65-73,159-167;
+// advanced_materials.go:14-19,117-123).  `has_*` = key present in the JSON object.
+HostMaterial make_material(const std::string& type, bool has_color, const double color[3], bool has_rough, double rough,
+                           bool has_metal, double metal, bool has_spec, double spec, bool has_ior, double ior);
+
+// createCube (scene.go:150-190): 12 triangles appended in the reference's order.
+void add_cube(HostScene& s, const double pos[3], const double size[3], int32_t mat);
+// triangularPrism extension (README.md:227-240): 8 triangles.
+void add_prism(HostScene& s, const double verts[6][3], int32_t mat);
+void add_sphere(HostScene& s, const double pos[3], double radius, int32_t mat);
+
+}  // namespace gort

@@ -1,0 +1,90 @@
+// kernels.h — launch interface between the host context (capi.cu) and the sm_100a kernels (kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace gort {
+
+constexpr int kTile = 32;                 // createRenderTasks tileSize (renderer.go:401)
+constexpr int kTilePixels = kTile * kTile;
+constexpr int kAccumFracBits = 30;        // fixed-point radiance accumulators: value * 2^30 in int64
+constexpr float kSampleClamp = 65536.0f;  // |per-sample radiance| clamp before fixed-point conversion
+
+enum Stream : uint32_t { kStreamJitter = 0, kStreamScatter = 1, kStreamShadow = 2 };
+
+// counters collected by the STATS kernel variant (indices into TraceParams::stats)
+enum StatIndex {
+    kStatClosest = 0,      // closest-hit hitWorld queries
+    kStatShadow = 1,       // boolean hitWorld queries (hard + soft shadow rays)
+    kStatNodes = 2,        // BVH inner nodes visited (two slab tests each)
+    kStatSphereTests = 3,
+    kStatSphereHits = 4,   // sphere tests that produced an accepted root
+    kStatTriTests = 5,
+    kStatTriRejA = 6,      // rejected at |a| < 1e-6   (triangle.go:42-44)
+    kStatTriRejU = 7,      // rejected at the u test   (triangle.go:50-52)
+    kStatTriRejV = 8,      // rejected at the v test   (triangle.go:57-59)
+    kStatTriRejT = 9,      // rejected at the t range  (triangle.go:63-65)
+    kStatTriHits = 10,
+    kStatShaded = 11,      // calculateDirectLighting + Scatter evaluations
+    kStatRngBlocks = 12,   // Philox4x32-10 blocks
+    kStatLightEvals = 13,  // (hit, light) pairs that cast a hard shadow ray
+    kStatSoftRays = 14,    // soft shadow rays
+    kStatDiffuse = 15,     // (hit, light) pairs with shadowFactor > 0
+    kStatSpec = 16,        // ... that also evaluate the Blinn-Phong term
+    kStatCount = 20
+};
+
+struct DevCamera {
+    float ox, oy, oz;     // ray origin
+    float llx, lly, llz;  // lower-left corner minus origin
+    float hx, hy, hz;     // horizontal span (u = 0..1)
+    float vx, vy, vz;     // vertical span   (v = 0..1; v = (y + jitter)/H)
+};
+
+struct SceneView {
+    const float4* nodes;
+    const float4* spheres;
+    const int2* sphere_meta;
+    const float4* tris;
+    const float4* mats;    // 4 float4 per material (see capi.cu pack_material)
+    const float4* lights;  // 2 float4 per light: (pos.xyz, intensity) (color.rgb, 0)
+    int n_nodes;
+    int n_lights;
+};
+
+struct TraceParams {
+    SceneView scene;
+    DevCamera cam;
+    int width, height, samples, max_depth;
+    int jitter, recursive, soft;
+    int tiles_x, tiles_y;
+    int shard_rank, shard_count, n_local_tiles;
+    int samples_per_unit, n_batches;
+    uint32_t n_units;
+    unsigned long long* accum;   // [n_local_tiles][1024][3] int64 fixed point
+    unsigned int* work_counter;  // zeroed before launch
+    unsigned long long* stats;   // [kStatCount] or nullptr
+    uint32_t rk[20];             // Philox4x32-10 round keys: rk[2r] = key0 + r*W0, rk[2r+1] = key1 + r*W1
+    int fog_enabled;
+    float fog_density, fog_r, fog_g, fog_b;
+};
+
+struct ResolveParams {
+    const unsigned long long* accum;
+    int n_local_tiles, shard_rank, shard_count;
+    int tiles_x, width, height, samples;
+    uint8_t* out;      // row-major frame (slab_mode 0) or tile-major slab (slab_mode 1)
+    int slab_mode;
+};
+
+// All launchers enqueue on `stream` and return the launch error (no synchronisation).
+cudaError_t launch_trace(const TraceParams& p, bool stats, int sm_count, cudaStream_t stream);
+cudaError_t launch_resolve(const ResolveParams& p, cudaStream_t stream);
+cudaError_t launch_unswizzle(const uint8_t* slabs, int shard_count, int width, int height, uint8_t* rgba, cudaStream_t stream);
+cudaError_t launch_trace_rays(const SceneView& scene, int n, const float* origins, const float* dirs, float tmin, float tmax,
+                              int any_hit, float* out_t, int* out_order, cudaStream_t stream);
+cudaError_t launch_ffma_peak(float* sink, int iters, int blocks, int threads, cudaStream_t stream);
+int trace_kernel_regs(bool stats);
+
+}  // namespace gort

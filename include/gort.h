@@ -1,0 +1,230 @@
+/*
+ * gort.h — C ABI of libgort.so: the B200-native (sm_100a) replacement for the per-pixel render
+ * hot path of JoshElkind/concurrent-raytracer-go.
+ *
+ * The reference is pure Go and has no FFI of its own; the seam this ABI replaces is
+ * the body of
+ *     func (r *ParallelRenderer) Render(scene *scene.Scene, width, height int) *image.RGBA
+ *                                                    (internal/renderer/renderer.go:67-126)
+ * together with the state it reads: the ParallelRenderer fields/setters
+ * (renderer.go:20-29,54-65; settings.go:3-25), scene.GetHittables/GetLights/Camera
+ * (internal/scene/scene.go:12-39,59-98) and the collector's toneMap + ToRGB + img.Set
+ * (renderer.go:92-97,348-367; internal/math/vector.go:106-109).
+ * One cgo call per frame; the Go signatures stay, only Render's body changes.
+ *
+ * Conventions: plain pointers and sizes only; the caller owns every host pointer; the library
+ * copies what it needs before returning and retains no caller pointer (cgo pointer rules).
+ * Every function returns 0 (GORT_OK) or a negative gort_status; gort_last_error() gives the text.
+ * A gort_ctx is externally synchronised (one call at a time per ctx — the reference's Render is
+ * not re-entrant either: renderer.go:103-117).  There is no CPU fallback: without a usable CUDA
+ * device gort_create fails with GORT_ERR_NO_DEVICE.
+ */
+#ifndef GORT_H
+#define GORT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GORT_ABI_VERSION 1u
+#define GORT_MAX_DEVICES 8
+#define GORT_TILE 32 /* createRenderTasks tileSize, renderer.go:401 */
+
+typedef enum gort_status {
+    GORT_OK = 0,
+    GORT_ERR_INVALID = -1,   /* bad argument / ABI version / size */
+    GORT_ERR_CUDA = -2,      /* CUDA runtime error (text in gort_last_error) */
+    GORT_ERR_NO_DEVICE = -3, /* no CUDA device: there is no CPU fallback */
+    GORT_ERR_NO_SCENE = -4,  /* gort_render before gort_scene_upload */
+    GORT_ERR_NCCL = -5,
+    GORT_ERR_PARSE = -6, /* scene JSON malformed, or would panic in the reference (scene.go:105-146) */
+    GORT_ERR_IO = -7
+} gort_status;
+
+/* material.Material implementations reachable from createMaterial (scene.go:104-148) */
+typedef enum gort_material_type {
+    GORT_MAT_LAMBERTIAN = 0,    /* material.go:18-55 */
+    GORT_MAT_METAL = 1,         /* material.go:57-149 */
+    GORT_MAT_SHINY = 2,         /* material.go:151-225 */
+    GORT_MAT_PERFECTMIRROR = 3, /* advanced_materials.go:111-171 */
+    GORT_MAT_GLASS = 4,         /* advanced_materials.go:9-66 */
+    GORT_MAT_DIELECTRIC = 5,    /* material.go:227-280 */
+    GORT_MAT_DIFFUSELIGHT = 6   /* material.go:288-318 */
+} gort_material_type;
+
+typedef enum gort_camera_mode {
+    GORT_CAMERA_REFERENCE = 0, /* getRay, renderer.go:377-390: position+aspect only, looks down -Z, v=0 is row 0 */
+    GORT_CAMERA_LOOKAT = 1     /* extension: honours lookAt/up/fov (scene.go:18-24 fields), upright image */
+} gort_camera_mode;
+
+/*
+ * Flat scene description = what scene.GetHittables()/GetLights()/Camera hand to Render, after
+ * createMaterial's defaults (scene.go:104-148) and createCube's 12-triangle expansion
+ * (scene.go:150-190) have been applied by the host.  Struct-of-arrays, float64 like the reference.
+ * `*_order` is the primitive's position in the reference's linear scan (hitWorld renderer.go:337,
+ * Mesh.Hit scene.go:200): it decides exact-tie winners (last wins).
+ */
+typedef struct gort_scene_desc {
+    uint32_t abi_version; /* GORT_ABI_VERSION */
+    uint32_t reserved0;
+
+    /* scene.Camera (scene.go:18-24) */
+    double cam_position[3];
+    double cam_look_at[3];
+    double cam_up[3];
+    double cam_fov;
+    double cam_aspect;
+
+    /* materials, one per object (post-constructor values: roughness/metallic/specular already min(x,1)) */
+    int32_t n_materials;
+    int32_t reserved1;
+    const int32_t* mat_type;     /* gort_material_type [n] */
+    const double* mat_color;     /* Albedo / Color / Emit [3n] */
+    const double* mat_roughness; /* [n] */
+    const double* mat_metallic;  /* [n]  (GetMetallic: PerfectMirror -> 1 is applied by the library) */
+    const double* mat_specular;  /* [n] */
+    const double* mat_ior;       /* [n]  RefractionIndex (glass, dielectric); Metal/Shiny 1.5, PerfectMirror 2.0 */
+
+    /* geometry.Sphere (sphere.go:8-20) */
+    int32_t n_spheres;
+    int32_t reserved2;
+    const double* sphere_center;     /* [3n] */
+    const double* sphere_radius;     /* [n] */
+    const int32_t* sphere_material;  /* [n] */
+    const int32_t* sphere_order;     /* [n] */
+
+    /* geometry.Triangle (triangle.go:7-20); flat-shaded: Normals = face normal */
+    int32_t n_triangles;
+    int32_t reserved3;
+    const double* tri_vertices;   /* [9n] v0 v1 v2 */
+    const int32_t* tri_material;  /* [n] */
+    const int32_t* tri_order;     /* [n] */
+
+    /* scene.Light (scene.go:34-39); Type is never read by the renderer */
+    int32_t n_lights;
+    int32_t reserved4;
+    const double* light_position;  /* [3n] */
+    const double* light_color;     /* [3n] */
+    const double* light_intensity; /* [n] */
+
+    /* extension: exponential fog on the primary-hit distance; 0 = reference behaviour */
+    int32_t fog_enabled;
+    int32_t reserved5;
+    double fog_density;
+    double fog_color[3];
+} gort_scene_desc;
+
+/* ParallelRenderer fields (renderer.go:20-29) + the additive knobs of this implementation. */
+typedef struct gort_render_params {
+    uint32_t abi_version; /* GORT_ABI_VERSION */
+    int32_t width, height;
+    int32_t samples;               /* renderer.go:58 default 100 */
+    int32_t max_depth;             /* renderer.go:57 default 50 */
+    int32_t anti_aliasing;         /* 1 = jitter each sample (what the reference always does, renderer.go:155-156);
+                                      0 = declared extension: sub-pixel offset (0.5,0.5) */
+    int32_t recursive_reflections; /* renderer.go:60 */
+    int32_t soft_shadows;          /* renderer.go:61 */
+    int32_t camera_mode;           /* gort_camera_mode */
+    int32_t shard_rank;            /* multi-process sharding: this process renders tiles with    */
+    int32_t shard_count;           /*   tile_id % shard_count == shard_rank (0/1 = whole frame)  */
+    int32_t collect_stats;         /* 1 = also count ray segments / node visits / primitive tests (slower kernel variant) */
+    uint64_t seed;                 /* Philox key; the image is a pure function of (scene, params, seed) */
+} gort_render_params;
+
+typedef struct gort_stats {
+    double kernel_ms;    /* CUDA-event time of trace + resolve kernels, max over the ctx's devices */
+    double trace_ms;     /* the trace kernel alone (device 0) */
+    double resolve_ms;   /* tone-map/quantise/pack kernel (+ gather/unswizzle when n_devices > 1) */
+    double total_ms;     /* host wall clock of the whole call (launch + D2H where applicable) */
+    double upload_ms;    /* last gort_scene_upload: host flatten + H2D */
+    double bvh_build_ms; /* last gort_scene_upload: host BVH build */
+    double device_ms[GORT_MAX_DEVICES];
+    int32_t n_devices;
+    int32_t n_tiles;     /* tiles rendered by this call */
+    uint64_t primary_rays;  /* width*height*samples of the rendered tiles (the reference's "rays") */
+    uint64_t bvh_nodes, bvh_bytes;
+    /* filled when collect_stats = 1 (device-side counters of the same frame) */
+    uint64_t closest_queries; /* hitWorld calls with closest-hit semantics */
+    uint64_t shadow_queries;  /* hitWorld calls used as a boolean (hard + soft shadow rays) */
+    uint64_t nodes_visited;   /* BVH inner nodes fetched (2 slab tests each) */
+    uint64_t sphere_tests, sphere_hits;
+    uint64_t tri_tests, tri_hits;
+    uint64_t tri_rejects[4];  /* rejected at |a|<1e-6, u, v, t (triangle.go:42-65) */
+    uint64_t shaded_hits;     /* calculateDirectLighting + Scatter evaluations */
+    uint64_t rng_blocks;      /* Philox4x32-10 blocks generated */
+    uint64_t light_evals;     /* (hit, light) pairs that cast the hard shadow ray */
+    uint64_t soft_shadow_rays;
+    uint64_t diffuse_evals;   /* (hit, light) pairs with shadowFactor > 0 */
+    uint64_t specular_evals;  /* ... of which metallic > 0.5 (Blinn-Phong term) */
+    double algorithmic_flops; /* SURVEY §8d per-operation costs applied to the counters above */
+} gort_stats;
+
+typedef struct gort_ctx gort_ctx;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+int gort_abi_version(void);
+int gort_device_count(void); /* >= 0, or a negative gort_status */
+/* device_ids == NULL -> devices 0..n_devices-1.  n_devices > 1 = single-process multi-GPU
+ * (tiles interleaved over the devices, gathered to device_ids[0]). */
+int gort_create(const int* device_ids, int n_devices, gort_ctx** out);
+void gort_destroy(gort_ctx* ctx);
+const char* gort_last_error(const gort_ctx* ctx); /* ctx may be NULL: error of a failed gort_create */
+/* Launch on a caller-owned CUDA stream (cudaStream_t as void*) of device_ids[0]; NULL restores the
+ * ctx's own stream.  Lets a host framework time/order the work with its own events. */
+int gort_set_stream(gort_ctx* ctx, void* cuda_stream);
+
+/* ---- scene (replaces scene.GetHittables()/GetLights() feeding Render, renderer.go:72-74) -- */
+int gort_scene_upload(gort_ctx* ctx, const gort_scene_desc* desc);
+/* Host mirror of scene.LoadFromFile + GetHittables (scene.go:45-90,104-190) for hosts that are not
+ * the Go program: parses the reference's scene JSON, applies its defaults, expands cubes, uploads.
+ * options: bit0 = load "triangularPrism" objects (extension; reference skips them, scene.go:80-82)
+ *          bit1 = honour the "fog" block (extension; reference ignores it) */
+int gort_scene_load_json(gort_ctx* ctx, const char* json_text, size_t json_len, uint32_t options);
+int gort_scene_load_file(gort_ctx* ctx, const char* path, uint32_t options);
+/* Introspection of the uploaded scene (flattened, reference scan order). */
+int gort_scene_counts(const gort_ctx* ctx, int32_t* n_spheres, int32_t* n_triangles, int32_t* n_materials,
+                      int32_t* n_lights, int32_t* n_hittables);
+int gort_scene_get_triangle(const gort_ctx* ctx, int32_t order_index_among_triangles, double* v9, int32_t* material);
+int gort_scene_get_material(const gort_ctx* ctx, int32_t index, int32_t* type, double* color3_rough_metal_spec_ior7);
+
+/* ---- render (replaces the body of ParallelRenderer.Render, renderer.go:67-126) ------------ */
+/* rgba_out: caller-owned host buffer of width*height*4 bytes, row-major, row y=0 first ==
+ * image.RGBA.Pix with Stride = 4*width (renderer.go:70,96).  With shard_count > 1 only the
+ * shard's tiles are written; other bytes are left untouched. */
+int gort_render(gort_ctx* ctx, const gort_render_params* params, uint8_t* rgba_out, size_t rgba_bytes,
+                gort_stats* stats_out);
+/* Same frame, but the row-major RGBA8 image stays in device memory (device_ids[0]); d_rgba is a
+ * device pointer with width*height*4 bytes.  Asynchronous on the ctx stream unless stats_out != NULL. */
+int gort_render_device(gort_ctx* ctx, const gort_render_params* params, void* d_rgba, size_t rgba_bytes,
+                       gort_stats* stats_out);
+/* Multi-process sharding (one process per GPU): render only this shard's tiles into a TILE-MAJOR
+ * slab in device memory: slab tile j = global tile (shard_rank + j*shard_count), each tile
+ * GORT_TILE*GORT_TILE*4 bytes, pixel (lx,ly) at ((ly*GORT_TILE+lx)*4).  slab_bytes must be
+ * gort_shard_slab_bytes().  The slabs of all ranks, concatenated rank-major (what an NCCL gather
+ * produces), are turned into the row-major frame by gort_unswizzle_device. */
+size_t gort_shard_slab_bytes(int32_t width, int32_t height, int32_t shard_count);
+int gort_render_shard_device(gort_ctx* ctx, const gort_render_params* params, void* d_slab, size_t slab_bytes,
+                             gort_stats* stats_out);
+int gort_unswizzle_device(gort_ctx* ctx, const void* d_slabs, int32_t shard_count, int32_t width, int32_t height,
+                          void* d_rgba, size_t rgba_bytes);
+/* Sample-averaged linear radiance (before tone-map) of the last render on this ctx, float64 RGB
+ * [height][width][3] on the host; tiles not owned by the shard are left untouched.  Test hook. */
+int gort_read_radiance(gort_ctx* ctx, double* radiance_out, size_t bytes);
+
+/* ---- test / measurement hooks ------------------------------------------------------------ */
+/* hitWorld on the GPU BVH for n rays (host arrays, float64 in, float64 out): out_t[n] (<0 = miss),
+ * out_order[n] = reference scan-order index of the primitive hit.  Contract: identical closest hit
+ * to the linear scan (renderer.go:333-346) up to fp32 rounding. */
+int gort_trace_rays(gort_ctx* ctx, int32_t n, const double* origins3, const double* directions3, double t_min,
+                    double t_max, int32_t any_hit, double* out_t, int32_t* out_order);
+/* Dependent-FFMA-chain microbenchmark on device_ids[0]: measured FP32 issue peak in TFLOP/s
+ * (FMA = 2 flops) — the roofline denominator MEASURED_PEAKS.json lacks. */
+int gort_measure_fp32_peak(gort_ctx* ctx, double* tflops_out, double* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GORT_H */
