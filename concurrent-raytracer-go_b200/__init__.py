@@ -38,6 +38,9 @@ EXPORTED_SYMBOLS = [
     "gort_scene_upload", "gort_scene_load_json", "gort_scene_load_file", "gort_scene_counts", "gort_scene_get_triangle",
     "gort_scene_get_material", "gort_render", "gort_render_device", "gort_shard_slab_bytes", "gort_render_shard_device",
     "gort_unswizzle_device", "gort_read_radiance", "gort_trace_rays", "gort_measure_fp32_peak",
+    "gort_host_scene_parse", "gort_host_scene_free", "gort_host_scene_counts", "gort_host_scene_get_sphere",
+    "gort_host_scene_get_triangle", "gort_host_scene_get_material", "gort_host_scene_get_light", "gort_host_scene_get_camera",
+    "gort_host_scene_bvh_validate",
 ]
 
 
@@ -134,6 +137,16 @@ def load_library() -> C.CDLL:
     L.gort_read_radiance.argtypes = [vp, dp, C.c_size_t]
     L.gort_trace_rays.argtypes = [vp, C.c_int32, dp, dp, C.c_double, C.c_double, C.c_int32, dp, ip]
     L.gort_measure_fp32_peak.argtypes = [vp, dp, dp]
+    L.gort_host_scene_parse.argtypes = [C.c_char_p, C.c_size_t, C.c_uint32, C.POINTER(vp), C.c_char_p, C.c_size_t]
+    L.gort_host_scene_free.argtypes = [vp]
+    L.gort_host_scene_free.restype = None
+    L.gort_host_scene_counts.argtypes = [vp, ip]
+    L.gort_host_scene_get_sphere.argtypes = [vp, C.c_int32, dp, ip, ip]
+    L.gort_host_scene_get_triangle.argtypes = [vp, C.c_int32, dp, ip, ip]
+    L.gort_host_scene_get_material.argtypes = [vp, C.c_int32, ip, dp]
+    L.gort_host_scene_get_light.argtypes = [vp, C.c_int32, dp]
+    L.gort_host_scene_get_camera.argtypes = [vp, dp]
+    L.gort_host_scene_bvh_validate.argtypes = [vp, C.POINTER(C.c_int64), C.c_char_p, C.c_size_t]
     _lib = L
     return L
 
@@ -166,6 +179,87 @@ def LoadFromFile(filename: str, options: int = 0) -> Scene:
 
 def SceneFromDict(desc: dict, options: int = 0) -> Scene:
     return Scene(json.dumps(desc), options)
+
+
+class HostScene:
+    """Host-only parse of the reference's scene JSON by libgort's loader (no CUDA needed): the
+    flattened GetHittables()/GetLights() view in the reference's scan order."""
+
+    def __init__(self, json_text: str, options: int = 0):
+        L = load_library()
+        self._L = L
+        self._h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        raw = json_text.encode()
+        rc = L.gort_host_scene_parse(raw, len(raw), options, C.byref(self._h), err, len(err))
+        if rc != 0:
+            raise GortError(rc, err.value.decode())
+
+    def __del__(self):
+        try:
+            if self._h.value:
+                self._L.gort_host_scene_free(self._h)
+        except Exception:
+            pass
+
+    def counts(self) -> dict:
+        c = (C.c_int32 * 5)()
+        self._L.gort_host_scene_counts(self._h, c)
+        return dict(zip(("spheres", "triangles", "materials", "lights", "hittables"), list(c)))
+
+    def sphere(self, i):
+        o = (C.c_double * 4)()
+        m, k = C.c_int32(), C.c_int32()
+        if self._L.gort_host_scene_get_sphere(self._h, i, o, C.byref(m), C.byref(k)) != 0:
+            raise IndexError(i)
+        return np.array(o[:3]), o[3], m.value, k.value
+
+    def triangle(self, i):
+        o = (C.c_double * 9)()
+        m, k = C.c_int32(), C.c_int32()
+        if self._L.gort_host_scene_get_triangle(self._h, i, o, C.byref(m), C.byref(k)) != 0:
+            raise IndexError(i)
+        return np.array(o[:]), m.value, k.value
+
+    def material(self, i):
+        o = (C.c_double * 7)()
+        t = C.c_int32()
+        if self._L.gort_host_scene_get_material(self._h, i, C.byref(t), o) != 0:
+            raise IndexError(i)
+        return t.value, np.array(o[:])
+
+    def light(self, i):
+        o = (C.c_double * 7)()
+        if self._L.gort_host_scene_get_light(self._h, i, o) != 0:
+            raise IndexError(i)
+        return np.array(o[:])
+
+    def camera(self):
+        o = (C.c_double * 11)()
+        self._L.gort_host_scene_get_camera(self._h, o)
+        return np.array(o[:])
+
+    def bvh_validate(self) -> dict:
+        info = (C.c_int64 * 4)()
+        err = C.create_string_buffer(256)
+        rc = self._L.gort_host_scene_bvh_validate(self._h, info, err, len(err))
+        if rc != 0:
+            raise GortError(rc, err.value.decode())
+        return dict(zip(("nodes", "max_depth", "leaves", "bytes"), list(info)))
+
+    def to_flat(self) -> "FlatScene":
+        """Re-express the parsed scene as a gort_scene_desc (what a Go host's Flatten() would pass)."""
+        c = self.counts()
+        cam = self.camera()
+        mats = []
+        for i in range(c["materials"]):
+            t, v = self.material(i)
+            mats.append({"type": t, "color": v[:3], "roughness": v[3], "metallic": v[4], "specular": v[5], "ior": v[6]})
+        sph = [(s[0], s[1], s[2], s[3]) for s in (self.sphere(i) for i in range(c["spheres"]))]
+        tri = [self.triangle(i) for i in range(c["triangles"])]
+        lts = [(l[:3], l[3:6], l[6]) for l in (self.light(i) for i in range(c["lights"]))]
+        return FlatScene({"position": cam[:3], "lookAt": cam[3:6], "up": cam[6:9], "fov": cam[9], "aspectRatio": cam[10]},
+                         mats, sph, tri, lts)
 
 
 class FlatScene:
@@ -287,7 +381,9 @@ class ParallelRenderer:
             raise GortError(rc, (self._L.gort_last_error(self._ctx) or b"").decode())
 
     def set_stream(self, cuda_stream_ptr: int):
-        self._check(self._L.gort_set_stream(self._ctx, C.c_void_p(cuda_stream_ptr)))
+        """Launch on a caller-owned stream.  A torch default stream has handle 0, which the C ABI reads as
+        "restore the ctx's own stream", so it is passed as cudaStreamLegacy (0x1)."""
+        self._check(self._L.gort_set_stream(self._ctx, C.c_void_p(cuda_stream_ptr if cuda_stream_ptr else 1)))
 
     # ---- scene upload (GetHittables/GetLights feeding Render, renderer.go:72-74) ----
     def UploadScene(self, scene) -> None:

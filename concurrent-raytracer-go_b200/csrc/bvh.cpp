@@ -140,13 +140,14 @@ struct Builder {
                     }
                 }
             }
-            if (best_axis >= 0 && count <= kMaxLeafPrims) {
+            // depth 0 never becomes a leaf when it can be split: the root node stores its children's boxes
+            if (best_axis >= 0 && count <= kMaxLeafPrims && depth > 0) {
                 // leaf cost = count (one unit per primitive test); split cost = 1 (node) + SAH
                 double split_cost = 1.0 + (parent_area > 0 ? best_cost / parent_area : (double)count);
                 if (split_cost >= (double)count) return make_leaf(first, count, depth, b);
             }
             if (best_axis < 0) {
-                if (count <= kMaxLeafPrims) return make_leaf(first, count, depth, b);
+                if (count <= kMaxLeafPrims && depth > 0) return make_leaf(first, count, depth, b);
                 split = first + count / 2;  // identical centroids: split by index
             } else {
                 const double cmin = cb.lo[best_axis], cmax = cb.hi[best_axis];
@@ -234,11 +235,12 @@ void build_bvh(const HostScene& scene, FlatBvh& out) {
 
     B.nodes.reserve((size_t)n);
     int root = B.build(0, n, 0);
-    // Aila-Laine nodes store the children's boxes in the parent, so a leaf root needs a wrapper.
+    // Nodes store the children's boxes in the parent, so a leaf root (single-primitive scene) needs
+    // a wrapper; both slots reference the same leaf (the second test ties and changes nothing).
     if (B.nodes[root].left < 0) {
         BNode w = B.nodes[root];
         w.left = root;
-        w.right = -2;  // empty
+        w.right = root;
         w.depth = 0;
         B.nodes.push_back(w);
         root = (int)B.nodes.size() - 1;
@@ -308,27 +310,28 @@ void build_bvh(const HostScene& scene, FlatBvh& out) {
         return (int32_t)~v;
     };
 
-    const float inf = std::numeric_limits<float>::infinity();
+    std::vector<int32_t> leaf_code(B.nodes.size(), 0);
+    std::vector<char> leaf_done(B.nodes.size(), 0);
     for (int32_t fi = 0; fi < out.n_nodes; fi++) {
         const BNode& nd = B.nodes[order[fi]];
         float lo[2][3], hi[2][3];
         int32_t child[2];
         const int32_t kids[2] = {nd.left, nd.right};
         for (int c = 0; c < 2; c++) {
-            if (kids[c] < 0) {  // empty slot
-                for (int a = 0; a < 3; a++) {
-                    lo[c][a] = inf;
-                    hi[c][a] = -inf;
-                }
-                child[c] = (int32_t)~0u;  // decodes as a 1-sphere leaf at 0 but its box is never hit
-                continue;
-            }
             const BNode& k = B.nodes[kids[c]];
             for (int a = 0; a < 3; a++) {
                 lo[c][a] = round_down(k.lo[a] - pad);
                 hi[c][a] = round_up(k.hi[a] + pad);
             }
-            child[c] = (k.left == -1) ? emit_leaf(k) : flat_index[kids[c]];
+            if (k.left == -1) {
+                if (!leaf_done[kids[c]]) {
+                    leaf_code[kids[c]] = emit_leaf(k);
+                    leaf_done[kids[c]] = 1;
+                }
+                child[c] = leaf_code[kids[c]];
+            } else {
+                child[c] = flat_index[kids[c]];
+            }
         }
         out.nodes[(size_t)fi * 4 + 0] = F4{lo[0][0], hi[0][0], lo[0][1], hi[0][1]};
         out.nodes[(size_t)fi * 4 + 1] = F4{lo[1][0], hi[1][0], lo[1][1], hi[1][1]};

@@ -173,7 +173,8 @@ int gort_create(const int* device_ids, int n_devices, gort_ctx** out);
 void gort_destroy(gort_ctx* ctx);
 const char* gort_last_error(const gort_ctx* ctx); /* ctx may be NULL: error of a failed gort_create */
 /* Launch on a caller-owned CUDA stream (cudaStream_t as void*) of device_ids[0]; NULL restores the
- * ctx's own stream.  Lets a host framework time/order the work with its own events. */
+ * ctx's own (non-blocking) stream; name the legacy default stream with cudaStreamLegacy (0x1).
+ * Lets a host framework time/order the work with its own events. */
 int gort_set_stream(gort_ctx* ctx, void* cuda_stream);
 
 /* ---- scene (replaces scene.GetHittables()/GetLights() feeding Render, renderer.go:72-74) -- */
@@ -213,6 +214,25 @@ int gort_unswizzle_device(gort_ctx* ctx, const void* d_slabs, int32_t shard_coun
 /* Sample-averaged linear radiance (before tone-map) of the last render on this ctx, float64 RGB
  * [height][width][3] on the host; tiles not owned by the shard are left untouched.  Test hook. */
 int gort_read_radiance(gort_ctx* ctx, double* radiance_out, size_t bytes);
+
+/* ---- host-only scene model (no CUDA needed): what the loader + BVH builder produce ---------- */
+typedef struct gort_host_scene gort_host_scene;
+/* Parse the reference's scene JSON exactly like gort_scene_load_json but keep the result on the host.
+ * errbuf (may be NULL) receives the message on failure. */
+int gort_host_scene_parse(const char* json_text, size_t json_len, uint32_t options, gort_host_scene** out, char* errbuf,
+                          size_t errbuf_len);
+void gort_host_scene_free(gort_host_scene* scene);
+/* counts5 = {spheres, triangles, materials, lights, hittables} */
+int gort_host_scene_counts(const gort_host_scene* scene, int32_t* counts5);
+int gort_host_scene_get_sphere(const gort_host_scene* scene, int32_t i, double* center3_radius4, int32_t* material, int32_t* order);
+int gort_host_scene_get_triangle(const gort_host_scene* scene, int32_t i, double* v9, int32_t* material, int32_t* order);
+int gort_host_scene_get_material(const gort_host_scene* scene, int32_t i, int32_t* type, double* color3_rough_metal_spec_ior7);
+int gort_host_scene_get_light(const gort_host_scene* scene, int32_t i, double* pos3_color3_intensity7);
+int gort_host_scene_get_camera(const gort_host_scene* scene, double* pos3_lookat3_up3_fov_aspect11);
+/* Build the BVH on the host and check its invariants (every primitive in exactly one leaf, leaves
+ * homogeneous and <= 4 primitives, every child box encloses its subtree, depth within the traversal
+ * stack).  Returns GORT_OK or GORT_ERR_INVALID; fills info4 = {inner nodes, max depth, leaves, bytes}. */
+int gort_host_scene_bvh_validate(const gort_host_scene* scene, int64_t* info4, char* errbuf, size_t errbuf_len);
 
 /* ---- test / measurement hooks ------------------------------------------------------------ */
 /* hitWorld on the GPU BVH for n rays (host arrays, float64 in, float64 out): out_t[n] (<0 = miss),

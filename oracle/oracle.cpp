@@ -1002,6 +1002,18 @@ void orc_scene_add_prism(void* sp, const double* verts18, const orc_material* m)
     for (int i = 0; i < 6; i++) v[i] = V3{verts18[3 * i], verts18[3 * i + 1], verts18[3 * i + 2]};
     add_prism(*s, v, mi);
 }
+// A Mesh hittable from explicit triangles (scene.Mesh, scene.go:192-209): used to mirror flat
+// gort_scene_desc inputs (synthetic scenes) where cubes arrive already expanded.
+void orc_scene_add_mesh(void* sp, const double* verts9n, int n_tris, const orc_material* m) {
+    Scene* s = (Scene*)sp;
+    int mi = add_material(s, m);
+    Hittable hb{PRIM_MESH, (int)s->tris.size(), n_tris};
+    for (int i = 0; i < n_tris; i++) {
+        const double* v = verts9n + 9 * i;
+        add_mesh_triangle(*s, V3{v[0], v[1], v[2]}, V3{v[3], v[4], v[5]}, V3{v[6], v[7], v[8]}, mi);
+    }
+    s->hittables.push_back(hb);
+}
 void orc_scene_add_light(void* sp, const double* pos, const double* color, double intensity) {
     Scene* s = (Scene*)sp;
     s->lights.push_back(Light{V3{pos[0], pos[1], pos[2]}, V3{color[0], color[1], color[2]}, intensity});

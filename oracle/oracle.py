@@ -83,6 +83,7 @@ def lib() -> C.CDLL:
         L.orc_scene_add_sphere.argtypes = [C.c_void_p, dp, C.c_double, C.POINTER(OrcMaterial)]
         L.orc_scene_add_cube.argtypes = [C.c_void_p, dp, dp, C.POINTER(OrcMaterial)]
         L.orc_scene_add_prism.argtypes = [C.c_void_p, dp, C.POINTER(OrcMaterial)]
+        L.orc_scene_add_mesh.argtypes = [C.c_void_p, dp, C.c_int, C.POINTER(OrcMaterial)]
         L.orc_scene_add_light.argtypes = [C.c_void_p, dp, dp, C.c_double]
         L.orc_scene_set_fog.argtypes = [C.c_void_p, C.c_int, C.c_double, dp]
         ip = C.POINTER(C.c_int)
@@ -179,6 +180,46 @@ class Scene:
         fg = desc.get("fog") or {}
         if fog and fg.get("enabled"):
             L.orc_scene_set_fog(self.h, 1, float(fg.get("density", 0.0)), _d3(_vec3(fg.get("color"))))
+
+    @classmethod
+    def from_flat(cls, camera: dict, materials, spheres, triangles, lights, fog=None) -> "Scene":
+        """Mirror of a flat gort_scene_desc (tests/synth.py): materials are post-constructor dicts with an
+        integer type; spheres (center, radius, material, order); triangles (v9, material, order) — runs of
+        triangles sharing a material become one Mesh, in scan order."""
+        self = cls({"camera": camera, "objects": [], "lights": []})
+        L = lib()
+
+        def mat(md):
+            m = OrcMaterial()
+            m.type = int(md["type"])
+            m.has_color, m.has_roughness, m.has_metallic, m.has_specular, m.has_ior = 1, 1, 1, 1, 1
+            m.color[:] = [float(x) for x in md["color"]]
+            m.roughness, m.metallic, m.specular, m.ior = float(md["roughness"]), float(md["metallic"]), float(md["specular"]), float(md["ior"])
+            return m
+
+        items = [(s[3], "s", s) for s in spheres] + [(t[2], "t", t) for t in triangles]
+        items.sort(key=lambda it: it[0])
+        i = 0
+        while i < len(items):
+            _, kind, it = items[i]
+            if kind == "s":
+                m = mat(materials[it[2]])
+                L.orc_scene_add_sphere(self.h, _d3(it[0]), float(it[1]), C.byref(m))
+                i += 1
+            else:
+                j = i
+                verts = []
+                while j < len(items) and items[j][1] == "t" and items[j][2][1] == it[1]:
+                    verts.extend(float(x) for x in items[j][2][0])
+                    j += 1
+                m = mat(materials[it[1]])
+                L.orc_scene_add_mesh(self.h, (C.c_double * len(verts))(*verts), (j - i), C.byref(m))
+                i = j
+        for lt in lights:
+            L.orc_scene_add_light(self.h, _d3(lt[0]), _d3(lt[1]), float(lt[2]))
+        if fog:
+            L.orc_scene_set_fog(self.h, 1, float(fog["density"]), _d3(fog["color"]))
+        return self
 
     @classmethod
     def from_file(cls, path: str, **kw) -> "Scene":

@@ -1,0 +1,105 @@
+"""Host logic of the product (no GPU): the C++ scene loader (mirror of scene.LoadFromFile/GetHittables,
+/root/reference internal/scene/scene.go:45-190) against the oracle's independent expansion, the BVH
+builder's invariants, and the error behaviour where the reference would panic."""
+import json
+
+import numpy as np
+import pytest
+
+import common as Cm
+
+
+@pytest.mark.parametrize("name,prisms", [("sphere_reflections_light.json", False), ("final_silver_prism_purple_cube_.json", False),
+                                         ("final_silver_prism_purple_cube_.json", True), ("two_red_cubes_scene.json", False)])
+def test_loader_matches_oracle_expansion(gort, oracle, name, prisms):
+    d = Cm.load_scene_dict(name)
+    hs = gort.HostScene(json.dumps(d), gort.LOAD_PRISMS if prisms else 0)
+    os_ = oracle.Scene(d, prisms=prisms)
+    hc, oc = hs.counts(), os_.counts()
+    assert (hc["spheres"], hc["triangles"], hc["hittables"], hc["lights"]) == (oc["spheres"], oc["triangles"], oc["hittables"], oc["lights"])
+    for i in range(hc["triangles"]):
+        v9, mat, order = hs.triangle(i)
+        o12, omat = os_.triangle(i)
+        assert v9.tolist() == o12[:9].tolist() and mat == omat
+    for i in range(hc["materials"]):
+        t, v = hs.material(i)
+        ot, ov = os_.material(i)
+        assert t == ot
+        assert v[:3].tolist() == ov[:3].tolist()
+        if t in (1, 2):  # metal / shiny carry all four scalars
+            assert v[3:].tolist() == ov[3:].tolist()
+        if t in (4, 5):
+            assert v[6] == ov[6]
+    # scan order is a permutation: spheres and triangles interleaved in object order
+    orders = [hs.sphere(i)[3] for i in range(hc["spheres"])] + [hs.triangle(i)[2] for i in range(hc["triangles"])]
+    assert sorted(orders) == list(range(len(orders)))
+
+
+def test_missing_color_default_and_camera(gort):
+    hs = gort.HostScene(open(Cm.SCENES + "/sphere_reflections_light.json").read())
+    t, v = hs.material(1)
+    assert t == 1 and v[:3].tolist() == [1, 1, 1] and v[4] == 1.0  # F5 default albedo, metallic default 1
+    cam = hs.camera()
+    assert cam[:3].tolist() == [0, 0, -8] and cam[9] == 60 and cam[10] == 1.33
+
+
+def test_vec3_object_form(gort):  # Vec3.UnmarshalJSON accepts {"X":..,"Y":..,"Z":..} (vector.go:185-192)
+    d = {"camera": {"position": {"X": 1, "Y": 2, "Z": 3}}, "objects": [], "lights": [{"position": [1, 2, 3], "color": {"X": 0.5, "Y": 0.25, "Z": 1}, "intensity": 2}]}
+    hs = gort.HostScene(json.dumps(d))
+    assert hs.camera()[:3].tolist() == [1, 2, 3]
+    assert hs.light(0).tolist() == [1, 2, 3, 0.5, 0.25, 1, 2]
+
+
+@pytest.mark.parametrize("bad", [
+    '{"objects": [{"type": "sphere", "radius": 1, "material": {"color": [1,1,1]}}]}',            # no material.type -> panic scene.go:105
+    '{"objects": [{"type": "sphere", "radius": 1}]}',                                               # nil material map
+    '{"objects": [{"type": "cube", "material": {"type": "metal", "color": "red"}}]}',              # colour not an array
+    '{"objects": [{"type": "sphere", "material": {"type": "metal", "color": [1,1,1], "roughness": "x"}}]}',
+    '{"objects": [{"type": "sphere", "position": [1,2], "material": {"type": "metal", "color": [1,1,1]}}]}',  # Vec3 needs 3
+    '{"objects": [',
+    '[]',
+])
+def test_loader_errors_where_reference_fails(gort, bad):
+    with pytest.raises(gort.GortError) as e:
+        gort.HostScene(bad)
+    assert e.value.code == -6
+
+
+def test_unknown_object_with_bad_material_is_skipped(gort):
+    # GetHittables only calls createMaterial for sphere/cube (scene.go:69-83)
+    hs = gort.HostScene('{"objects": [{"type": "torus"}, {"type": "triangularPrism", "material": 5}]}')
+    assert hs.counts()["hittables"] == 0
+
+
+@pytest.mark.parametrize("n,seed", [(1, 0), (2, 1), (5, 2), (64, 3), (1000, 4), (20000, 5)])
+def test_bvh_invariants_random_spheres(gort, n, seed):
+    d = Cm.random_sphere_scene(n, seed)
+    info = gort.HostScene(json.dumps(d)).bvh_validate()
+    assert info["max_depth"] <= 56
+    assert info["leaves"] >= (n + 3) // 4
+
+
+def test_bvh_invariants_mixed_and_degenerate(gort):
+    rng = np.random.default_rng(9)
+    objs = []
+    for i in range(300):
+        m = {"type": "lambertian", "color": [1, 1, 1]}
+        if i % 2:
+            objs.append({"type": "cube", "position": rng.uniform(-5, 5, 3).tolist(), "size": rng.uniform(0.1, 1, 3).tolist(), "material": m})
+        else:
+            objs.append({"type": "sphere", "position": rng.uniform(-5, 5, 3).tolist(), "radius": 0.3, "material": m})
+    # degenerate: many identical centroids, zero-size cube, zero-radius sphere
+    for _ in range(40):
+        objs.append({"type": "sphere", "position": [1, 1, 1], "radius": 0.5, "material": {"type": "glass", "color": [1, 1, 1]}})
+    objs.append({"type": "cube", "position": [0, 0, 0], "size": [0, 0, 0], "material": {"type": "metal", "color": [1, 1, 1]}})
+    objs.append({"type": "sphere", "position": [0, 0, 0], "radius": 0.0, "material": {"type": "metal", "color": [1, 1, 1]}})
+    hs = gort.HostScene(json.dumps({"objects": objs}))
+    info = hs.bvh_validate()
+    assert hs.counts()["triangles"] == 151 * 12 and info["max_depth"] <= 56
+
+
+def test_flat_scene_round_trip_types(gort):
+    hs = gort.HostScene(open(Cm.SCENES + "/final_silver_prism_purple_cube_.json").read(), gort.LOAD_PRISMS)
+    flat = hs.to_flat()
+    assert flat.desc.n_triangles == 40 and flat.desc.n_materials == 4 and flat.desc.n_lights == 3
+    assert flat.desc.abi_version == gort.ABI_VERSION

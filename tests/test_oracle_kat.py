@@ -1,0 +1,264 @@
+"""Pins the CPU oracle against every known-answer vector the reference's own tests hold for this
+path (/root/reference internal/math/vector_test.go:8-105, math_benchmarks_test.go:126-165 — the only
+tests that touch the path) plus the hand-derived answers of SURVEY §4 and the published
+Philox4x32-10 test vectors (Random123 kat_vectors)."""
+import math
+
+import numpy as np
+import pytest
+
+import common as Cm
+
+
+# ---- internal/math/vector_test.go -------------------------------------------------------------
+def test_vec3_add(oracle):  # vector_test.go:8-18
+    assert oracle.vec_add((1, 2, 3), (4, 5, 6)).tolist() == [5, 7, 9]
+
+
+def test_vec3_sub(oracle):  # vector_test.go:20-30
+    assert oracle.vec_sub((5, 7, 9), (1, 2, 3)).tolist() == [4, 5, 6]
+
+
+def test_vec3_dot(oracle):  # vector_test.go:32-42
+    assert oracle.vec_dot((1, 2, 3), (4, 5, 6)) == 32.0
+
+
+def test_vec3_cross(oracle):  # vector_test.go:44-54
+    assert oracle.vec_cross((1, 0, 0), (0, 1, 0)).tolist() == [0, 0, 1]
+
+
+def test_vec3_length(oracle):  # vector_test.go:56-64
+    assert abs(oracle.vec_length((3, 4, 0)) - 5.0) <= 1e-10
+
+
+def test_vec3_normalize(oracle):  # vector_test.go:66-77
+    assert np.allclose(oracle.vec_normalize((3, 4, 0)), (0.6, 0.8, 0), atol=1e-10, rtol=0)
+    assert oracle.vec_normalize((0, 0, 0)).tolist() == [0, 0, 0]  # vector.go:63-65
+
+
+def test_vec3_reflect(oracle):  # vector_test.go:79-91
+    assert np.allclose(oracle.vec_reflect((1, -1, 0), (0, 1, 0)), (1, 1, 0), atol=1e-10, rtol=0)
+
+
+def test_vec3_clamp(oracle):  # vector_test.go:93-101
+    assert oracle.vec_clamp((-1, 0.5, 2), 0, 1).tolist() == [0, 0.5, 1]
+
+
+def test_vec3_to_rgb(oracle):  # vector_test.go:103-113: truncating conversion
+    assert oracle.vec_to_rgb((0.5, 0.25, 1.0)) == (127, 63, 255)
+
+
+# ---- internal/math/math_benchmarks_test.go:126-165 (value checks) ------------------------------
+def test_bench_values(oracle):
+    assert oracle.vec_mul((1, 2, 3), (4, 5, 6)).tolist() == [4, 10, 18]
+    assert oracle.vec_cross((1, 2, 3), (4, 5, 6)).tolist() == [-3, 6, -3]
+    assert abs(oracle.vec_length((1, 2, 3)) - math.sqrt(14)) < 1e-12
+
+
+# ---- hand-derived known answers ----------------------------------------------------
+def test_sphere_hit_front(oracle):  # sphere.go:23-50
+    h = oracle.sphere_hit((0, 0, 0), 1.0, (0, 0, 5), (0, 0, -1))
+    assert h["t"] == 4.0 and h["point"].tolist() == [0, 0, 1] and h["normal"].tolist() == [0, 0, 1] and h["front_face"]
+
+
+def test_sphere_hit_unnormalised_direction(oracle):
+    h = oracle.sphere_hit((0, 0, 0), 1.0, (0, 0, 5), (0, 0, -2))
+    assert h["t"] == 2.0
+
+
+def test_sphere_hit_inside(oracle):  # near root rejected by tMin, outward normal flipped
+    h = oracle.sphere_hit((0, 0, 0), 1.0, (0, 0, 0), (0, 0, 1))
+    assert h["t"] == 1.0 and h["normal"].tolist() == [0, 0, -1] and not h["front_face"]
+
+
+def test_sphere_hit_range(oracle):  # root < tMin || tMax < root (sphere.go:35-40)
+    assert oracle.sphere_hit((0, 0, 0), 1.0, (0, 0, 5), (0, 0, -1), 0.001, 3.9) is None
+    assert oracle.sphere_hit((0, 0, 0), 1.0, (0, 0, 5), (0, 0, -1), 0.001, 4.0)["t"] == 4.0  # t == tMax accepted
+    assert oracle.sphere_hit((0, 0, 0), 1.0, (0, 0, 5), (0, 0, -1), 4.5, 10.0)["t"] == 6.0  # far root
+    assert oracle.sphere_hit((0, 0, 0), 1.0, (0, 3, 5), (0, 0, -1)) is None  # discriminant < 0
+
+
+def test_triangle_hit(oracle):  # triangle.go:36-88
+    v0, v1, v2 = (0, 0, 0), (1, 0, 0), (0, 1, 0)
+    h = oracle.triangle_hit(v0, v1, v2, (0.25, 0.25, 1), (0, 0, -1))
+    assert h["t"] == 1.0 and h["normal"].tolist() == [0, 0, 1] and h["front_face"]
+    h = oracle.triangle_hit(v0, v1, v2, (0.25, 0.25, -1), (0, 0, 2))  # back side, unnormalised: two-sided, normal flipped
+    assert h["t"] == 0.5 and h["normal"].tolist() == [0, 0, -1] and not h["front_face"]
+    assert oracle.triangle_hit(v0, v1, v2, (0.75, 0.75, 1), (0, 0, -1)) is None  # u + v > 1
+    assert oracle.triangle_hit(v0, v1, v2, (-0.1, 0.2, 1), (0, 0, -1)) is None  # u < 0
+    assert oracle.triangle_hit(v0, v1, v2, (0.25, 0.25, 1), (1, 0, 0)) is None  # |a| < 1e-6 (parallel)
+    assert oracle.triangle_hit(v0, v1, v2, (0.25, 0.25, 1), (0, 0, -1), 0.001, 0.5) is None  # t > tMax
+
+
+def test_tie_rule_last_wins(oracle):
+    """hitWorld (renderer.go:337-343): a later primitive at EQUAL t replaces the earlier one."""
+    d = {"camera": {"position": [0, 0, 5], "aspectRatio": 1.0},
+         "objects": [{"type": "sphere", "position": [0, 0, 0], "radius": 1.0, "material": {"type": "lambertian", "color": [1, 0, 0]}},
+                     {"type": "sphere", "position": [0, 0, 0], "radius": 1.0, "material": {"type": "lambertian", "color": [0, 1, 0]}}],
+         "lights": []}
+    s = oracle.Scene(d)
+    for accel in (False, True):
+        h = s.hit_world((0, 0, 5), (0, 0, -1), use_accel=accel)
+        assert h["t"] == 4.0 and h["material"] == 1 and h["prim"] == 1
+
+
+def test_fresnel_f0(oracle):  # material.go:71,117; advanced_materials.go:121,147
+    assert abs(oracle.schlick(1.5, 1.0) - 0.04) < 1e-15
+    assert abs(oracle.schlick(2.0, 1.0) - 1.0 / 9.0) < 1e-15
+    # unnormalised direction: cosTheta > 1 makes (1-cos)^5 negative (material.go:85,123)
+    assert oracle.schlick(1.5, 1.5) < 0.04
+
+
+def test_reflectance(oracle):  # material.go:282-286
+    r0 = ((1 - 1.5) / (1 + 1.5)) ** 2
+    assert abs(oracle.reflectance(1.0, 1.5) - r0) < 1e-15
+    assert abs(oracle.reflectance(0.0, 1.5) - 1.0) < 1e-15
+
+
+def test_refract(oracle):  # vector.go:81-96
+    v = np.array([math.sin(0.5), -math.cos(0.5), 0.0])
+    out = oracle.vec_refract(v, (0, 1, 0), 1 / 1.5)
+    assert abs(np.linalg.norm(out) - 1.0) < 1e-12
+    assert abs(out[0] - math.sin(0.5) / 1.5) < 1e-12  # Snell
+    # total internal reflection inside Refract falls back to Reflect
+    v = np.array([math.sin(1.2), -math.cos(1.2), 0.0])
+    assert np.allclose(oracle.vec_refract(v, (0, 1, 0), 1.5), oracle.vec_reflect(v, (0, 1, 0)))
+
+
+@pytest.mark.parametrize("radiance,expected", [(0.0, 0), (0.05, 64), (0.07, 74), (0.08, 79), (0.1, 87), (0.25, 128), (0.5, 166), (1.0, 207), (3.0, 249)])
+def test_tone_map_table(oracle, radiance, expected):  # renderer.go:348-367 + vector.go:106-109
+    assert oracle.tone_map_rgb((radiance,) * 3) == (expected,) * 3
+
+
+def test_tone_map_negative_is_zero(oracle):  # declared: NaN -> 0
+    assert oracle.tone_map_rgb((-0.5, 0.1, 1e9)) == (0, 87, 255)
+
+
+def test_reference_camera(oracle):  # getRay renderer.go:377-390
+    s = oracle.Scene(Cm.load_scene_dict("sphere_reflections_light.json"))
+    o, d = s.get_ray(0.0, 0.0)
+    assert o.tolist() == [0, 0, -8]
+    assert np.allclose(d, (-1.33, -1.0, -1.0), atol=1e-15)
+    o, d = s.get_ray(1.0, 1.0)
+    assert np.allclose(d, (1.33, 1.0, -1.0), atol=1e-15)
+    o, d = s.get_ray(0.5, 0.5)
+    assert np.allclose(d, (0, 0, -1.0), atol=1e-15)  # not normalised, looks down -Z whatever lookAt says
+
+
+def test_shipped_scenes_render_black_with_reference_camera(oracle):
+    """both README scenes sit behind the committed camera -> every pixel (0,0,0,255)."""
+    for name in ("sphere_reflections_light.json", "final_silver_prism_purple_cube_.json"):
+        img, _, cnt = oracle.Scene(Cm.load_scene_dict(name)).render(96, 72, samples=2, seed=1)
+        assert (img[..., :3] == 0).all() and (img[..., 3] == 255).all()
+        assert cnt["scatters"] == 0
+
+
+# ---- scene factory (scene.go:104-190) -----------------------------------------------------------
+def test_create_material_defaults(oracle):
+    d = {"camera": {}, "lights": [], "objects": [
+        {"type": "sphere", "radius": 1, "position": [0, 0, 0], "material": {"type": "metal", "color": [0.5, 0.6, 0.7]}},
+        {"type": "sphere", "radius": 1, "position": [0, 0, 0], "material": {"type": "metal", "refractionIndex": 1.5}},  # F5: no colour
+        {"type": "sphere", "radius": 1, "position": [0, 0, 0], "material": {"type": "shiny", "color": [1, 0, 0], "roughness": 3.0}},
+        {"type": "sphere", "radius": 1, "position": [0, 0, 0], "material": {"type": "perfectmirror", "color": [1, 1, 1]}},
+        {"type": "sphere", "radius": 1, "position": [0, 0, 0], "material": {"type": "glass", "color": [1, 1, 1]}},
+        {"type": "sphere", "radius": 1, "position": [0, 0, 0], "material": {"type": "dielectric", "refractionIndex": 1.33}},
+        {"type": "sphere", "radius": 1, "position": [0, 0, 0], "material": {"type": "plastic", "color": [0.1, 0.2, 0.3]}},
+    ]}
+    s = oracle.Scene(d)
+    t, v = s.material(0)
+    assert t == 1 and v.tolist() == [0.5, 0.6, 0.7, 0.0, 1.0, 1.0, 1.5]  # roughness 0, metallic 1, specular 1, IOR 1.5
+    t, v = s.material(1)
+    assert t == 1 and v[:3].tolist() == [1, 1, 1]
+    t, v = s.material(2)
+    assert t == 2 and v[3] == 1.0 and v[4] == 0.0 and v[5] == 1.0  # min(roughness,1), metallic 0
+    t, v = s.material(3)
+    assert t == 3 and v[6] == 2.0
+    t, v = s.material(4)
+    assert t == 4 and v[6] == 1.5
+    t, v = s.material(5)
+    assert t == 5 and v[6] == 1.33
+    t, v = s.material(6)
+    assert t == 0 and v[:3].tolist() == [0.1, 0.2, 0.3]  # default branch -> lambertian
+
+
+def test_create_cube_order(oracle):
+    d = {"camera": {}, "lights": [], "objects": [
+        {"type": "cube", "position": [1, 2, 3], "size": [2, 4, 6], "material": {"type": "lambertian", "color": [1, 1, 1]}}]}
+    s = oracle.Scene(d)
+    assert s.counts() == {"spheres": 0, "triangles": 12, "hittables": 1, "lights": 0}
+    t0, _ = s.triangle(0)  # face {0,1,2,3} -> (v0,v1,v2)
+    assert t0[:9].tolist() == [0, 0, 0, 2, 0, 0, 2, 4, 0]
+    assert t0[9:].tolist() == [0, 0, 1]  # normalize((v1-v0) x (v2-v0)); this winding faces +z
+    t1, _ = s.triangle(1)  # (v0,v2,v3)
+    assert t1[:9].tolist() == [0, 0, 0, 2, 4, 0, 0, 4, 0]
+    t11, _ = s.triangle(11)  # face {4,5,1,0} second triangle (v4, v1, v0)
+    assert t11[:9].tolist() == [0, 0, 6, 2, 0, 0, 0, 0, 0]
+
+
+def test_unknown_objects_skipped(oracle):  # scene.go:80-82; prisms only with the extension flag
+    d = Cm.load_scene_dict("final_silver_prism_purple_cube_.json")
+    assert oracle.Scene(d).counts() == {"spheres": 0, "triangles": 24, "hittables": 2, "lights": 3}
+    assert oracle.Scene(d, prisms=True).counts() == {"spheres": 0, "triangles": 40, "hittables": 4, "lights": 3}
+
+
+# ---- Philox4x32-10 (Random123 known-answer vectors) --------------------------------------------
+def test_philox_kat(oracle):
+    assert oracle.philox4x32_10((0, 0, 0, 0), (0, 0)) == (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)
+    assert oracle.philox4x32_10((0xffffffff,) * 4, (0xffffffff,) * 2) == (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)
+    assert oracle.philox4x32_10((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == \
+        (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)
+
+
+def test_philox_independent_python_restatement(oracle):
+    def philox(ctr, key):
+        c = list(ctr)
+        k = list(key)
+        for _ in range(10):
+            p0 = 0xD2511F53 * c[0]
+            p1 = 0xCD9E8D57 * c[2]
+            c = [(p1 >> 32) ^ c[1] ^ k[0], p1 & 0xffffffff, (p0 >> 32) ^ c[3] ^ k[1], p0 & 0xffffffff]
+            k = [(k[0] + 0x9E3779B9) & 0xffffffff, (k[1] + 0xBB67AE85) & 0xffffffff]
+        return tuple(c)
+    rng = np.random.default_rng(5)
+    for _ in range(50):
+        ctr = [int(x) for x in rng.integers(0, 2 ** 32, 4)]
+        key = [int(x) for x in rng.integers(0, 2 ** 32, 2)]
+        assert oracle.philox4x32_10(ctr, key) == philox(ctr, key)
+
+
+def test_in_unit_sphere_distribution(oracle):  # vector.go:132-139: uniform in the open unit ball
+    pts = np.array([oracle.in_unit_sphere(3, i, 0, 0, oracle.STREAM_SHADOW, 0) for i in range(4000)])
+    r = np.linalg.norm(pts, axis=1)
+    assert (r < 1).all()
+    assert abs((r ** 3).mean() - 0.5) < 0.03  # r^3 ~ U[0,1)
+    assert np.abs(pts.mean(axis=0)).max() < 0.03
+
+
+def test_scatter_rules(oracle):
+    n = (0, 0, 1)
+    # Metal, roughness 0: pure reflection of the UNNORMALISED direction, always scatters (material.go:75-113)
+    s = oracle.scatter({"type": "metal", "color": [0.8, 0.8, 0.9]}, (0, 0, 5), (0.3, 0, -2), (0, 0, 1), n, True)
+    assert np.allclose(s["direction"], (0.3, 0, 2))
+    cos_t = 2.0
+    f = 0.04 + 0.96 * (1 - cos_t) ** 5
+    e = np.clip(np.array([0.8, 0.8, 0.9]) * 0.0 + f * 1.0, 0, 1)  # fresnelStrength = 1 for metallic 1
+    e = e * (1 - 0.9) + f * 0.9  # metallic > 0.8: blend again, unclamped
+    assert np.allclose(s["attenuation"], e)
+    # DiffuseLight never scatters (material.go:296-298)
+    assert oracle.scatter({"type": "diffuselight", "color": [1, 1, 1]}, (0, 0, 5), (0, 0, -1), (0, 0, 1), n, True) is None
+    # Dielectric at normal incidence: attenuation 1, direction either straight through or straight back
+    s = oracle.scatter({"type": "dielectric"}, (0, 0, 5), (0, 0, -3), (0, 0, 1), n, True, seed=1)
+    assert s["attenuation"].tolist() == [1, 1, 1] and abs(abs(s["direction"][2]) - 1) < 1e-12
+    # Lambertian: unit direction in the normal's hemisphere (N + ball, normalised)
+    s = oracle.scatter({"type": "lambertian", "color": [0.2, 0.3, 0.4]}, (0, 0, 5), (0, 0, -1), (0, 0, 1), n, True, seed=2)
+    assert abs(np.linalg.norm(s["direction"]) - 1) < 1e-12 and s["direction"][2] > 0 and s["attenuation"].tolist() == [0.2, 0.3, 0.4]
+
+
+def test_trace_ray_known_radiance(oracle):
+    """One lambertian-free analytic case: a diffuse light sphere seen head-on returns emitted + ambient
+    (no scatter -> emitted + direct, renderer.go:181-184; direct = ambient 0.1 with no lights)."""
+    d = {"camera": {"position": [0, 0, 5], "aspectRatio": 1.0}, "lights": [],
+         "objects": [{"type": "sphere", "position": [0, 0, 0], "radius": 1.0, "material": {"type": "diffuselight", "color": [0.5, 0.25, 2.0]}}]}
+    _, rad, _ = oracle.Scene(d).render(8, 8, samples=1, max_depth=5, jitter=False, want_radiance=True)
+    assert np.allclose(rad[4, 4], (0.6, 0.35, 2.1))
+    assert rad[0, 0].tolist() == [0, 0, 0]  # miss -> black, not skyColor (renderer.go:171-173)
