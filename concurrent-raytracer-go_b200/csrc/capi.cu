@@ -37,7 +37,9 @@ struct DeviceState {
     // per-frame buffers
     unsigned long long* d_accum = nullptr;
     size_t accum_tiles = 0;
-    unsigned int* d_counter = nullptr;
+    unsigned int* d_counter = nullptr;  // [0] work counter, [1] active block count
+    uint32_t* d_active = nullptr;       // active pixel-block list
+    size_t active_bytes = 0;
     unsigned long long* d_stats = nullptr;
     uint8_t* d_out = nullptr;  // frame (row-major) or slab (tile-major)
     size_t out_bytes = 0;
@@ -154,6 +156,8 @@ void pack_material(const HostMaterial& m, F4 out[4]) {
         fs = 0.4 + m.specular * 0.4;
     } else if (m.type == GORT_MAT_PERFECTMIRROR) {
         fs = 0.9;
+    } else if (m.type == GORT_MAT_GLASS || m.type == GORT_MAT_DIELECTRIC) {
+        fs = 1.0 / ior;  // refractionRatio on the front face (advanced_materials.go:25-29, material.go:239-243)
     }
     out[0] = F4{as_float(m.type), (float)color[0], (float)color[1], (float)color[2]};
     out[1] = F4{(float)m.roughness, (float)metallic, (float)m.specular, (float)ior};
@@ -281,7 +285,8 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
 
     CUDA_TRY(ctx, cudaEventRecord(d.ev[0], st));
     if (accum_want) CUDA_TRY(ctx, cudaMemsetAsync(d.d_accum, 0, accum_want, st));
-    CUDA_TRY(ctx, cudaMemsetAsync(d.d_counter, 0, sizeof(unsigned int), st));
+    CUDA_TRY(ctx, cudaMemsetAsync(d.d_counter, 0, 2 * sizeof(unsigned int), st));
+    if (int rc = ensure(ctx, d.d_active, d.active_bytes, (size_t)n_local * 32 * sizeof(uint32_t))) return rc;
     if (p->collect_stats) CUDA_TRY(ctx, cudaMemsetAsync(d.d_stats, 0, kStatCount * sizeof(unsigned long long), st));
     if (slab_mode && slab_bytes > (size_t)n_local * kTilePixels * 4)
         CUDA_TRY(ctx, cudaMemsetAsync(out + (size_t)n_local * kTilePixels * 4, 0, slab_bytes - (size_t)n_local * kTilePixels * 4, st));
@@ -296,14 +301,9 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     tp.jitter = p->anti_aliasing ? 1 : 0; tp.recursive = p->recursive_reflections ? 1 : 0; tp.soft = p->soft_shadows ? 1 : 0;
     tp.tiles_x = tiles_x; tp.tiles_y = tiles_y;
     tp.shard_rank = eff_rank; tp.shard_count = eff_count; tp.n_local_tiles = n_local;
-    // work units: (sample batch, tile, 8x4 block); aim for >= 8 units per resident warp
-    const long long blocks = (long long)n_local * 32;
-    const long long target_units = 8LL * d.sm_count * 2 * 8;
-    const long long min_batches = blocks > 0 ? (target_units + blocks - 1) / blocks : 1;
-    int spu = (int)std::max<long long>(1, std::min<long long>(16, p->samples / std::max<long long>(1, min_batches)));
-    tp.samples_per_unit = spu;
-    tp.n_batches = (p->samples + spu - 1) / spu;
-    tp.n_units = (uint32_t)(blocks * tp.n_batches);
+    // work units = (sample batch, active 8x4 block), sized on the device: aim for >= 8 per resident warp
+    tp.target_units = 8u * (uint32_t)d.sm_count * 2u * 8u;
+    tp.active_list = d.d_active; tp.active_count = d.d_counter + 1;
     tp.accum = d.d_accum; tp.work_counter = d.d_counter; tp.stats = p->collect_stats ? d.d_stats : nullptr;
     const uint32_t k0 = (uint32_t)p->seed, k1 = (uint32_t)(p->seed >> 32);
     for (int r = 0; r < 10; r++) {
@@ -313,6 +313,7 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     tp.fog_enabled = ctx->scene.fog_enabled;
     tp.fog_density = (float)ctx->scene.fog_density;
     tp.fog_r = (float)ctx->scene.fog_color[0]; tp.fog_g = (float)ctx->scene.fog_color[1]; tp.fog_b = (float)ctx->scene.fog_color[2];
+    CUDA_TRY(ctx, launch_cull(tp, d.d_active, d.d_counter + 1, st));
     CUDA_TRY(ctx, launch_trace(tp, p->collect_stats != 0, d.sm_count, st));
     CUDA_TRY(ctx, cudaEventRecord(d.ev[1], st));
 
@@ -456,7 +457,7 @@ void gort_destroy(gort_ctx* ctx) {
         cudaSetDevice(d.dev);
         if (d.own_stream) cudaStreamSynchronize(d.own_stream);
         free_scene(d);
-        cudaFree(d.d_accum); cudaFree(d.d_counter); cudaFree(d.d_stats); cudaFree(d.d_out); cudaFree(d.d_gather);
+        cudaFree(d.d_accum); cudaFree(d.d_active); cudaFree(d.d_counter); cudaFree(d.d_stats); cudaFree(d.d_out); cudaFree(d.d_gather);
         if (d.h_pinned) cudaFreeHost(d.h_pinned);
         for (auto& e : d.ev)
             if (e) cudaEventDestroy(e);

@@ -46,11 +46,29 @@ __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, fl
     return fmaf(az, bz, fmaf(ay, by, ax * bx));
 }
 
+// Single-MUFU approximations (<= 2 ulp).  IEEE-rounded 1/x and sqrt expand to ~10 instructions each
+// and were ~18 % of all issued instructions in the first profile (profiles/r1_trace_v0_summary.md);
+// fp32 against the float64 reference already differs by more than these 2 ulp.
+__device__ __forceinline__ float rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rsqrt_fast(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sqrt_fast(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // Vec3.Normalize (vector.go:61-67): zero vector stays zero.
 __device__ __forceinline__ void normalize3(float& x, float& y, float& z) {
-    float l2 = dot3(x, y, z, x, y, z);
-    float l = sqrtf(l2);
-    float inv = l > 0.f ? 1.0f / l : 0.f;
+    const float l2 = dot3(x, y, z, x, y, z);
+    const float inv = l2 > 0.f ? rsqrt_fast(l2) : 0.f;
     x *= inv;
     y *= inv;
     z *= inv;
@@ -113,12 +131,12 @@ __device__ __forceinline__ bool traverse(const SceneView& S, float ox, float oy,
     stat_add<STATS>(st, ANY ? kStatShadow : kStatClosest);
     if (S.n_nodes == 0) return false;
     const float ooeps = 8.27180613e-25f;  // 2^-80
-    const float idx = 1.0f / (fabsf(dx) > ooeps ? dx : copysignf(ooeps, dx));
-    const float idy = 1.0f / (fabsf(dy) > ooeps ? dy : copysignf(ooeps, dy));
-    const float idz = 1.0f / (fabsf(dz) > ooeps ? dz : copysignf(ooeps, dz));
+    const float idx = rcp_fast(fabsf(dx) > ooeps ? dx : copysignf(ooeps, dx));
+    const float idy = rcp_fast(fabsf(dy) > ooeps ? dy : copysignf(ooeps, dy));
+    const float idz = rcp_fast(fabsf(dz) > ooeps ? dz : copysignf(ooeps, dz));
     const float oodx = ox * idx, oody = oy * idy, oodz = oz * idz;
     const float a = dot3(dx, dy, dz, dx, dy, dz);  // ray.Direction.LengthSquared() sphere.go:24
-    const float inv_a = 1.0f / a;
+    const float inv_a = rcp_fast(a);
 
     int stack[64];
     int sp = 0;
@@ -179,7 +197,7 @@ __device__ __forceinline__ bool traverse(const SceneView& S, float ox, float oy,
                     const float lx = fmaf(-k, dx, ocx), ly = fmaf(-k, dy, ocy), lz = fmaf(-k, dz, ocz);
                     const float dn = fmaf(s.w, s.w, -dot3(lx, ly, lz, lx, ly, lz));
                     if (dn < 0.f) continue;
-                    const float sq = sqrtf(dn * a);
+                    const float sq = sqrt_fast(dn * a);
                     float root = (-hb - sq) * inv_a;
                     if (ANY) {
                         if (!(root < tmin || tmax < root)) { stat_add<STATS>(st, kStatSphereHits); return true; }
@@ -209,7 +227,7 @@ __device__ __forceinline__ bool traverse(const SceneView& S, float ox, float oy,
                     const float hx = dy * e2.z - dz * e2.y, hy = dz * e2.x - dx * e2.z, hz = dx * e2.y - dy * e2.x;
                     const float aa = dot3(e1.x, e1.y, e1.z, hx, hy, hz);
                     if (aa > -1e-6f && aa < 1e-6f) { stat_add<STATS>(st, kStatTriRejA); continue; }
-                    const float f = 1.0f / aa;
+                    const float f = rcp_fast(aa);
                     const float sx = ox - v0.x, sy = oy - v0.y, sz = oz - v0.z;
                     const float u = f * dot3(sx, sy, sz, hx, hy, hz);
                     if (u < 0.0f || u > 1.0f) { stat_add<STATS>(st, kStatTriRejU); continue; }
@@ -330,6 +348,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) trace_kernel(const __gri
     float fx = 0.f, fy = 0.f;
     bool lane_valid = false;
     const float inv_w = 1.0f / (float)P.width, inv_h = 1.0f / (float)P.height;
+    // Work units are sized on the device from the number of pixel blocks the cull pass kept:
+    // enough units for dynamic balance (target_units), at most 16 samples each.
+    const uint32_t n_active = *P.active_count;
+    if (n_active == 0) return;
+    int spu;
+    {
+        const uint32_t want_batches = (P.target_units + n_active - 1) / n_active;
+        spu = max(1, min(16, P.samples / (int)max(1u, want_batches)));
+    }
+    const uint32_t n_units = n_active * (uint32_t)((P.samples + spu - 1) / spu);
+    bool jit_valid = false;
+    uint32_t jit_z = 0, jit_w = 0;
 
     for (;;) {
         // ================= FILL: primary rays (tracePixel renderer.go:150-163, getRay :377-390) =========
@@ -339,15 +369,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) trace_kernel(const __gri
                 uint32_t u = 0;
                 if (lane == 0) u = atomicAdd(P.work_counter, 1u);
                 u = __shfl_sync(FULL_MASK, u, 0);
-                if (u >= P.n_units) {
+                if (u >= n_units) {
                     more_units = false;
                     break;
                 }
-                // unit = (batch, local tile, 8x4 block); batch-major so heavy pixels spread over time
-                const uint32_t per_batch = (uint32_t)P.n_local_tiles * 32u;
-                const uint32_t batch = u / per_batch;
-                const uint32_t rem = u - batch * per_batch;
-                const uint32_t ltile = rem >> 5, block = rem & 31u;
+                // unit = (sample batch, active 8x4 block); batch-major so heavy pixels spread over time
+                const uint32_t batch = u / n_active;
+                const uint32_t packed = __ldg(P.active_list + (u - batch * n_active));
+                const uint32_t ltile = packed >> 5, block = packed & 31u;
                 const uint32_t gtile = (uint32_t)P.shard_rank + ltile * (uint32_t)P.shard_count;
                 const uint32_t tx = gtile % (uint32_t)P.tiles_x, ty = gtile / (uint32_t)P.tiles_x;
                 const uint32_t lx = ((block & 3u) << 3) + (lane & 7u), ly = ((block >> 2) << 2) + (lane >> 3);
@@ -357,18 +386,29 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) trace_kernel(const __gri
                 pixl = ltile * kTilePixels + ly * kTile + lx;
                 fx = (float)x;
                 fy = (float)y;
-                s_cur = (int)batch * P.samples_per_unit;
-                s_end = min(s_cur + P.samples_per_unit, P.samples);
+                s_cur = (int)batch * spu;
+                s_end = min(s_cur + spu, P.samples);
+                jit_valid = false;
             }
             PathState ps;
             bool hit = false;
             if (lane_valid) {
                 float ju = 0.5f, jv = 0.5f;
                 if (P.jitter) {
-                    const uint4 r = philox(P.rk, pixg, (uint32_t)s_cur, kStreamJitter, 0u);
-                    stat_add<STATS>(st, kStatRngBlocks);
-                    ju = (float)(r.x >> 8) * (1.0f / 16777216.0f);
-                    jv = (float)(r.y >> 8) * (1.0f / 16777216.0f);
+                    // one Philox block serves two consecutive samples: (x,y) the even one, (z,w) the odd one
+                    uint32_t jx, jy;
+                    if ((s_cur & 1) && jit_valid) {
+                        jx = jit_z; jy = jit_w;
+                    } else {
+                        const uint4 r = philox(P.rk, pixg, (uint32_t)s_cur >> 1, kStreamJitter, 0u);
+                        stat_add<STATS>(st, kStatRngBlocks);
+                        jit_z = r.z; jit_w = r.w;
+                        jx = (s_cur & 1) ? r.z : r.x;
+                        jy = (s_cur & 1) ? r.w : r.y;
+                    }
+                    jit_valid = !(s_cur & 1);
+                    ju = (float)(jx >> 8) * (1.0f / 16777216.0f);
+                    jv = (float)(jy >> 8) * (1.0f / 16777216.0f);
                 }
                 const float u = (fx + ju) * inv_w, v = (fy + jv) * inv_h;
                 ps.ox = P.cam.ox; ps.oy = P.cam.oy; ps.oz = P.cam.oz;
@@ -386,7 +426,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) trace_kernel(const __gri
                 ps.pixg = pixg; ps.pixl = pixl; ps.sample = (uint32_t)s_cur; ps.depth = 0;
                 ps.fog = 0.f;
                 if (P.fog_enabled) {
-                    const float dist = ps.t * sqrtf(dot3(ps.dx, ps.dy, ps.dz, ps.dx, ps.dy, ps.dz));
+                    const float dist = ps.t * sqrt_fast(dot3(ps.dx, ps.dy, ps.dz, ps.dx, ps.dy, ps.dz));
                     ps.fog = 1.0f - expf(-P.fog_density * dist);
                 }
                 queue_store(Q, qcount + __popc(hm & ((1u << lane) - 1u)), ps);
@@ -411,7 +451,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) trace_kernel(const __gri
         int mat;
         if (ps.prim >= 0) {
             const float4 s = ldg4(S.spheres + ps.prim);
-            const float inv_r = 1.0f / s.w;
+            const float inv_r = rcp_fast(s.w);
             nx = (px - s.x) * inv_r; ny = (py - s.y) * inv_r; nz = (pz - s.z) * inv_r;
             mat = __ldg(&S.sphere_meta[ps.prim]).x;
         } else {
@@ -437,8 +477,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) trace_kernel(const __gri
         for (int l = 0; l < S.n_lights; l++) {
             const float4 L0 = ldg4(S.lights + 2 * l), L1 = ldg4(S.lights + 2 * l + 1);
             float ldx = L0.x - px, ldy = L0.y - py, ldz = L0.z - pz;
-            const float dist = sqrtf(dot3(ldx, ldy, ldz, ldx, ldy, ldz));
-            const float inv_d = dist > 0.f ? 1.0f / dist : 0.f;
+            const float dist2 = dot3(ldx, ldy, ldz, ldx, ldy, ldz);
+            const float inv_d = dist2 > 0.f ? rsqrt_fast(dist2) : 0.f;
+            const float dist = dist2 * inv_d;
             ldx *= inv_d; ldy *= inv_d; ldz *= inv_d;
             const bool consider = act && !(dist < 0.001f);
             // ---- calculateSmartShadow (renderer.go:299-331): hard ray first ----
@@ -490,7 +531,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) trace_kernel(const __gri
             if (factor > 0.0f) {
                 stat_add<STATS>(st, kStatDiffuse);
                 const float cosT = fmaxf(0.f, dot3(nx, ny, nz, ldx, ldy, ldz));
-                const float inten = cosT * L0.w / (dist * dist);
+                const float inten = cosT * L0.w * (inv_d * inv_d);
                 const float kdw = m2.y * inten * factor;
                 dr = fmaf(alr, kdw, dr); dg = fmaf(alg, kdw, dg); db = fmaf(alb, kdw, db);
                 if (m3.x > 0.f) {  // metallic > 0.5, resolved in float64 on the host
@@ -548,16 +589,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) trace_kernel(const __gri
                 }
             } else if (mtype <= 5) {  // Glass / Dielectric (advanced_materials.go:21-46; material.go:235-260)
                 ar = m0.y; ag = m0.z; ab = m0.w;  // Glass colour; Dielectric packed as (1,1,1)
-                const float ratio = front ? 1.0f / m1.w : m1.w;
+                const float ratio = front ? m3.z : m1.w;  // 1/ior precomputed in float64 on the host
                 float ux = ps.dx, uy = ps.dy, uz = ps.dz;
                 normalize3(ux, uy, uz);
                 const float udn = dot3(ux, uy, uz, nx, ny, nz);
                 const float cosT = fminf(-udn, 1.0f);
-                const float sinT = sqrtf(1.0f - cosT * cosT);
+                const float sinT = sqrt_fast(1.0f - cosT * cosT);
                 bool reflect = ratio * sinT > 1.0f;  // cannotRefract
                 if (!reflect) {
-                    float r0 = (1.0f - ratio) / (1.0f + ratio);
-                    r0 = r0 * r0;
+                    const float r0 = m3.y;  // ((1-x)/(1+x))^2 is the same for x = ior and x = 1/ior
                     const float refl = fmaf(1.0f - r0, pow5(1.0f - cosT), r0);  // reflectance material.go:282-286
                     const uint4 r = philox(P.rk, ps.pixg, ps.sample, bs, 0u);
                     stat_add<STATS>(st, kStatRngBlocks);
@@ -568,13 +608,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) trace_kernel(const __gri
                 } else {
                     // Vec3.Refract (vector.go:81-96) with v = unit direction, normal against the ray
                     float cn = udn, eta = ratio, rnx = nx, rny = ny, rnz = nz;
-                    if (cn > 0.f) { rnx = -nx; rny = -ny; rnz = -nz; eta = 1.0f / eta; cn = -cn; }
+                    if (cn > 0.f) { rnx = -nx; rny = -ny; rnz = -nz; eta = rcp_fast(eta); cn = -cn; }
                     const float sin2 = eta * eta * (1.0f - cn * cn);
                     if (sin2 > 1.0f) {
                         const float d2 = dot3(ux, uy, uz, rnx, rny, rnz);
                         sx = fmaf(-2.0f * d2, rnx, ux); sy = fmaf(-2.0f * d2, rny, uy); sz = fmaf(-2.0f * d2, rnz, uz);
                     } else {
-                        const float k = fmaf(eta, cn, sqrtf(1.0f - sin2));
+                        const float k = fmaf(eta, cn, sqrt_fast(1.0f - sin2));
                         sx = fmaf(eta, ux, -k * rnx); sy = fmaf(eta, uy, -k * rny); sz = fmaf(eta, uz, -k * rnz);
                     }
                 }
@@ -622,12 +662,148 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) trace_kernel(const __gri
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// cull pass: which 8x4 pixel blocks can see geometry at all?
+//
+// Every primary ray of a block (all samples, any jitter) has a direction that is an affine function
+// of (u,v) over the block's rectangle, so it lies inside the pyramid spanned by the four corner
+// directions.  The pyramid is walked down the BVH with the conservative plane/box test (a box is
+// rejected only when it lies entirely behind one side plane); reaching a primitive whose own bound
+// (sphere: centre/radius, triangle: vertices) survives marks the block active.  Blocks that are
+// culled would only have produced misses (black, renderer.go:171-173), so the image is unchanged;
+// in the reference's own scenes 97-100 % of the blocks are culled.
+// ---------------------------------------------------------------------------------------------
+struct Beam {
+    float ox, oy, oz;
+    float nx[4], ny[4], nz[4];  // inward side-plane normals
+};
+
+__device__ __forceinline__ bool beam_box_outside(const Beam& B, float lox, float hix, float loy, float hiy, float loz, float hiz) {
+    const float ax = fmaxf(fabsf(lox - B.ox), fabsf(hix - B.ox)), ay = fmaxf(fabsf(loy - B.oy), fabsf(hiy - B.oy)),
+                az = fmaxf(fabsf(loz - B.oz), fabsf(hiz - B.oz));
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float px = (B.nx[i] >= 0.f ? hix : lox) - B.ox, py = (B.ny[i] >= 0.f ? hiy : loy) - B.oy, pz = (B.nz[i] >= 0.f ? hiz : loz) - B.oz;
+        const float d = dot3(B.nx[i], B.ny[i], B.nz[i], px, py, pz);
+        const float tol = 4e-6f * (fabsf(B.nx[i]) * ax + fabsf(B.ny[i]) * ay + fabsf(B.nz[i]) * az);
+        if (d < -tol) return true;
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(128) cull_kernel(const __grid_constant__ TraceParams P, uint32_t* __restrict__ active_list,
+                                                    unsigned int* __restrict__ active_count) {
+    const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= (uint32_t)P.n_local_tiles * 32u) return;
+    const SceneView& S = P.scene;
+    if (S.n_nodes == 0 || P.max_depth <= 0) return;
+    const uint32_t ltile = id >> 5, block = id & 31u;
+    const uint32_t gtile = (uint32_t)P.shard_rank + ltile * (uint32_t)P.shard_count;
+    const uint32_t tx = gtile % (uint32_t)P.tiles_x, ty = gtile / (uint32_t)P.tiles_x;
+    const uint32_t x0 = tx * kTile + ((block & 3u) << 3), y0 = ty * kTile + ((block >> 2) << 2);
+    if (x0 >= (uint32_t)P.width || y0 >= (uint32_t)P.height) return;
+    const uint32_t x1 = min(x0 + 8u, (uint32_t)P.width), y1 = min(y0 + 4u, (uint32_t)P.height);
+    // (u,v) rectangle of every sample of the block, widened by a rounding margin
+    const float u0 = ((float)x0 - 1e-3f) / (float)P.width, u1 = ((float)x1 + 1e-3f) / (float)P.width;
+    const float v0 = ((float)y0 - 1e-3f) / (float)P.height, v1 = ((float)y1 + 1e-3f) / (float)P.height;
+    const DevCamera& C = P.cam;
+    float cx[4], cy[4], cz[4];
+    const float uu[4] = {u0, u1, u1, u0}, vv[4] = {v0, v0, v1, v1};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        cx[i] = fmaf(vv[i], C.vx, fmaf(uu[i], C.hx, C.llx));
+        cy[i] = fmaf(vv[i], C.vy, fmaf(uu[i], C.hy, C.lly));
+        cz[i] = fmaf(vv[i], C.vz, fmaf(uu[i], C.hz, C.llz));
+    }
+    const float mx = 0.25f * (cx[0] + cx[1] + cx[2] + cx[3]), my = 0.25f * (cy[0] + cy[1] + cy[2] + cy[3]), mz = 0.25f * (cz[0] + cz[1] + cz[2] + cz[3]);
+    Beam B;
+    B.ox = C.ox; B.oy = C.oy; B.oz = C.oz;
+    bool degenerate = false;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int j = (i + 1) & 3;
+        float nx = cy[i] * cz[j] - cz[i] * cy[j], ny = cz[i] * cx[j] - cx[i] * cz[j], nz = cx[i] * cy[j] - cy[i] * cx[j];
+        const float sgn = dot3(nx, ny, nz, mx, my, mz);
+        if (!(fabsf(sgn) > 0.f)) degenerate = true;  // collapsed pyramid (zero-area viewport): keep the block
+        if (sgn < 0.f) { nx = -nx; ny = -ny; nz = -nz; }
+        B.nx[i] = nx; B.ny[i] = ny; B.nz[i] = nz;
+    }
+    bool active = degenerate;
+    int stack[64];
+    int sp = 0;
+    int node = 0;
+    while (!active) {
+        if (node >= 0) {
+            const float4* np = S.nodes + 4 * (size_t)node;
+            const float4 n0 = ldg4(np), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3);
+            const bool h0 = !beam_box_outside(B, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y);
+            const bool h1 = !beam_box_outside(B, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w);
+            const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+            if (h0 && h1) {
+                stack[sp++] = c1;
+                node = c0;
+            } else if (h0) {
+                node = c0;
+            } else if (h1) {
+                node = c1;
+            } else {
+                if (sp == 0) break;
+                node = stack[--sp];
+            }
+        } else {
+            const uint32_t v = ~(uint32_t)node;
+            const uint32_t start = v & 0x3FFFFFFu;
+            const int cnt = (int)((v >> 26) & 15u) + 1;
+            if (((v >> 30) & 1u) == 0) {
+                for (int i = 0; i < cnt && !active; i++) {
+                    const float4 s = ldg4(S.spheres + start + i);
+                    const float px = s.x - B.ox, py = s.y - B.oy, pz = s.z - B.oz;
+                    const float r = fabsf(s.w) * 1.00001f + 1e-6f * (fabsf(px) + fabsf(py) + fabsf(pz));
+                    bool out = false;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const float d = dot3(B.nx[k], B.ny[k], B.nz[k], px, py, pz);
+                        const float nl = sqrtf(dot3(B.nx[k], B.ny[k], B.nz[k], B.nx[k], B.ny[k], B.nz[k]));
+                        if (d < -r * nl) out = true;
+                    }
+                    if (!out) active = true;
+                }
+            } else {
+                for (int i = 0; i < cnt && !active; i++) {
+                    const float4* tp = S.tris + 4 * (size_t)(start + i);
+                    const float4 a = ldg4(tp), e1 = ldg4(tp + 1), e2 = ldg4(tp + 2);
+                    const float ax = a.x - B.ox, ay = a.y - B.oy, az = a.z - B.oz;
+                    const float ext = 1e-5f * (fabsf(ax) + fabsf(ay) + fabsf(az) + fabsf(e1.x) + fabsf(e1.y) + fabsf(e1.z) + fabsf(e2.x) + fabsf(e2.y) + fabsf(e2.z));
+                    bool out = false;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const float nl = fabsf(B.nx[k]) + fabsf(B.ny[k]) + fabsf(B.nz[k]);
+                        const float d0 = dot3(B.nx[k], B.ny[k], B.nz[k], ax, ay, az);
+                        const float d1 = d0 + dot3(B.nx[k], B.ny[k], B.nz[k], e1.x, e1.y, e1.z);
+                        const float d2 = d0 + dot3(B.nx[k], B.ny[k], B.nz[k], e2.x, e2.y, e2.z);
+                        if (fmaxf(d0, fmaxf(d1, d2)) < -ext * nl) out = true;
+                    }
+                    if (!out) active = true;
+                }
+            }
+            if (active || sp == 0) break;
+            node = stack[--sp];
+        }
+    }
+    if (active) active_list[atomicAdd(active_count, 1u)] = id;
+}
+
+cudaError_t launch_cull(const TraceParams& p, uint32_t* active_list, unsigned int* active_count, cudaStream_t stream) {
+    const unsigned int n = (unsigned int)p.n_local_tiles * 32u;
+    if (n == 0) return cudaSuccess;
+    cull_kernel<<<(n + 127) / 128, 128, 0, stream>>>(p, active_list, active_count);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_trace(const TraceParams& p, bool stats, int sm_count, cudaStream_t stream) {
-    if (p.n_units == 0) return cudaSuccess;
+    if (p.n_local_tiles == 0) return cudaSuccess;
     const int threads = kWarpsPerCta * 32;
     int blocks = sm_count * 2;  // persistent: 2 resident CTAs per SM (launch bounds)
-    const unsigned int need = (p.n_units + kWarpsPerCta - 1) / kWarpsPerCta;
-    if ((unsigned int)blocks > need) blocks = (int)need;
     if (stats) trace_kernel<true><<<blocks, threads, 0, stream>>>(p);
     else trace_kernel<false><<<blocks, threads, 0, stream>>>(p);
     return cudaGetLastError();

@@ -60,8 +60,9 @@ struct TraceParams {
     int jitter, recursive, soft;
     int tiles_x, tiles_y;
     int shard_rank, shard_count, n_local_tiles;
-    int samples_per_unit, n_batches;
-    uint32_t n_units;
+    uint32_t target_units;           // desired number of work units (dynamic balance), see trace_kernel
+    const uint32_t* active_list;     // pixel blocks kept by the cull pass: (local tile << 5) | block
+    const unsigned int* active_count;
     unsigned long long* accum;   // [n_local_tiles][1024][3] int64 fixed point
     unsigned int* work_counter;  // zeroed before launch
     unsigned long long* stats;   // [kStatCount] or nullptr
@@ -79,6 +80,7 @@ struct ResolveParams {
 };
 
 // All launchers enqueue on `stream` and return the launch error (no synchronisation).
+cudaError_t launch_cull(const TraceParams& p, uint32_t* active_list, unsigned int* active_count, cudaStream_t stream);
 cudaError_t launch_trace(const TraceParams& p, bool stats, int sm_count, cudaStream_t stream);
 cudaError_t launch_resolve(const ResolveParams& p, cudaStream_t stream);
 cudaError_t launch_unswizzle(const uint8_t* slabs, int shard_count, int width, int height, uint8_t* rgba, cudaStream_t stream);

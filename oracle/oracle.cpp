@@ -704,7 +704,13 @@ struct Tracer {
             double ju = 0.5, jv = 0.5;
             if (p.jitter) {
                 if (rng.mode == RNG_MT) { ju = rng.mt_float(); jv = rng.mt_float(); }
-                else { ju = rng.uniform(STREAM_JITTER, 0, 0); jv = rng.uniform(STREAM_JITTER, 0, 1); }
+                else {
+                    // one Philox block serves two consecutive samples: lanes (0,1) the even one, (2,3) the odd one
+                    rng.sample = (uint32_t)s >> 1;
+                    ju = rng.uniform(STREAM_JITTER, 0, (s & 1) * 2);
+                    jv = rng.uniform(STREAM_JITTER, 0, (s & 1) * 2 + 1);
+                    rng.sample = (uint32_t)s;
+                }
             }
             double u = ((double)x + ju) / (double)p.width;
             double v = ((double)y + jv) / (double)p.height;
