@@ -226,12 +226,46 @@ def test_philox_independent_python_restatement(oracle):
         assert oracle.philox4x32_10(ctr, key) == philox(ctr, key)
 
 
-def test_in_unit_sphere_distribution(oracle):  # vector.go:132-139: uniform in the open unit ball
-    pts = np.array([oracle.in_unit_sphere(3, i, 0, 0, oracle.STREAM_SHADOW, 0) for i in range(4000)])
+def _ball_moments(pts):
+    r = np.linalg.norm(pts, axis=1)
+    return {"r3_mean": (r ** 3).mean(), "mean": np.abs(pts.mean(axis=0)).max(), "z_over_r_var": ((pts[:, 2] / r) ** 2).mean(),
+            "x2": (pts[:, 0] ** 2).mean(), "y2": (pts[:, 1] ** 2).mean(), "z2": (pts[:, 2] ** 2).mean()}
+
+
+def test_in_unit_sphere_distribution(oracle):
+    """RandomVec3InUnitSphere (vector.go:132-139) is uniform in the open unit ball.  The Philox-mode sampler
+    (loop-free mapping shared with the CUDA path) must obey the same law: r^3 ~ U[0,1), direction isotropic,
+    E[x^2] = E[y^2] = E[z^2] = 1/5."""
+    n = 20000
+    pts = np.array([oracle.in_unit_sphere(3, i, 0, 0, oracle.STREAM_SHADOW, 0) for i in range(n)])
     r = np.linalg.norm(pts, axis=1)
     assert (r < 1).all()
-    assert abs((r ** 3).mean() - 0.5) < 0.03  # r^3 ~ U[0,1)
-    assert np.abs(pts.mean(axis=0)).max() < 0.03
+    m = _ball_moments(pts)
+    assert abs(m["r3_mean"] - 0.5) < 0.01 and m["mean"] < 0.012
+    assert abs(m["z_over_r_var"] - 1 / 3) < 0.01
+    for k in ("x2", "y2", "z2"):
+        assert abs(m[k] - 0.2) < 0.006
+    # Kolmogorov-Smirnov against the uniform law of r^3 and of the azimuth
+    from scipy import stats
+    assert stats.kstest(r ** 3, "uniform").pvalue > 1e-3
+    assert stats.kstest((np.arctan2(pts[:, 1], pts[:, 0]) + np.pi) / (2 * np.pi), "uniform").pvalue > 1e-3
+    assert stats.kstest((pts[:, 2] / r + 1) / 2, "uniform").pvalue > 1e-3
+
+
+def test_rejection_and_loop_free_samplers_agree(oracle):
+    """Reference-mode (mt19937 + the Go rejection loop) and Philox-mode renders of a rough-metal / lambertian
+    scene with soft shadows converge to the same image: the two unit-ball samplers are interchangeable."""
+    d = {"camera": {"position": [0, 0, 2.8], "aspectRatio": 1.0},
+         "objects": [{"type": "sphere", "position": [0, 0, 0], "radius": 1.2, "material": {"type": "metal", "color": [0.8, 0.6, 0.3], "roughness": 0.5, "metallic": 0.6}},
+                     {"type": "sphere", "position": [0.9, 0.9, 1.3], "radius": 0.35, "material": {"type": "lambertian", "color": [0.3, 0.7, 0.9]}}],
+         "lights": [{"position": [3, 3, 4], "color": [1, 1, 1], "intensity": 12}]}
+    s = oracle.Scene(d)
+    _, a, _ = s.render(32, 32, samples=1500, max_depth=6, rng_mode=oracle.RNG_MT, seed=5, want_radiance=True)
+    _, b, _ = s.render(32, 32, samples=1500, max_depth=6, rng_mode=oracle.RNG_PHILOX, seed=6, want_radiance=True)
+    lit = a.sum(-1) > 0
+    assert lit.sum() > 100
+    rel = np.abs(a[lit] - b[lit]).mean() / a[lit].mean()
+    assert rel < 0.01, rel
 
 
 def test_scatter_rules(oracle):
