@@ -34,6 +34,7 @@ struct DeviceState {
     float4* d_tris = nullptr;
     float4* d_mats = nullptr;
     float4* d_lights = nullptr;
+    size_t cap_nodes = 0, cap_spheres = 0, cap_meta = 0, cap_tris = 0, cap_mats = 0, cap_lights = 0;
     // per-frame buffers
     unsigned long long* d_accum = nullptr;
     size_t accum_tiles = 0;
@@ -106,6 +107,7 @@ void free_scene(DeviceState& d) {
     cudaFree(d.d_nodes); cudaFree(d.d_spheres); cudaFree(d.d_meta); cudaFree(d.d_tris); cudaFree(d.d_mats); cudaFree(d.d_lights);
     d.d_nodes = d.d_spheres = d.d_tris = d.d_mats = d.d_lights = nullptr;
     d.d_meta = nullptr;
+    d.cap_nodes = d.cap_spheres = d.cap_meta = d.cap_tris = d.cap_mats = d.cap_lights = 0;
 }
 
 float as_float(int32_t i) {
@@ -182,20 +184,19 @@ int upload_scene(gort_ctx* ctx) {
     for (size_t i = 0; i < ctx->devs.size(); i++) {
         DeviceState& d = ctx->devs[i];
         CUDA_TRY(ctx, cudaSetDevice(d.dev));
-        free_scene(d);
         cudaStream_t st = stream_of(ctx, (int)i);
-        auto up = [&](auto*& dst, const void* src, size_t bytes) -> cudaError_t {
-            cudaError_t e = cudaMalloc(&dst, std::max<size_t>(bytes, 16));
-            if (e != cudaSuccess) return e;
-            if (bytes) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
-            return e;
+        // device buffers are kept across uploads and only grow (a re-upload per frame costs no cudaMalloc)
+        auto up = [&](auto*& dst, size_t& cap, const void* src, size_t bytes) -> int {
+            if (int rc = ensure(ctx, dst, cap, bytes)) return rc;
+            if (bytes) CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+            return GORT_OK;
         };
-        CUDA_TRY(ctx, up(d.d_nodes, b.nodes.data(), b.nodes.size() * sizeof(F4)));
-        CUDA_TRY(ctx, up(d.d_spheres, b.spheres.data(), b.spheres.size() * sizeof(F4)));
-        CUDA_TRY(ctx, up(d.d_meta, b.sphere_meta.data(), b.sphere_meta.size() * sizeof(I2)));
-        CUDA_TRY(ctx, up(d.d_tris, b.tris.data(), b.tris.size() * sizeof(F4)));
-        CUDA_TRY(ctx, up(d.d_mats, mats.data(), mats.size() * sizeof(F4)));
-        CUDA_TRY(ctx, up(d.d_lights, lights.data(), lights.size() * sizeof(F4)));
+        if (int rc = up(d.d_nodes, d.cap_nodes, b.nodes.data(), b.nodes.size() * sizeof(F4))) return rc;
+        if (int rc = up(d.d_spheres, d.cap_spheres, b.spheres.data(), b.spheres.size() * sizeof(F4))) return rc;
+        if (int rc = up(d.d_meta, d.cap_meta, b.sphere_meta.data(), b.sphere_meta.size() * sizeof(I2))) return rc;
+        if (int rc = up(d.d_tris, d.cap_tris, b.tris.data(), b.tris.size() * sizeof(F4))) return rc;
+        if (int rc = up(d.d_mats, d.cap_mats, mats.data(), mats.size() * sizeof(F4))) return rc;
+        if (int rc = up(d.d_lights, d.cap_lights, lights.data(), lights.size() * sizeof(F4))) return rc;
         CUDA_TRY(ctx, cudaStreamSynchronize(st));  // host vectors go out of scope: the copies must be done
     }
     ctx->has_scene = true;
@@ -296,6 +297,7 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     tp.scene.nodes = d.d_nodes; tp.scene.spheres = d.d_spheres; tp.scene.sphere_meta = d.d_meta; tp.scene.tris = d.d_tris;
     tp.scene.mats = d.d_mats; tp.scene.lights = d.d_lights;
     tp.scene.n_nodes = ctx->bvh.n_nodes; tp.scene.n_lights = (int)ctx->scene.lights.size();
+    tp.scene.n_spheres = (int)ctx->scene.spheres.size(); tp.scene.n_tris = (int)ctx->scene.tris.size();
     tp.cam = make_camera(ctx->scene, p->camera_mode);
     tp.width = p->width; tp.height = p->height; tp.samples = p->samples; tp.max_depth = p->max_depth;
     tp.jitter = p->anti_aliasing ? 1 : 0; tp.recursive = p->recursive_reflections ? 1 : 0; tp.soft = p->soft_shadows ? 1 : 0;
@@ -638,9 +640,19 @@ int gort_render(gort_ctx* ctx, const gort_render_params* p, uint8_t* rgba_out, s
             if (int rc = render_frame_device(ctx, p, lead.d_out, t0, nullptr, false)) return rc;
         }
         CUDA_TRY(ctx, cudaSetDevice(lead.dev));
-        CUDA_TRY(ctx, cudaMemcpyAsync(lead.h_pinned, lead.d_out, frame_bytes, cudaMemcpyDeviceToHost, st0));
-        CUDA_TRY(ctx, cudaStreamSynchronize(st0));
-        memcpy(rgba_out, lead.h_pinned, frame_bytes);
+        // page-locked caller memory (cudaHostRegister / cudaMallocHost) takes the DMA directly;
+        // pageable memory (a Go slice) goes through the ctx's pinned staging buffer
+        cudaPointerAttributes pa;
+        const bool caller_pinned = cudaPointerGetAttributes(&pa, rgba_out) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (caller_pinned) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(rgba_out, lead.d_out, frame_bytes, cudaMemcpyDeviceToHost, st0));
+            CUDA_TRY(ctx, cudaStreamSynchronize(st0));
+        } else {
+            CUDA_TRY(ctx, cudaMemcpyAsync(lead.h_pinned, lead.d_out, frame_bytes, cudaMemcpyDeviceToHost, st0));
+            CUDA_TRY(ctx, cudaStreamSynchronize(st0));
+            memcpy(rgba_out, lead.h_pinned, frame_bytes);
+        }
     } else {
         // process-level shard with a host destination: render the slab, copy back, write own tiles only
         if (ctx->devs.size() != 1) return fail(ctx, GORT_ERR_INVALID, "a multi-device ctx renders whole frames (shard_count must be 1)");
@@ -733,6 +745,7 @@ int gort_trace_rays(gort_ctx* ctx, int32_t n, const double* origins3, const doub
     SceneView sv;
     sv.nodes = d.d_nodes; sv.spheres = d.d_spheres; sv.sphere_meta = d.d_meta; sv.tris = d.d_tris; sv.mats = d.d_mats; sv.lights = d.d_lights;
     sv.n_nodes = ctx->bvh.n_nodes; sv.n_lights = (int)ctx->scene.lights.size();
+    sv.n_spheres = (int)ctx->scene.spheres.size(); sv.n_tris = (int)ctx->scene.tris.size();
     const float tmax_f = std::isinf(t_max) ? INFINITY : (float)t_max;
     CUDA_TRY(ctx, launch_trace_rays(sv, n, d_o, d_d, (float)t_min, tmax_f, any_hit, d_t, d_ord, st));
     std::vector<float> ht(n);

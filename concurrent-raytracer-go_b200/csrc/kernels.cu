@@ -133,25 +133,116 @@ __device__ __forceinline__ int prim_order(const SceneView& S, int prim) {
     return __float_as_int(ldg4(S.tris + 4 * (size_t)(prim & 0x7fffffff) + 1).w);
 }
 
+struct RayQuery {
+    float ox, oy, oz, dx, dy, dz;
+    float a, inv_a;      // |d|^2 and its reciprocal (ray.Direction.LengthSquared(), sphere.go:24)
+    float tmin, tbest;   // tbest starts at tMax and shrinks (closestT, renderer.go:335-341)
+    int best;
+    bool found;
+};
+
+// ---- Sphere.Hit (geometry/sphere.go:22-59) for spheres [start, start+cnt) ----
 template <bool ANY, bool STATS>
+__device__ __forceinline__ bool test_spheres(const SceneView& S, RayQuery& q, uint32_t start, int cnt, Stats& st) {
+    for (int i = 0; i < cnt; i++) {
+        stat_add<STATS>(st, kStatSphereTests);
+        const float4 s = ldg4(S.spheres + start + i);
+        const float ocx = q.ox - s.x, ocy = q.oy - s.y, ocz = q.oz - s.z;
+        const float hb = dot3(ocx, ocy, ocz, q.dx, q.dy, q.dz);
+        // discriminant/a from the component of oc perpendicular to the ray: the same quantity as
+        // halfB^2 - a*c (sphere.go:28) without fp32 cancellation.
+        const float k = hb * q.inv_a;
+        const float lx = fmaf(-k, q.dx, ocx), ly = fmaf(-k, q.dy, ocy), lz = fmaf(-k, q.dz, ocz);
+        const float dn = fmaf(s.w, s.w, -dot3(lx, ly, lz, lx, ly, lz));
+        if (dn < 0.f) continue;
+        const float sq = sqrt_fast(dn * q.a);
+        float root = (-hb - sq) * q.inv_a;
+        if (ANY) {
+            if (!(root < q.tmin || q.tbest < root)) { stat_add<STATS>(st, kStatSphereHits); return true; }
+            root = (-hb + sq) * q.inv_a;
+            if (!(root < q.tmin || q.tbest < root)) { stat_add<STATS>(st, kStatSphereHits); return true; }
+        } else {
+            if (root < q.tmin || q.tbest < root) {
+                root = (-hb + sq) * q.inv_a;
+                if (root < q.tmin || q.tbest < root) continue;
+            }
+            stat_add<STATS>(st, kStatSphereHits);
+            const int pr = (int)(start + i);
+            if (root == q.tbest && q.found) {
+                if (prim_order(S, pr) < prim_order(S, q.best)) continue;
+            }
+            q.tbest = root;
+            q.best = pr;
+            q.found = true;
+        }
+    }
+    return false;
+}
+
+// ---- Triangle.Hit (geometry/triangle.go:36-88), Moller-Trumbore, for triangles [start, start+cnt) ----
+template <bool ANY, bool STATS>
+__device__ __forceinline__ bool test_tris(const SceneView& S, RayQuery& q, uint32_t start, int cnt, Stats& st) {
+    for (int i = 0; i < cnt; i++) {
+        stat_add<STATS>(st, kStatTriTests);
+        const float4* tp = S.tris + 4 * (size_t)(start + i);
+        const float4 v0 = ldg4(tp), e1 = ldg4(tp + 1), e2 = ldg4(tp + 2);
+        const float hx = q.dy * e2.z - q.dz * e2.y, hy = q.dz * e2.x - q.dx * e2.z, hz = q.dx * e2.y - q.dy * e2.x;
+        const float aa = dot3(e1.x, e1.y, e1.z, hx, hy, hz);
+        if (aa > -1e-6f && aa < 1e-6f) { stat_add<STATS>(st, kStatTriRejA); continue; }
+        const float f = rcp_fast(aa);
+        const float sx = q.ox - v0.x, sy = q.oy - v0.y, sz = q.oz - v0.z;
+        const float u = f * dot3(sx, sy, sz, hx, hy, hz);
+        if (u < 0.0f || u > 1.0f) { stat_add<STATS>(st, kStatTriRejU); continue; }
+        const float qx = sy * e1.z - sz * e1.y, qy = sz * e1.x - sx * e1.z, qz = sx * e1.y - sy * e1.x;
+        const float vv = f * dot3(q.dx, q.dy, q.dz, qx, qy, qz);
+        if (vv < 0.0f || u + vv > 1.0f) { stat_add<STATS>(st, kStatTriRejV); continue; }
+        const float t = f * dot3(e2.x, e2.y, e2.z, qx, qy, qz);
+        if (t < q.tmin || t > q.tbest) { stat_add<STATS>(st, kStatTriRejT); continue; }
+        stat_add<STATS>(st, kStatTriHits);
+        if (ANY) return true;
+        const int pr = (int)((start + i) | 0x80000000u);
+        if (t == q.tbest && q.found) {
+            if (prim_order(S, pr) < prim_order(S, q.best)) continue;
+        }
+        q.tbest = t;
+        q.best = pr;
+        q.found = true;
+    }
+    return false;
+}
+
+// SMALL: scenes of a handful of primitives skip the BVH and run the reference's own linear scan
+// (renderer.go:337-343) — every lane tests the same primitive, so the loads are warp-uniform broadcasts
+// and there is no stack, no node fetch and no traversal divergence.
+template <bool ANY, bool STATS, bool SMALL>
 __device__ __forceinline__ bool traverse(const SceneView& S, float ox, float oy, float oz, float dx, float dy, float dz,
                                          float tmin, float tmax, float& t_out, int& prim_out, Stats& st) {
     stat_add<STATS>(st, ANY ? kStatShadow : kStatClosest);
+    RayQuery q;
+    q.ox = ox; q.oy = oy; q.oz = oz; q.dx = dx; q.dy = dy; q.dz = dz;
+    q.a = dot3(dx, dy, dz, dx, dy, dz);
+    q.inv_a = rcp_fast(q.a);
+    q.tmin = tmin; q.tbest = tmax; q.best = 0; q.found = false;
+
+    if (SMALL) {
+        if (test_spheres<ANY, STATS>(S, q, 0u, S.n_spheres, st)) return true;
+        if (test_tris<ANY, STATS>(S, q, 0u, S.n_tris, st)) return true;
+        if (ANY) return false;
+        t_out = q.tbest;
+        prim_out = q.best;
+        return q.found;
+    }
+
     if (S.n_nodes == 0) return false;
     const float ooeps = 8.27180613e-25f;  // 2^-80
     const float idx = rcp_fast(fabsf(dx) > ooeps ? dx : copysignf(ooeps, dx));
     const float idy = rcp_fast(fabsf(dy) > ooeps ? dy : copysignf(ooeps, dy));
     const float idz = rcp_fast(fabsf(dz) > ooeps ? dz : copysignf(ooeps, dz));
     const float oodx = ox * idx, oody = oy * idy, oodz = oz * idz;
-    const float a = dot3(dx, dy, dz, dx, dy, dz);  // ray.Direction.LengthSquared() sphere.go:24
-    const float inv_a = rcp_fast(a);
 
     int stack[64];
     int sp = 0;
     int node = 0;
-    float tbest = tmax;
-    int best = 0;
-    bool found = false;
 
     for (;;) {
         if (node >= 0) {
@@ -165,9 +256,9 @@ __device__ __forceinline__ bool traverse(const SceneView& S, float ox, float oy,
             const float c1loy = fmaf(n1.z, idy, -oody), c1hiy = fmaf(n1.w, idy, -oody);
             const float c1loz = fmaf(n2.z, idz, -oodz), c1hiz = fmaf(n2.w, idz, -oodz);
             const float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), tmin));
-            const float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), tbest));
+            const float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), q.tbest));
             const float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), tmin));
-            const float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), tbest));
+            const float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), q.tbest));
             // 1 + 2^-22 widening of the far side keeps the fp32 slab test conservative
             const bool h0 = t0n <= t0f * 1.0000002f;
             const bool h1 = t1n <= t1f * 1.0000002f;
@@ -193,81 +284,18 @@ __device__ __forceinline__ bool traverse(const SceneView& S, float ox, float oy,
             const uint32_t start = v & 0x3FFFFFFu;
             const int cnt = (int)((v >> 26) & 15u) + 1;
             if (((v >> 30) & 1u) == 0) {
-                // ---- Sphere.Hit (geometry/sphere.go:22-59) ----
-                for (int i = 0; i < cnt; i++) {
-                    stat_add<STATS>(st, kStatSphereTests);
-                    const float4 s = ldg4(S.spheres + start + i);
-                    const float ocx = ox - s.x, ocy = oy - s.y, ocz = oz - s.z;
-                    const float hb = dot3(ocx, ocy, ocz, dx, dy, dz);
-                    // discriminant/a from the component of oc perpendicular to the ray: the same
-                    // quantity as halfB^2 - a*c (sphere.go:28) without fp32 cancellation.
-                    const float k = hb * inv_a;
-                    const float lx = fmaf(-k, dx, ocx), ly = fmaf(-k, dy, ocy), lz = fmaf(-k, dz, ocz);
-                    const float dn = fmaf(s.w, s.w, -dot3(lx, ly, lz, lx, ly, lz));
-                    if (dn < 0.f) continue;
-                    const float sq = sqrt_fast(dn * a);
-                    float root = (-hb - sq) * inv_a;
-                    if (ANY) {
-                        if (!(root < tmin || tmax < root)) { stat_add<STATS>(st, kStatSphereHits); return true; }
-                        root = (-hb + sq) * inv_a;
-                        if (!(root < tmin || tmax < root)) { stat_add<STATS>(st, kStatSphereHits); return true; }
-                    } else {
-                        if (root < tmin || tbest < root) {
-                            root = (-hb + sq) * inv_a;
-                            if (root < tmin || tbest < root) continue;
-                        }
-                        stat_add<STATS>(st, kStatSphereHits);
-                        const int pr = (int)(start + i);
-                        if (root == tbest && found) {
-                            if (prim_order(S, pr) < prim_order(S, best)) continue;
-                        }
-                        tbest = root;
-                        best = pr;
-                        found = true;
-                    }
-                }
+                if (test_spheres<ANY, STATS>(S, q, start, cnt, st)) return true;
             } else {
-                // ---- Triangle.Hit (geometry/triangle.go:36-88), Moller-Trumbore ----
-                for (int i = 0; i < cnt; i++) {
-                    stat_add<STATS>(st, kStatTriTests);
-                    const float4* tp = S.tris + 4 * (size_t)(start + i);
-                    const float4 v0 = ldg4(tp), e1 = ldg4(tp + 1), e2 = ldg4(tp + 2);
-                    const float hx = dy * e2.z - dz * e2.y, hy = dz * e2.x - dx * e2.z, hz = dx * e2.y - dy * e2.x;
-                    const float aa = dot3(e1.x, e1.y, e1.z, hx, hy, hz);
-                    if (aa > -1e-6f && aa < 1e-6f) { stat_add<STATS>(st, kStatTriRejA); continue; }
-                    const float f = rcp_fast(aa);
-                    const float sx = ox - v0.x, sy = oy - v0.y, sz = oz - v0.z;
-                    const float u = f * dot3(sx, sy, sz, hx, hy, hz);
-                    if (u < 0.0f || u > 1.0f) { stat_add<STATS>(st, kStatTriRejU); continue; }
-                    const float qx = sy * e1.z - sz * e1.y, qy = sz * e1.x - sx * e1.z, qz = sx * e1.y - sy * e1.x;
-                    const float vv = f * dot3(dx, dy, dz, qx, qy, qz);
-                    if (vv < 0.0f || u + vv > 1.0f) { stat_add<STATS>(st, kStatTriRejV); continue; }
-                    const float t = f * dot3(e2.x, e2.y, e2.z, qx, qy, qz);
-                    if (ANY) {
-                        if (t < tmin || t > tmax) { stat_add<STATS>(st, kStatTriRejT); continue; }
-                        stat_add<STATS>(st, kStatTriHits);
-                        return true;
-                    } else {
-                        if (t < tmin || t > tbest) { stat_add<STATS>(st, kStatTriRejT); continue; }
-                        stat_add<STATS>(st, kStatTriHits);
-                        const int pr = (int)((start + i) | 0x80000000u);
-                        if (t == tbest && found) {
-                            if (prim_order(S, pr) < prim_order(S, best)) continue;
-                        }
-                        tbest = t;
-                        best = pr;
-                        found = true;
-                    }
-                }
+                if (test_tris<ANY, STATS>(S, q, start, cnt, st)) return true;
             }
             if (sp == 0) break;
             node = stack[--sp];
         }
     }
     if (ANY) return false;
-    t_out = tbest;
-    prim_out = best;
-    return found;
+    t_out = q.tbest;
+    prim_out = q.best;
+    return q.found;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -335,7 +363,7 @@ __device__ __forceinline__ float pow5(float x) {  // math.Pow(x, 5): sign-preser
 // ---------------------------------------------------------------------------------------------
 // the trace kernel
 // ---------------------------------------------------------------------------------------------
-template <bool STATS>
+template <bool STATS, bool SMALL>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) trace_kernel(const __grid_constant__ TraceParams P) {
     __shared__ uint32_t q_smem[kWarpsPerCta][QF_COUNT][kQueueCap];
     const int lane = threadIdx.x & 31;
@@ -425,7 +453,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) trace_kernel(const __gri
                 ps.dz = fmaf(v, P.cam.vz, fmaf(u, P.cam.hz, P.cam.llz));
                 // traceRay depth 0 (renderer.go:166-173); max_depth <= 0 returns black before any hit test
                 if (P.max_depth > 0)
-                    hit = traverse<false, STATS>(S, ps.ox, ps.oy, ps.oz, ps.dx, ps.dy, ps.dz, 0.001f, FLT_MAX * 2.0f, ps.t, ps.prim, st);
+                    hit = traverse<false, STATS, SMALL>(S, ps.ox, ps.oy, ps.oz, ps.dx, ps.dy, ps.dz, 0.001f, FLT_MAX * 2.0f, ps.t, ps.prim, st);
             }
             const unsigned hm = __ballot_sync(FULL_MASK, hit);
             if (hit) {
@@ -496,7 +524,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) trace_kernel(const __gri
                 float tt;
                 int pp;
                 stat_add<STATS>(st, kStatLightEvals);
-                lit = !traverse<true, STATS>(S, px, py, pz, ldx, ldy, ldz, 0.001f, dist, tt, pp, st);
+                lit = !traverse<true, STATS, SMALL>(S, px, py, pz, ldx, ldy, ldz, 0.001f, dist, tt, pp, st);
             }
             float factor = lit ? 1.0f : 0.0f;
             if (P.soft) {
@@ -528,7 +556,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) trace_kernel(const __gri
                         normalize3(sdx, sdy, sdz);
                         float tt;
                         int pp;
-                        unocc = !traverse<true, STATS>(S, spx, spy, spz, sdx, sdy, sdz, 0.001f, sdist, tt, pp, st);
+                        unocc = !traverse<true, STATS, SMALL>(S, spx, spy, spz, sdx, sdy, sdz, 0.001f, sdist, tt, pp, st);
                     }
                     const unsigned ub = __ballot_sync(FULL_MASK, unocc);
                     if (lane == a) cnt = __popc(ub & 0xFFFFu);
@@ -650,7 +678,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) trace_kernel(const __gri
         // ================= EXTEND: hitWorld for the scattered rays =======================================
         bool hit = false;
         if (cont) {
-            hit = traverse<false, STATS>(S, ps.ox, ps.oy, ps.oz, ps.dx, ps.dy, ps.dz, 0.001f, FLT_MAX * 2.0f, ps.t, ps.prim, st);
+            hit = traverse<false, STATS, SMALL>(S, ps.ox, ps.oy, ps.oz, ps.dx, ps.dy, ps.dz, 0.001f, FLT_MAX * 2.0f, ps.t, ps.prim, st);
             if (!hit) flush_path(P, ps);  // miss returns black (renderer.go:171-173)
         }
         const unsigned hm = __ballot_sync(FULL_MASK, hit);
@@ -808,18 +836,28 @@ cudaError_t launch_cull(const TraceParams& p, uint32_t* active_list, unsigned in
     return cudaGetLastError();
 }
 
+// Linear scan instead of the BVH when the whole scene costs about as much as one node visit chain
+// (a sphere test ~20 instructions, a triangle test ~35, a BVH node ~45).
+bool scene_is_small(const SceneView& s) { return s.n_spheres + 2 * s.n_tris <= 12; }
+
 cudaError_t launch_trace(const TraceParams& p, bool stats, int sm_count, cudaStream_t stream) {
     if (p.n_local_tiles == 0) return cudaSuccess;
     const int threads = kWarpsPerCta * 32;
     int blocks = sm_count * 2;  // persistent: 2 resident CTAs per SM (launch bounds)
-    if (stats) trace_kernel<true><<<blocks, threads, 0, stream>>>(p);
-    else trace_kernel<false><<<blocks, threads, 0, stream>>>(p);
+    const bool small = scene_is_small(p.scene);
+    if (stats) {
+        if (small) trace_kernel<true, true><<<blocks, threads, 0, stream>>>(p);
+        else trace_kernel<true, false><<<blocks, threads, 0, stream>>>(p);
+    } else {
+        if (small) trace_kernel<false, true><<<blocks, threads, 0, stream>>>(p);
+        else trace_kernel<false, false><<<blocks, threads, 0, stream>>>(p);
+    }
     return cudaGetLastError();
 }
 
 int trace_kernel_regs(bool stats) {
     cudaFuncAttributes a;
-    cudaError_t e = stats ? cudaFuncGetAttributes(&a, trace_kernel<true>) : cudaFuncGetAttributes(&a, trace_kernel<false>);
+    cudaError_t e = stats ? cudaFuncGetAttributes(&a, trace_kernel<true, false>) : cudaFuncGetAttributes(&a, trace_kernel<false, false>);
     return e == cudaSuccess ? a.numRegs : -1;
 }
 
@@ -898,8 +936,8 @@ __global__ void trace_rays_kernel(const SceneView S, int n, const float* __restr
     float t = -1.f;
     int prim = 0;
     bool hit;
-    if (any_hit) hit = traverse<true, false>(S, o[3 * i], o[3 * i + 1], o[3 * i + 2], d[3 * i], d[3 * i + 1], d[3 * i + 2], tmin, tmax, t, prim, st);
-    else hit = traverse<false, false>(S, o[3 * i], o[3 * i + 1], o[3 * i + 2], d[3 * i], d[3 * i + 1], d[3 * i + 2], tmin, tmax, t, prim, st);
+    if (any_hit) hit = traverse<true, false, false>(S, o[3 * i], o[3 * i + 1], o[3 * i + 2], d[3 * i], d[3 * i + 1], d[3 * i + 2], tmin, tmax, t, prim, st);
+    else hit = traverse<false, false, false>(S, o[3 * i], o[3 * i + 1], o[3 * i + 2], d[3 * i], d[3 * i + 1], d[3 * i + 2], tmin, tmax, t, prim, st);
     if (any_hit) {
         out_t[i] = hit ? 1.f : -1.f;
         out_order[i] = -1;

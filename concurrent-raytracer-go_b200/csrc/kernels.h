@@ -51,6 +51,7 @@ struct SceneView {
     const float4* lights;  // 2 float4 per light: (pos.xyz, intensity) (color.rgb, 0)
     int n_nodes;
     int n_lights;
+    int n_spheres, n_tris;
 };
 
 struct TraceParams {
@@ -88,5 +89,6 @@ cudaError_t launch_trace_rays(const SceneView& scene, int n, const float* origin
                               int any_hit, float* out_t, int* out_order, cudaStream_t stream);
 cudaError_t launch_ffma_peak(float* sink, int iters, int blocks, int threads, cudaStream_t stream);
 int trace_kernel_regs(bool stats);
+bool scene_is_small(const SceneView& s);
 
 }  // namespace gort
