@@ -24,7 +24,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgort.so")
+LIB_PATH = os.environ.get("GORT_LIB") or os.path.join(_HERE, "lib", "libgort.so")  # GORT_LIB: A/B builds of the same ABI
 
 ABI_VERSION = 1
 TILE = 32

@@ -38,10 +38,11 @@ struct DeviceState {
     // per-frame buffers
     unsigned long long* d_accum = nullptr;
     size_t accum_tiles = 0;
-    unsigned int* d_counter = nullptr;  // [0] work counter, [1] active block count
+    unsigned int* d_counter = nullptr;  // [0] work counter, [1] deep active blocks, [2] other active blocks
     uint32_t* d_active = nullptr;       // active pixel-block list
     size_t active_bytes = 0;
     unsigned long long* d_stats = nullptr;
+    unsigned long long* d_debug = nullptr;  // GORT_DEBUG_TIMES
     uint8_t* d_out = nullptr;  // frame (row-major) or slab (tile-major)
     size_t out_bytes = 0;
     uint8_t* d_gather = nullptr;  // lead device only: rank-major slabs of all devices
@@ -251,6 +252,7 @@ int validate(gort_ctx* ctx, const gort_render_params* p) {
     if (!ctx->has_scene) return fail(ctx, GORT_ERR_NO_SCENE, "no scene uploaded");
     if (p->width <= 0 || p->height <= 0) return fail(ctx, GORT_ERR_INVALID, "width/height must be positive");
     if ((int64_t)p->width * p->height > (int64_t)1 << 28) return fail(ctx, GORT_ERR_INVALID, "image too large");
+    if (p->width > 65535 || p->height > 65535) return fail(ctx, GORT_ERR_INVALID, "width/height must be <= 65535");
     if (p->samples <= 0 || p->samples > 65535) return fail(ctx, GORT_ERR_INVALID, "samples must be in 1..65535");
     if (p->max_depth < 0 || p->max_depth > (1 << 20)) return fail(ctx, GORT_ERR_INVALID, "max_depth out of range");
     const int sc = p->shard_count <= 0 ? 1 : p->shard_count;
@@ -286,7 +288,7 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
 
     CUDA_TRY(ctx, cudaEventRecord(d.ev[0], st));
     if (accum_want) CUDA_TRY(ctx, cudaMemsetAsync(d.d_accum, 0, accum_want, st));
-    CUDA_TRY(ctx, cudaMemsetAsync(d.d_counter, 0, 2 * sizeof(unsigned int), st));
+    CUDA_TRY(ctx, cudaMemsetAsync(d.d_counter, 0, 4 * sizeof(unsigned int), st));
     if (int rc = ensure(ctx, d.d_active, d.active_bytes, (size_t)n_local * 32 * sizeof(uint32_t))) return rc;
     if (p->collect_stats) CUDA_TRY(ctx, cudaMemsetAsync(d.d_stats, 0, kStatCount * sizeof(unsigned long long), st));
     if (slab_mode && slab_bytes > (size_t)n_local * kTilePixels * 4)
@@ -300,12 +302,30 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     tp.scene.n_spheres = (int)ctx->scene.spheres.size(); tp.scene.n_tris = (int)ctx->scene.tris.size();
     tp.cam = make_camera(ctx->scene, p->camera_mode);
     tp.width = p->width; tp.height = p->height; tp.samples = p->samples; tp.max_depth = p->max_depth;
+    tp.inv_w = 1.0f / (float)p->width; tp.inv_h = 1.0f / (float)p->height;
+    // tiny sphere-only scenes: the spheres ride in the kernel parameters, in scan order
+    tp.small_n = 0;
+    if (ctx->scene.tris.empty() && !ctx->scene.spheres.empty() && (int)ctx->scene.spheres.size() <= kSmallMax) {
+        std::vector<const HostSphere*> sorted;
+        for (const HostSphere& hs : ctx->scene.spheres) sorted.push_back(&hs);
+        std::sort(sorted.begin(), sorted.end(), [](const HostSphere* a, const HostSphere* b) { return a->order < b->order; });
+        tp.small_n = (int)sorted.size();
+        for (int i = 0; i < tp.small_n; i++) {
+            tp.small_sph[i] = make_float4((float)sorted[i]->c[0], (float)sorted[i]->c[1], (float)sorted[i]->c[2], (float)sorted[i]->r);
+            tp.small_mat[i] = sorted[i]->mat;
+        }
+    }
     tp.jitter = p->anti_aliasing ? 1 : 0; tp.recursive = p->recursive_reflections ? 1 : 0; tp.soft = p->soft_shadows ? 1 : 0;
     tp.tiles_x = tiles_x; tp.tiles_y = tiles_y;
     tp.shard_rank = eff_rank; tp.shard_count = eff_count; tp.n_local_tiles = n_local;
     // work units = (sample batch, active 8x4 block), sized on the device: aim for >= 8 per resident warp
-    tp.target_units = 8u * (uint32_t)d.sm_count * 2u * 8u;
+    tp.target_units = 8u * (uint32_t)d.sm_count * 3u * 8u;
     tp.active_list = d.d_active; tp.active_count = d.d_counter + 1;
+    {
+        const char* ud = getenv("GORT_URGENT_DEPTH");
+        tp.urgent_depth = ud ? atoi(ud) : 2;
+    }
+    tp.debug_times = d.d_debug;
     tp.accum = d.d_accum; tp.work_counter = d.d_counter; tp.stats = p->collect_stats ? d.d_stats : nullptr;
     const uint32_t k0 = (uint32_t)p->seed, k1 = (uint32_t)(p->seed >> 32);
     for (int r = 0; r < 10; r++) {
@@ -433,6 +453,7 @@ int gort_create(const int* device_ids, int n_devices, gort_ctx** out) {
         for (int k = 0; k < 4 && e == cudaSuccess; k++) e = cudaEventCreate(&d.ev[k]);
         if (e == cudaSuccess) e = cudaMalloc(&d.d_counter, 16);
         if (e == cudaSuccess) e = cudaMalloc(&d.d_stats, kStatCount * sizeof(unsigned long long));
+        if (e == cudaSuccess && getenv("GORT_DEBUG_TIMES")) e = cudaMalloc(&d.d_debug, (1 + 2 * 148 * 8 * 8) * sizeof(unsigned long long));
         if (e != cudaSuccess) return bail(GORT_ERR_CUDA, std::string("device init: ") + cudaGetErrorString(e));
     }
     if (n_devices > 1) {  // direct NVLink copies for the slab gather
@@ -459,7 +480,7 @@ void gort_destroy(gort_ctx* ctx) {
         cudaSetDevice(d.dev);
         if (d.own_stream) cudaStreamSynchronize(d.own_stream);
         free_scene(d);
-        cudaFree(d.d_accum); cudaFree(d.d_active); cudaFree(d.d_counter); cudaFree(d.d_stats); cudaFree(d.d_out); cudaFree(d.d_gather);
+        cudaFree(d.d_debug); cudaFree(d.d_accum); cudaFree(d.d_active); cudaFree(d.d_counter); cudaFree(d.d_stats); cudaFree(d.d_out); cudaFree(d.d_gather);
         if (d.h_pinned) cudaFreeHost(d.h_pinned);
         for (auto& e : d.ev)
             if (e) cudaEventDestroy(e);

@@ -22,7 +22,10 @@
 // (pixel, sample, bounce, purpose) so any work-to-lane assignment draws the same numbers.
 #include "kernels.h"
 
+#include <algorithm>
 #include <cfloat>
+#include <cstdio>
+#include <vector>
 
 namespace gort {
 
@@ -211,10 +214,7 @@ __device__ __forceinline__ bool test_tris(const SceneView& S, RayQuery& q, uint3
     return false;
 }
 
-// SMALL: scenes of a handful of primitives skip the BVH and run the reference's own linear scan
-// (renderer.go:337-343) — every lane tests the same primitive, so the loads are warp-uniform broadcasts
-// and there is no stack, no node fetch and no traversal divergence.
-template <bool ANY, bool STATS, bool SMALL>
+template <bool ANY, bool STATS>
 __device__ __forceinline__ bool traverse(const SceneView& S, float ox, float oy, float oz, float dx, float dy, float dz,
                                          float tmin, float tmax, float& t_out, int& prim_out, Stats& st) {
     stat_add<STATS>(st, ANY ? kStatShadow : kStatClosest);
@@ -223,15 +223,6 @@ __device__ __forceinline__ bool traverse(const SceneView& S, float ox, float oy,
     q.a = dot3(dx, dy, dz, dx, dy, dz);
     q.inv_a = rcp_fast(q.a);
     q.tmin = tmin; q.tbest = tmax; q.best = 0; q.found = false;
-
-    if (SMALL) {
-        if (test_spheres<ANY, STATS>(S, q, 0u, S.n_spheres, st)) return true;
-        if (test_tris<ANY, STATS>(S, q, 0u, S.n_tris, st)) return true;
-        if (ANY) return false;
-        t_out = q.tbest;
-        prim_out = q.best;
-        return q.found;
-    }
 
     if (S.n_nodes == 0) return false;
     const float ooeps = 8.27180613e-25f;  // 2^-80
@@ -361,14 +352,76 @@ __device__ __forceinline__ float pow5(float x) {  // math.Pow(x, 5): sign-preser
 }
 
 // ---------------------------------------------------------------------------------------------
+// tiny sphere-only scenes (<= kSmallMax spheres, no triangles): the reference's own linear scan
+// (hitWorld renderer.go:337-343), fully unrolled, with the spheres read straight from the kernel
+// parameter bank (constant-bank operands: no load, no address arithmetic).  All tests of a ray are
+// independent instruction streams, so the scheduler overlaps them; the closest-hit reduction keeps the
+// scan order, which makes `<=` the reference's last-wins tie rule.
+// ---------------------------------------------------------------------------------------------
+template <bool ANY, bool STATS>
+__device__ __forceinline__ bool small_query(const TraceParams& P, float ox, float oy, float oz, float dx, float dy, float dz, float tmin,
+                                            float tmax, float& t_out, int& prim_out, Stats& st) {
+    stat_add<STATS>(st, ANY ? kStatShadow : kStatClosest);
+    const float a = dot3(dx, dy, dz, dx, dy, dz);
+    const float inv_a = rcp_fast(a);
+    float tbest = tmax;
+    int best = -1;
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < kSmallMax; i++) {
+        if (i < P.small_n) {
+            stat_add<STATS>(st, kStatSphereTests);
+            const float4 s = P.small_sph[i];
+            const float ocx = ox - s.x, ocy = oy - s.y, ocz = oz - s.z;
+            const float hb = dot3(ocx, ocy, ocz, dx, dy, dz);
+            const float k = hb * inv_a;
+            const float lx = fmaf(-k, dx, ocx), ly = fmaf(-k, dy, ocy), lz = fmaf(-k, dz, ocz);
+            const float dn = fmaf(s.w, s.w, -dot3(lx, ly, lz, lx, ly, lz));  // discriminant / a (sphere.go:28)
+            if (dn >= 0.f) {  // most tests miss: the roots are only worked out for the few that do not
+                const float sq = sqrt_fast(dn * a);
+                const float r0 = (-hb - sq) * inv_a, r1 = (-hb + sq) * inv_a;
+                if (ANY) {
+                    const bool h = !(r0 < tmin || tmax < r0) || !(r1 < tmin || tmax < r1);
+                    if (STATS && h) stat_add<STATS>(st, kStatSphereHits);
+                    any |= h;
+                } else {
+                    // sphere.go:35-40 with tMax = closestT: the near root if it is >= tMin, else the far root
+                    const float cand = (r0 < tmin) ? r1 : r0;
+                    const bool h = !(cand < tmin || tbest < cand);
+                    if (STATS && h) stat_add<STATS>(st, kStatSphereHits);
+                    tbest = h ? cand : tbest;
+                    best = h ? i : best;
+                }
+            }
+        }
+    }
+    if (ANY) return any;
+    t_out = tbest;
+    prim_out = best;
+    return best >= 0;
+}
+
+template <bool ANY, bool STATS, bool SMALL>
+__device__ __forceinline__ bool query(const TraceParams& P, float ox, float oy, float oz, float dx, float dy, float dz, float tmin,
+                                      float tmax, float& t_out, int& prim_out, Stats& st) {
+    if (SMALL) return small_query<ANY, STATS>(P, ox, oy, oz, dx, dy, dz, tmin, tmax, t_out, prim_out, st);
+    return traverse<ANY, STATS>(P.scene, ox, oy, oz, dx, dy, dz, tmin, tmax, t_out, prim_out, st);
+}
+
+// ---------------------------------------------------------------------------------------------
 // the trace kernel
 // ---------------------------------------------------------------------------------------------
+#ifndef GORT_MIN_CTAS
+#define GORT_MIN_CTAS 3
+#endif
+
+__device__ __forceinline__ float qf(uint32_t (*Q)[kQueueCap], int f, int slot) { return __uint_as_float(Q[f][slot]); }
+
 template <bool STATS, bool SMALL>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) trace_kernel(const __grid_constant__ TraceParams P) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel(const __grid_constant__ TraceParams P) {
     __shared__ uint32_t q_smem[kWarpsPerCta][QF_COUNT][kQueueCap];
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    uint32_t(*Q)[kQueueCap] = q_smem[warp];
+    uint32_t(*Q)[kQueueCap] = q_smem[threadIdx.x >> 5];
     const SceneView& S = P.scene;
     Stats st;
     if (STATS) {
@@ -376,30 +429,42 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) trace_kernel(const __gri
         for (int i = 0; i < kStatCount; i++) st.v[i] = 0;
     }
 
-    int qcount = 0;          // warp-uniform
-    bool more_units = true;  // warp-uniform
-    int s_cur = 0, s_end = 0;
-    // this lane's pixel in the current work unit
-    uint32_t pixg = 0, pixl = 0;
-    float fx = 0.f, fy = 0.f;
-    bool lane_valid = false;
-    const float inv_w = 1.0f / (float)P.width, inv_h = 1.0f / (float)P.height;
     // Work units are sized on the device from the number of pixel blocks the cull pass kept:
     // enough units for dynamic balance (target_units), at most 16 samples each.
-    const uint32_t n_active = *P.active_count;
+    const uint32_t n_deep = P.active_count[0], n_norm = P.active_count[1];
+    const uint32_t n_active = n_deep + n_norm;
     if (n_active == 0) return;
     int spu;
     {
         const uint32_t want_batches = (P.target_units + n_active - 1) / n_active;
         spu = max(1, min(16, P.samples / (int)max(1u, want_batches)));
     }
-    const uint32_t n_units = n_active * (uint32_t)((P.samples + spu - 1) / spu);
-    bool jit_valid = false;
+    const uint32_t n_batches = (uint32_t)((P.samples + spu - 1) / spu);
+    const uint32_t n_units = n_active * n_batches, deep_units = n_deep * n_batches;
+
+    unsigned long long t_units_done = 0;
+    if (P.debug_times && lane == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMin(P.debug_times, t);
+    }
+
+    int qcount = 0;          // warp-uniform
+    bool more_units = true;  // warp-uniform
+    int s_cur = 0, s_end = 0;
+    // this lane's pixel in the current work unit: (y << 16) | x, local accumulator index
+    uint32_t pix_xy = 0, pixl = 0;
+    bool lane_valid = false, jit_valid = false;
     uint32_t jit_z = 0, jit_w = 0;
+
+    // A warp that holds survivors at depth >= urgent_depth shades them at once instead of first topping
+    // its queue up with fresh primary hits: a 50-bounce glass path then advances every ~3 us instead of
+    // once per full round, and no longer forms the tail of the launch (profiles/r1_tail.md).
+    bool urgent = false;  // warp-uniform
 
     for (;;) {
         // ================= FILL: primary rays (tracePixel renderer.go:150-163, getRay :377-390) =========
-        while (qcount < 32) {
+        while (qcount < 32 && !urgent) {
             if (s_cur >= s_end) {
                 if (!more_units) break;
                 uint32_t u = 0;
@@ -407,27 +472,37 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) trace_kernel(const __gri
                 u = __shfl_sync(FULL_MASK, u, 0);
                 if (u >= n_units) {
                     more_units = false;
+                    if (P.debug_times) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_units_done));
                     break;
                 }
-                // unit = (sample batch, active 8x4 block); batch-major so heavy pixels spread over time
-                const uint32_t batch = u / n_active;
-                const uint32_t packed = __ldg(P.active_list + (u - batch * n_active));
+                // unit = (sample batch, active 8x4 block), batch-major; all units of the blocks that can see
+                // glass (deep paths) come first, the other blocks follow
+                uint32_t batch, idx;
+                if (u < deep_units) {
+                    batch = u / n_deep;
+                    idx = u - batch * n_deep;
+                } else {
+                    const uint32_t v = u - deep_units;
+                    batch = v / n_norm;
+                    idx = P.n_local_tiles * 32u - 1u - (v - batch * n_norm);  // the normal list grows down from the end
+                }
+                const uint32_t packed = __ldg(P.active_list + idx);
                 const uint32_t ltile = packed >> 5, block = packed & 31u;
                 const uint32_t gtile = (uint32_t)P.shard_rank + ltile * (uint32_t)P.shard_count;
                 const uint32_t tx = gtile % (uint32_t)P.tiles_x, ty = gtile / (uint32_t)P.tiles_x;
                 const uint32_t lx = ((block & 3u) << 3) + (lane & 7u), ly = ((block >> 2) << 2) + (lane >> 3);
                 const uint32_t x = tx * kTile + lx, y = ty * kTile + ly;
                 lane_valid = (x < (uint32_t)P.width) && (y < (uint32_t)P.height);
-                pixg = y * (uint32_t)P.width + x;
+                pix_xy = (y << 16) | x;
                 pixl = ltile * kTilePixels + ly * kTile + lx;
-                fx = (float)x;
-                fy = (float)y;
                 s_cur = (int)batch * spu;
                 s_end = min(s_cur + spu, P.samples);
                 jit_valid = false;
             }
             PathState ps;
             bool hit = false;
+            const uint32_t x = pix_xy & 0xffffu, y = pix_xy >> 16;
+            const uint32_t pixg = y * (uint32_t)P.width + x;
             if (lane_valid) {
                 float ju = 0.5f, jv = 0.5f;
                 if (P.jitter) {
@@ -446,14 +521,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) trace_kernel(const __gri
                     ju = (float)(jx >> 8) * (1.0f / 16777216.0f);
                     jv = (float)(jy >> 8) * (1.0f / 16777216.0f);
                 }
-                const float u = (fx + ju) * inv_w, v = (fy + jv) * inv_h;
+                const float u = ((float)x + ju) * P.inv_w, v = ((float)y + jv) * P.inv_h;
                 ps.ox = P.cam.ox; ps.oy = P.cam.oy; ps.oz = P.cam.oz;
                 ps.dx = fmaf(v, P.cam.vx, fmaf(u, P.cam.hx, P.cam.llx));
                 ps.dy = fmaf(v, P.cam.vy, fmaf(u, P.cam.hy, P.cam.lly));
                 ps.dz = fmaf(v, P.cam.vz, fmaf(u, P.cam.hz, P.cam.llz));
                 // traceRay depth 0 (renderer.go:166-173); max_depth <= 0 returns black before any hit test
                 if (P.max_depth > 0)
-                    hit = traverse<false, STATS, SMALL>(S, ps.ox, ps.oy, ps.oz, ps.dx, ps.dy, ps.dz, 0.001f, FLT_MAX * 2.0f, ps.t, ps.prim, st);
+                    hit = query<false, STATS, SMALL>(P, ps.ox, ps.oy, ps.oz, ps.dx, ps.dy, ps.dz, 0.001f, FLT_MAX * 2.0f, ps.t, ps.prim, st);
             }
             const unsigned hm = __ballot_sync(FULL_MASK, hit);
             if (hit) {
@@ -474,44 +549,59 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) trace_kernel(const __gri
         __syncwarp();
 
         // ================= SHADE: 32 queued hits =========================================================
+        // Only the hit geometry is pulled into registers here; throughput, radiance and the incoming
+        // direction stay in the queue slot until after the light loop (the slots are not overwritten
+        // before EXTEND), which keeps the register count of the shadow-ray loops down.
         const int n = min(32, qcount);
         qcount -= n;
         const bool act = lane < n;
-        PathState ps;
-        queue_load(Q, qcount + (act ? lane : 0), ps);
-        __syncwarp();
-
-        // hit record (sphere.go:42-50, triangle.go:69-73)
-        const float px = fmaf(ps.t, ps.dx, ps.ox), py = fmaf(ps.t, ps.dy, ps.oy), pz = fmaf(ps.t, ps.dz, ps.oz);
-        float nx, ny, nz;
+        const int slot = qcount + (act ? lane : 0);
+        const uint32_t h_pixg = Q[QF_PIXG][slot], h_sample = Q[QF_SAMPLE][slot], h_depth = Q[QF_DEPTH][slot];
+        float px, py, pz, nx, ny, nz;
+        bool front;
         int mat;
-        if (ps.prim >= 0) {
-            const float4 s = ldg4(S.spheres + ps.prim);
-            const float inv_r = rcp_fast(s.w);
-            nx = (px - s.x) * inv_r; ny = (py - s.y) * inv_r; nz = (pz - s.z) * inv_r;
-            mat = __ldg(&S.sphere_meta[ps.prim]).x;
-        } else {
-            const float4* tp = S.tris + 4 * (size_t)(ps.prim & 0x7fffffff);
-            mat = __float_as_int(ldg4(tp).w);
-            const float4 nn = ldg4(tp + 3);
-            nx = nn.x; ny = nn.y; nz = nn.z;
+        {
+            const float dx = qf(Q, QF_DX, slot), dy = qf(Q, QF_DY, slot), dz = qf(Q, QF_DZ, slot);
+            const float t = qf(Q, QF_T, slot);
+            const int prim = (int)Q[QF_PRIM][slot];
+            // hit record (sphere.go:42-50, triangle.go:69-73)
+            px = fmaf(t, dx, qf(Q, QF_OX, slot)); py = fmaf(t, dy, qf(Q, QF_OY, slot)); pz = fmaf(t, dz, qf(Q, QF_OZ, slot));
+            if (SMALL) {
+                const float4 s = P.small_sph[prim];
+                const float inv_r = rcp_fast(s.w);
+                nx = (px - s.x) * inv_r; ny = (py - s.y) * inv_r; nz = (pz - s.z) * inv_r;
+                mat = P.small_mat[prim];
+            } else if (prim >= 0) {
+                const float4 s = ldg4(S.spheres + prim);
+                const float inv_r = rcp_fast(s.w);
+                nx = (px - s.x) * inv_r; ny = (py - s.y) * inv_r; nz = (pz - s.z) * inv_r;
+                mat = __ldg(&S.sphere_meta[prim]).x;
+            } else {
+                const float4* tp = S.tris + 4 * (size_t)(prim & 0x7fffffff);
+                mat = __float_as_int(ldg4(tp).w);
+                const float4 nn = ldg4(tp + 3);
+                nx = nn.x; ny = nn.y; nz = nn.z;
+            }
+            front = dot3(dx, dy, dz, nx, ny, nz) < 0.f;
+            if (!front) { nx = -nx; ny = -ny; nz = -nz; }
         }
-        const bool front = dot3(ps.dx, ps.dy, ps.dz, nx, ny, nz) < 0.f;
-        if (!front) { nx = -nx; ny = -ny; nz = -nz; }
-        const float4 m0 = ldg4(S.mats + 4 * (size_t)mat);      // (type, color)
-        const float4 m1 = ldg4(S.mats + 4 * (size_t)mat + 1);  // (roughness, metallic, specular, ior)
-        const float4 m2 = ldg4(S.mats + 4 * (size_t)mat + 2);  // (ambient, kd, wr, wd)
-        const float4 m3 = ldg4(S.mats + 4 * (size_t)mat + 3);  // (spec power, f0, fresnel strength, metallic fresnel | -1)
-        const int mtype = __float_as_int(m0.x);
-        const bool is_light = (mtype == 6);
-        // GetAlbedo: DiffuseLight -> 0 (material.go:304); Dielectric -> 1 (packed by the host)
-        const float alr = is_light ? 0.f : m0.y, alg = is_light ? 0.f : m0.z, alb = is_light ? 0.f : m0.w;
-        const float metallic = m1.y;
+        const float4* mp = S.mats + 4 * (size_t)mat;
 
         // ---- calculateDirectLighting (renderer.go:229-297) ----
-        float dr = m2.x, dg = m2.x, db = m2.x;  // ambient
+        float dr, dg, db;        // running total, starts at the ambient term
+        float kar, kag, kab;     // diffuseStrength * albedo
+        float spec_w, spec_pow;  // metallic * 3 and the Blinn-Phong exponent (0: no specular term)
+        {
+            const float4 m0 = ldg4(mp), m2 = ldg4(mp + 2);  // (type, color) (ambient, kd, wr, wd)
+            const bool is_light = __float_as_int(m0.x) == 6;
+            // GetAlbedo: DiffuseLight -> 0 (material.go:304); Dielectric -> 1 (packed by the host)
+            kar = is_light ? 0.f : m0.y * m2.y; kag = is_light ? 0.f : m0.z * m2.y; kab = is_light ? 0.f : m0.w * m2.y;
+            dr = dg = db = m2.x;
+            spec_pow = __ldg(&mp[3].x);
+            spec_w = __ldg(&mp[1].y) * 3.0f;
+        }
         for (int l = 0; l < S.n_lights; l++) {
-            const float4 L0 = ldg4(S.lights + 2 * l), L1 = ldg4(S.lights + 2 * l + 1);
+            const float4 L0 = ldg4(S.lights + 2 * l);
             float ldx = L0.x - px, ldy = L0.y - py, ldz = L0.z - pz;
             const float dist2 = dot3(ldx, ldy, ldz, ldx, ldy, ldz);
             const float inv_d = dist2 > 0.f ? rsqrt_fast(dist2) : 0.f;
@@ -524,7 +614,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) trace_kernel(const __gri
                 float tt;
                 int pp;
                 stat_add<STATS>(st, kStatLightEvals);
-                lit = !traverse<true, STATS, SMALL>(S, px, py, pz, ldx, ldy, ldz, 0.001f, dist, tt, pp, st);
+                lit = !query<true, STATS, SMALL>(P, px, py, pz, ldx, ldy, ldz, 0.001f, dist, tt, pp, st);
             }
             float factor = lit ? 1.0f : 0.0f;
             if (P.soft) {
@@ -544,9 +634,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) trace_kernel(const __gri
                     const float spx = __shfl_sync(FULL_MASK, px, srcc), spy = __shfl_sync(FULL_MASK, py, srcc), spz = __shfl_sync(FULL_MASK, pz, srcc);
                     float sdx = __shfl_sync(FULL_MASK, ldx, srcc), sdy = __shfl_sync(FULL_MASK, ldy, srcc), sdz = __shfl_sync(FULL_MASK, ldz, srcc);
                     const float sdist = __shfl_sync(FULL_MASK, dist, srcc);
-                    const uint32_t spix = __shfl_sync(FULL_MASK, ps.pixg, srcc);
-                    const uint32_t ssamp = __shfl_sync(FULL_MASK, ps.sample, srcc);
-                    const uint32_t sdepth = __shfl_sync(FULL_MASK, ps.depth, srcc);
+                    const uint32_t spix = __shfl_sync(FULL_MASK, h_pixg, srcc);
+                    const uint32_t ssamp = __shfl_sync(FULL_MASK, h_sample, srcc);
+                    const uint32_t sdepth = __shfl_sync(FULL_MASK, h_depth, srcc);
                     bool unocc = false;
                     if (src >= 0) {
                         float bx, by, bz;
@@ -556,7 +646,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) trace_kernel(const __gri
                         normalize3(sdx, sdy, sdz);
                         float tt;
                         int pp;
-                        unocc = !traverse<true, STATS, SMALL>(S, spx, spy, spz, sdx, sdy, sdz, 0.001f, sdist, tt, pp, st);
+                        unocc = !query<true, STATS, SMALL>(P, spx, spy, spz, sdx, sdy, sdz, 0.001f, sdist, tt, pp, st);
                     }
                     const unsigned ub = __ballot_sync(FULL_MASK, unocc);
                     if (lane == a) cnt = __popc(ub & 0xFFFFu);
@@ -568,27 +658,33 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) trace_kernel(const __gri
                 stat_add<STATS>(st, kStatDiffuse);
                 const float cosT = fmaxf(0.f, dot3(nx, ny, nz, ldx, ldy, ldz));
                 const float inten = cosT * L0.w * (inv_d * inv_d);
-                const float kdw = m2.y * inten * factor;
-                dr = fmaf(alr, kdw, dr); dg = fmaf(alg, kdw, dg); db = fmaf(alb, kdw, db);
-                if (m3.x > 0.f) {  // metallic > 0.5, resolved in float64 on the host
+                const float kdw = inten * factor;
+                dr = fmaf(kar, kdw, dr); dg = fmaf(kag, kdw, dg); db = fmaf(kab, kdw, db);
+                if (spec_pow > 0.f) {  // metallic > 0.5, resolved in float64 on the host
                     stat_add<STATS>(st, kStatSpec);
+                    const float4 L1 = ldg4(S.lights + 2 * l + 1);
                     float vx = -px, vy = -py, vz = -pz;  // viewDir toward the world origin (renderer.go:279)
                     normalize3(vx, vy, vz);
                     float hx = ldx + vx, hy = ldy + vy, hz = ldz + vz;
                     normalize3(hx, hy, hz);
                     const float nh = fmaxf(0.f, dot3(nx, ny, nz, hx, hy, hz));
                     const float x2 = nh * nh, x4 = x2 * x2, x8 = x4 * x4, x16 = x8 * x8, x32 = x16 * x16;
-                    const float si = (m3.x > 56.f) ? x32 * x32 : ((m3.x > 40.f) ? x32 * x16 : x32);
-                    const float sw = si * inten * factor * metallic * 3.0f;
+                    const float si = (spec_pow > 56.f) ? x32 * x32 : ((spec_pow > 40.f) ? x32 * x16 : x32);
+                    const float sw = si * inten * factor * spec_w;
                     dr = fmaf(L1.x, sw, dr); dg = fmaf(L1.y, sw, dg); db = fmaf(L1.z, sw, db);
                 }
             }
         }
 
         // ---- Material.Scatter + traceRay's combination (renderer.go:177-226) ----
+        PathState ps;
         bool cont = false;
         if (act) {
             stat_add<STATS>(st, kStatShaded);
+            queue_load(Q, slot, ps);  // the rest of the path state, still intact in the queue slot
+            const float4 m0 = ldg4(mp), m1 = ldg4(mp + 1), m2 = ldg4(mp + 2), m3 = ldg4(mp + 3);
+            const int mtype = __float_as_int(m0.x);
+            const bool is_light = (mtype == 6);
             const float er = is_light ? m0.y : 0.f, eg = is_light ? m0.z : 0.f, eb = is_light ? m0.w : 0.f;  // Emitted
             bool scattered = true;
             float sx = 0.f, sy = 0.f, sz = 0.f, ar = 0.f, ag = 0.f, ab = 0.f;
@@ -674,19 +770,28 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) trace_kernel(const __gri
                 }
             }
         }
+        __syncwarp();  // every lane has read its slot before EXTEND overwrites the popped region
 
         // ================= EXTEND: hitWorld for the scattered rays =======================================
         bool hit = false;
         if (cont) {
-            hit = traverse<false, STATS, SMALL>(S, ps.ox, ps.oy, ps.oz, ps.dx, ps.dy, ps.dz, 0.001f, FLT_MAX * 2.0f, ps.t, ps.prim, st);
+            hit = query<false, STATS, SMALL>(P, ps.ox, ps.oy, ps.oz, ps.dx, ps.dy, ps.dz, 0.001f, FLT_MAX * 2.0f, ps.t, ps.prim, st);
             if (!hit) flush_path(P, ps);  // miss returns black (renderer.go:171-173)
         }
         const unsigned hm = __ballot_sync(FULL_MASK, hit);
         if (hit) queue_store(Q, qcount + __popc(hm & ((1u << lane) - 1u)), ps);
         qcount += __popc(hm);
+        urgent = __any_sync(FULL_MASK, hit && (int)ps.depth >= P.urgent_depth);
         __syncwarp();
     }
 
+    if (P.debug_times && lane == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        const unsigned int w = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+        P.debug_times[1 + 2 * w] = t_units_done;
+        P.debug_times[2 + 2 * w] = t;
+    }
     if (STATS && P.stats) {
 #pragma unroll
         for (int i = 0; i < kStatCount; i++) {
@@ -764,11 +869,13 @@ __global__ void __launch_bounds__(128) cull_kernel(const __grid_constant__ Trace
         if (sgn < 0.f) { nx = -nx; ny = -ny; nz = -nz; }
         B.nx[i] = nx; B.ny[i] = ny; B.nz[i] = nz;
     }
-    bool active = degenerate;
+    // active: some primitive may be visible; deep: one of them is glass/dielectric (paths can stay trapped
+    // by total internal reflection up to max_depth) -> those blocks are scheduled first
+    bool active = degenerate, deep = false;
     int stack[64];
     int sp = 0;
     int node = 0;
-    while (!active) {
+    while (!deep) {
         if (node >= 0) {
             const float4* np = S.nodes + 4 * (size_t)node;
             const float4 n0 = ldg4(np), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3);
@@ -791,7 +898,7 @@ __global__ void __launch_bounds__(128) cull_kernel(const __grid_constant__ Trace
             const uint32_t start = v & 0x3FFFFFFu;
             const int cnt = (int)((v >> 26) & 15u) + 1;
             if (((v >> 30) & 1u) == 0) {
-                for (int i = 0; i < cnt && !active; i++) {
+                for (int i = 0; i < cnt && !deep; i++) {
                     const float4 s = ldg4(S.spheres + start + i);
                     const float px = s.x - B.ox, py = s.y - B.oy, pz = s.z - B.oz;
                     const float r = fabsf(s.w) * 1.00001f + 1e-6f * (fabsf(px) + fabsf(py) + fabsf(pz));
@@ -802,10 +909,14 @@ __global__ void __launch_bounds__(128) cull_kernel(const __grid_constant__ Trace
                         const float nl = sqrtf(dot3(B.nx[k], B.ny[k], B.nz[k], B.nx[k], B.ny[k], B.nz[k]));
                         if (d < -r * nl) out = true;
                     }
-                    if (!out) active = true;
+                    if (!out) {
+                        active = true;
+                        const int mt = __float_as_int(ldg4(S.mats + 4 * (size_t)__ldg(&S.sphere_meta[start + i]).x).x);
+                        deep = (mt == 4 || mt == 5);
+                    }
                 }
             } else {
-                for (int i = 0; i < cnt && !active; i++) {
+                for (int i = 0; i < cnt && !deep; i++) {
                     const float4* tp = S.tris + 4 * (size_t)(start + i);
                     const float4 a = ldg4(tp), e1 = ldg4(tp + 1), e2 = ldg4(tp + 2);
                     const float ax = a.x - B.ox, ay = a.y - B.oy, az = a.z - B.oz;
@@ -819,14 +930,20 @@ __global__ void __launch_bounds__(128) cull_kernel(const __grid_constant__ Trace
                         const float d2 = d0 + dot3(B.nx[k], B.ny[k], B.nz[k], e2.x, e2.y, e2.z);
                         if (fmaxf(d0, fmaxf(d1, d2)) < -ext * nl) out = true;
                     }
-                    if (!out) active = true;
+                    if (!out) {
+                        active = true;
+                        const int mt = __float_as_int(ldg4(S.mats + 4 * (size_t)__float_as_int(a.w)).x);
+                        deep = (mt == 4 || mt == 5);
+                    }
                 }
             }
-            if (active || sp == 0) break;
+            if (deep || sp == 0) break;
             node = stack[--sp];
         }
     }
-    if (active) active_list[atomicAdd(active_count, 1u)] = id;
+    // one array, two cursors: deep blocks fill it from the front, the others from the back
+    if (deep || degenerate) active_list[atomicAdd(active_count, 1u)] = id;
+    else if (active) active_list[(uint32_t)P.n_local_tiles * 32u - 1u - atomicAdd(active_count + 1, 1u)] = id;
 }
 
 cudaError_t launch_cull(const TraceParams& p, uint32_t* active_list, unsigned int* active_count, cudaStream_t stream) {
@@ -836,23 +953,47 @@ cudaError_t launch_cull(const TraceParams& p, uint32_t* active_list, unsigned in
     return cudaGetLastError();
 }
 
-// Linear scan instead of the BVH when the whole scene costs about as much as one node visit chain
-// (a sphere test ~20 instructions, a triangle test ~35, a BVH node ~45).
-bool scene_is_small(const SceneView& s) { return s.n_spheres + 2 * s.n_tris <= 12; }
+
+template <bool STATS, bool SMALL>
+static cudaError_t launch_trace_variant(const TraceParams& p, int sm_count, cudaStream_t stream) {
+    // persistent grid: as many CTAs as fit on the chip at once (occupancy is register-bound)
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+        int n = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_kernel<STATS, SMALL>, kWarpsPerCta * 32, 0);
+        if (e != cudaSuccess) return e;
+        ctas_per_sm = n > 0 ? n : 1;
+    }
+    if (p.debug_times) {  // GORT_DEBUG_TIMES: per-warp finish times of this launch on stderr
+        const int nw = sm_count * ctas_per_sm * kWarpsPerCta;
+        cudaMemsetAsync(p.debug_times, 0xff, 8, stream);
+        cudaMemsetAsync(p.debug_times + 1, 0, (size_t)nw * 16, stream);
+        trace_kernel<STATS, SMALL><<<sm_count * ctas_per_sm, kWarpsPerCta * 32, 0, stream>>>(p);
+        std::vector<unsigned long long> h(1 + 2 * (size_t)nw);
+        cudaMemcpyAsync(h.data(), p.debug_times, h.size() * 8, cudaMemcpyDeviceToHost, stream);
+        cudaStreamSynchronize(stream);
+        std::vector<double> units, drain;
+        for (int w = 0; w < nw; w++) {
+            if (!h[2 + 2 * w]) continue;
+            units.push_back((double)(h[1 + 2 * w] - h[0]) * 1e-3);
+            drain.push_back((double)(h[2 + 2 * w] - h[0]) * 1e-3);
+        }
+        std::sort(units.begin(), units.end());
+        std::sort(drain.begin(), drain.end());
+        auto pct = [](const std::vector<double>& v, double q) { return v.empty() ? 0.0 : v[(size_t)(q * (v.size() - 1))]; };
+        fprintf(stderr, "[gort debug] warps %zu  units-exhausted us: p0 %.1f p50 %.1f p100 %.1f | warp-finished us: p0 %.1f p10 %.1f p50 %.1f p90 %.1f p99 %.1f p100 %.1f\n",
+                drain.size(), pct(units, 0), pct(units, 0.5), pct(units, 1), pct(drain, 0), pct(drain, 0.1), pct(drain, 0.5), pct(drain, 0.9), pct(drain, 0.99), pct(drain, 1));
+        return cudaGetLastError();
+    }
+    trace_kernel<STATS, SMALL><<<sm_count * ctas_per_sm, kWarpsPerCta * 32, 0, stream>>>(p);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_trace(const TraceParams& p, bool stats, int sm_count, cudaStream_t stream) {
     if (p.n_local_tiles == 0) return cudaSuccess;
-    const int threads = kWarpsPerCta * 32;
-    int blocks = sm_count * 2;  // persistent: 2 resident CTAs per SM (launch bounds)
-    const bool small = scene_is_small(p.scene);
-    if (stats) {
-        if (small) trace_kernel<true, true><<<blocks, threads, 0, stream>>>(p);
-        else trace_kernel<true, false><<<blocks, threads, 0, stream>>>(p);
-    } else {
-        if (small) trace_kernel<false, true><<<blocks, threads, 0, stream>>>(p);
-        else trace_kernel<false, false><<<blocks, threads, 0, stream>>>(p);
-    }
-    return cudaGetLastError();
+    const bool small = p.small_n > 0;
+    if (stats) return small ? launch_trace_variant<true, true>(p, sm_count, stream) : launch_trace_variant<true, false>(p, sm_count, stream);
+    return small ? launch_trace_variant<false, true>(p, sm_count, stream) : launch_trace_variant<false, false>(p, sm_count, stream);
 }
 
 int trace_kernel_regs(bool stats) {
@@ -936,8 +1077,8 @@ __global__ void trace_rays_kernel(const SceneView S, int n, const float* __restr
     float t = -1.f;
     int prim = 0;
     bool hit;
-    if (any_hit) hit = traverse<true, false, false>(S, o[3 * i], o[3 * i + 1], o[3 * i + 2], d[3 * i], d[3 * i + 1], d[3 * i + 2], tmin, tmax, t, prim, st);
-    else hit = traverse<false, false, false>(S, o[3 * i], o[3 * i + 1], o[3 * i + 2], d[3 * i], d[3 * i + 1], d[3 * i + 2], tmin, tmax, t, prim, st);
+    if (any_hit) hit = traverse<true, false>(S, o[3 * i], o[3 * i + 1], o[3 * i + 2], d[3 * i], d[3 * i + 1], d[3 * i + 2], tmin, tmax, t, prim, st);
+    else hit = traverse<false, false>(S, o[3 * i], o[3 * i + 1], o[3 * i + 2], d[3 * i], d[3 * i + 1], d[3 * i + 2], tmin, tmax, t, prim, st);
     if (any_hit) {
         out_t[i] = hit ? 1.f : -1.f;
         out_order[i] = -1;

@@ -8,6 +8,7 @@ namespace gort {
 
 constexpr int kTile = 32;                 // createRenderTasks tileSize (renderer.go:401)
 constexpr int kTilePixels = kTile * kTile;
+constexpr int kSmallMax = 12;             // sphere-only scenes up to this size use the unrolled linear scan
 constexpr int kAccumFracBits = 30;        // fixed-point radiance accumulators: value * 2^30 in int64
 constexpr float kSampleClamp = 65536.0f;  // |per-sample radiance| clamp before fixed-point conversion
 
@@ -58,18 +59,26 @@ struct TraceParams {
     SceneView scene;
     DevCamera cam;
     int width, height, samples, max_depth;
+    float inv_w, inv_h;
     int jitter, recursive, soft;
     int tiles_x, tiles_y;
     int shard_rank, shard_count, n_local_tiles;
     uint32_t target_units;           // desired number of work units (dynamic balance), see trace_kernel
-    const uint32_t* active_list;     // pixel blocks kept by the cull pass: (local tile << 5) | block
-    const unsigned int* active_count;
+    const uint32_t* active_list;     // pixel blocks kept by the cull pass: (local tile << 5) | block;
+                                     // [0, n_deep) from the front, n_norm more from the back of [0, 32*n_local_tiles)
+    const unsigned int* active_count;  // {n_deep, n_norm}
+    int urgent_depth;                // survivors at this depth or deeper are shaded before the queue is refilled
     unsigned long long* accum;   // [n_local_tiles][1024][3] int64 fixed point
     unsigned int* work_counter;  // zeroed before launch
     unsigned long long* stats;   // [kStatCount] or nullptr
+    unsigned long long* debug_times;  // nullptr, or [1 + 2*n_warps]: kernel start, then per warp (end of units, end of drain) in ns
     uint32_t rk[20];             // Philox4x32-10 round keys: rk[2r] = key0 + r*W0, rk[2r+1] = key1 + r*W1
     int fog_enabled;
     float fog_density, fog_r, fog_g, fog_b;
+    // tiny sphere-only scene, in the reference's scan order (small_n == 0: use the BVH)
+    int small_n;
+    int small_mat[kSmallMax];
+    float4 small_sph[kSmallMax];
 };
 
 struct ResolveParams {
@@ -89,6 +98,5 @@ cudaError_t launch_trace_rays(const SceneView& scene, int n, const float* origin
                               int any_hit, float* out_t, int* out_order, cudaStream_t stream);
 cudaError_t launch_ffma_peak(float* sink, int iters, int blocks, int threads, cudaStream_t stream);
 int trace_kernel_regs(bool stats);
-bool scene_is_small(const SceneView& s);
 
 }  // namespace gort
