@@ -243,6 +243,37 @@ DevCamera make_camera(const HostScene& s, int mode) {
     return c;
 }
 
+// Loose float64 upper bound on |traceRay(...)| per unit of throughput, for the exact dead-path test:
+//   per bounce   emitted <= E, direct <= ambient + sum_l |I_l| max(1,|color_l|) / tMin^2 * (kd*albedo + 3)
+//                (lights closer than 0.001 are skipped, renderer.go:252; cos, shadow factor, metallic <= 1)
+//   attenuation  |w_r * atten| <= F = max(1, max albedo, max |Schlick|), |Schlick| <= max(1, f0 + (1-f0)(|D|max-1)^5)
+//                with |D|max = the longest (unnormalised) primary direction — reflection keeps |D|
+//   radiance     R <= max_depth * (E + D) * F^max_depth
+float dead_path_bound(const HostScene& s, const DevCamera& c, int max_depth) {
+    double emax = 0, amax = 1.0;
+    for (const HostMaterial& m : s.mats) {
+        const double cm = std::max(std::fabs(m.color[0]), std::max(std::fabs(m.color[1]), std::fabs(m.color[2])));
+        if (m.type == GORT_MAT_DIFFUSELIGHT) emax = std::max(emax, cm);
+        amax = std::max(amax, cm);
+    }
+    double dsum = 0.1;
+    for (const HostLight& l : s.lights) {
+        const double cl = std::max(1.0, std::max(std::fabs(l.color[0]), std::max(std::fabs(l.color[1]), std::fabs(l.color[2]))));
+        dsum += std::fabs(l.intensity) * cl * 1e6 * (0.25 * amax + 3.0);
+    }
+    double dmax = 1.0;
+    for (int i = 0; i < 4; i++) {
+        const double u = (i & 1) ? 1.0 : 0.0, v = (i & 2) ? 1.0 : 0.0;
+        const double x = c.llx + u * c.hx + v * c.vx, y = c.lly + u * c.hy + v * c.vy, z = c.llz + u * c.hz + v * c.vz;
+        dmax = std::max(dmax, std::sqrt(x * x + y * y + z * z) * 1.001);
+    }
+    const double fres = std::max(1.0, 1.0 + std::pow(dmax - 1.0, 5.0));
+    const double F = std::max(amax, fres) * 1.0001;
+    const double bound = (double)std::max(1, max_depth) * (emax + dsum) * std::pow(F, (double)std::max(1, max_depth));
+    if (!(bound < 1e30)) return 0.f;  // no useful bound: never cut
+    return (float)bound;
+}
+
 int local_tile_count(int n_tiles, int rank, int count) { return rank < n_tiles ? (n_tiles - rank + count - 1) / count : 0; }
 
 int validate(gort_ctx* ctx, const gort_render_params* p) {
@@ -319,12 +350,9 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     tp.tiles_x = tiles_x; tp.tiles_y = tiles_y;
     tp.shard_rank = eff_rank; tp.shard_count = eff_count; tp.n_local_tiles = n_local;
     // work units = (sample batch, active 8x4 block), sized on the device: aim for >= 8 per resident warp
-    tp.target_units = 8u * (uint32_t)d.sm_count * 3u * 8u;
+    tp.target_units = 8u * (uint32_t)d.sm_count * 24u;  // ~8 units per resident warp
     tp.active_list = d.d_active; tp.active_count = d.d_counter + 1;
-    {
-        const char* ud = getenv("GORT_URGENT_DEPTH");
-        tp.urgent_depth = ud ? atoi(ud) : 2;
-    }
+
     tp.debug_times = d.d_debug;
     tp.accum = d.d_accum; tp.work_counter = d.d_counter; tp.stats = p->collect_stats ? d.d_stats : nullptr;
     const uint32_t k0 = (uint32_t)p->seed, k1 = (uint32_t)(p->seed >> 32);
@@ -332,6 +360,7 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
         tp.rk[2 * r] = k0 + (uint32_t)r * 0x9E3779B9u;
         tp.rk[2 * r + 1] = k1 + (uint32_t)r * 0xBB67AE85u;
     }
+    tp.dead_bound = getenv("GORT_NO_DEAD_PATH") ? 0.f : dead_path_bound(ctx->scene, tp.cam, p->max_depth);
     tp.fog_enabled = ctx->scene.fog_enabled;
     tp.fog_density = (float)ctx->scene.fog_density;
     tp.fog_r = (float)ctx->scene.fog_color[0]; tp.fog_g = (float)ctx->scene.fog_color[1]; tp.fog_b = (float)ctx->scene.fog_color[2];
@@ -397,6 +426,7 @@ int collect_stats(gort_ctx* ctx, const gort_render_params* p, gort_stats* s, dou
         s->tri_rejects[0] = tot[kStatTriRejA]; s->tri_rejects[1] = tot[kStatTriRejU]; s->tri_rejects[2] = tot[kStatTriRejV]; s->tri_rejects[3] = tot[kStatTriRejT];
         s->shaded_hits = tot[kStatShaded]; s->rng_blocks = tot[kStatRngBlocks]; s->light_evals = tot[kStatLightEvals];
         s->soft_shadow_rays = tot[kStatSoftRays]; s->diffuse_evals = tot[kStatDiffuse]; s->specular_evals = tot[kStatSpec];
+        s->paths_depth_ge5 = tot[kStatDepth5]; s->paths_depth_ge20 = tot[kStatDepth20]; s->paths_depth_max = tot[kStatDepthMax];
         // SURVEY §8d operation costs (FMA = 2 flops): ray generation 12, AABB slab 24 (two per node),
         // sphere 23 miss / 47 hit, triangle 20/30/46/52 staged rejects / 92 accept, 30 per (hit, light)
         // set-up, 36 per soft-shadow direction, 50 per diffuse term, 45 per specular term, ~70 per
@@ -453,7 +483,7 @@ int gort_create(const int* device_ids, int n_devices, gort_ctx** out) {
         for (int k = 0; k < 4 && e == cudaSuccess; k++) e = cudaEventCreate(&d.ev[k]);
         if (e == cudaSuccess) e = cudaMalloc(&d.d_counter, 16);
         if (e == cudaSuccess) e = cudaMalloc(&d.d_stats, kStatCount * sizeof(unsigned long long));
-        if (e == cudaSuccess && getenv("GORT_DEBUG_TIMES")) e = cudaMalloc(&d.d_debug, (1 + 2 * 148 * 8 * 8) * sizeof(unsigned long long));
+        if (e == cudaSuccess && getenv("GORT_DEBUG_TIMES")) e = cudaMalloc(&d.d_debug, (1 + 4 * 148 * 64) * sizeof(unsigned long long));
         if (e != cudaSuccess) return bail(GORT_ERR_CUDA, std::string("device init: ") + cudaGetErrorString(e));
     }
     if (n_devices > 1) {  // direct NVLink copies for the slab gather

@@ -145,8 +145,8 @@ struct RayQuery {
 };
 
 // ---- Sphere.Hit (geometry/sphere.go:22-59) for spheres [start, start+cnt) ----
-template <bool ANY, bool STATS>
-__device__ __forceinline__ bool test_spheres(const SceneView& S, RayQuery& q, uint32_t start, int cnt, Stats& st) {
+template <bool STATS>
+__device__ __forceinline__ void test_spheres(const SceneView& S, RayQuery& q, uint32_t start, int cnt, Stats& st) {
     for (int i = 0; i < cnt; i++) {
         stat_add<STATS>(st, kStatSphereTests);
         const float4 s = ldg4(S.spheres + start + i);
@@ -160,31 +160,24 @@ __device__ __forceinline__ bool test_spheres(const SceneView& S, RayQuery& q, ui
         if (dn < 0.f) continue;
         const float sq = sqrt_fast(dn * q.a);
         float root = (-hb - sq) * q.inv_a;
-        if (ANY) {
-            if (!(root < q.tmin || q.tbest < root)) { stat_add<STATS>(st, kStatSphereHits); return true; }
+        if (root < q.tmin || q.tbest < root) {
             root = (-hb + sq) * q.inv_a;
-            if (!(root < q.tmin || q.tbest < root)) { stat_add<STATS>(st, kStatSphereHits); return true; }
-        } else {
-            if (root < q.tmin || q.tbest < root) {
-                root = (-hb + sq) * q.inv_a;
-                if (root < q.tmin || q.tbest < root) continue;
-            }
-            stat_add<STATS>(st, kStatSphereHits);
-            const int pr = (int)(start + i);
-            if (root == q.tbest && q.found) {
-                if (prim_order(S, pr) < prim_order(S, q.best)) continue;
-            }
-            q.tbest = root;
-            q.best = pr;
-            q.found = true;
+            if (root < q.tmin || q.tbest < root) continue;
         }
+        stat_add<STATS>(st, kStatSphereHits);
+        const int pr = (int)(start + i);
+        if (root == q.tbest && q.found) {
+            if (prim_order(S, pr) < prim_order(S, q.best)) continue;
+        }
+        q.tbest = root;
+        q.best = pr;
+        q.found = true;
     }
-    return false;
 }
 
 // ---- Triangle.Hit (geometry/triangle.go:36-88), Moller-Trumbore, for triangles [start, start+cnt) ----
-template <bool ANY, bool STATS>
-__device__ __forceinline__ bool test_tris(const SceneView& S, RayQuery& q, uint32_t start, int cnt, Stats& st) {
+template <bool STATS>
+__device__ __forceinline__ void test_tris(const SceneView& S, RayQuery& q, uint32_t start, int cnt, Stats& st) {
     for (int i = 0; i < cnt; i++) {
         stat_add<STATS>(st, kStatTriTests);
         const float4* tp = S.tris + 4 * (size_t)(start + i);
@@ -202,7 +195,6 @@ __device__ __forceinline__ bool test_tris(const SceneView& S, RayQuery& q, uint3
         const float t = f * dot3(e2.x, e2.y, e2.z, qx, qy, qz);
         if (t < q.tmin || t > q.tbest) { stat_add<STATS>(st, kStatTriRejT); continue; }
         stat_add<STATS>(st, kStatTriHits);
-        if (ANY) return true;
         const int pr = (int)((start + i) | 0x80000000u);
         if (t == q.tbest && q.found) {
             if (prim_order(S, pr) < prim_order(S, q.best)) continue;
@@ -211,20 +203,21 @@ __device__ __forceinline__ bool test_tris(const SceneView& S, RayQuery& q, uint3
         q.best = pr;
         q.found = true;
     }
-    return false;
 }
 
-template <bool ANY, bool STATS>
+// hitWorld over the BVH.  `any` (per lane, data not code: closest-hit and shadow rays share every
+// instruction of a batch) ends the walk at the first accepted primitive — exactly how the renderer
+// uses hitWorld for shadows (renderer.go:305,320: only `hit` is read).
+template <bool STATS>
 __device__ __forceinline__ bool traverse(const SceneView& S, float ox, float oy, float oz, float dx, float dy, float dz,
-                                         float tmin, float tmax, float& t_out, int& prim_out, Stats& st) {
-    stat_add<STATS>(st, ANY ? kStatShadow : kStatClosest);
+                                         float tmin, float tmax, bool any, float& t_out, int& prim_out, Stats& st) {
+    stat_add<STATS>(st, any ? kStatShadow : kStatClosest);
+    if (S.n_nodes == 0) return false;
     RayQuery q;
     q.ox = ox; q.oy = oy; q.oz = oz; q.dx = dx; q.dy = dy; q.dz = dz;
     q.a = dot3(dx, dy, dz, dx, dy, dz);
     q.inv_a = rcp_fast(q.a);
     q.tmin = tmin; q.tbest = tmax; q.best = 0; q.found = false;
-
-    if (S.n_nodes == 0) return false;
     const float ooeps = 8.27180613e-25f;  // 2^-80
     const float idx = rcp_fast(fabsf(dx) > ooeps ? dx : copysignf(ooeps, dx));
     const float idy = rcp_fast(fabsf(dy) > ooeps ? dy : copysignf(ooeps, dy));
@@ -274,30 +267,92 @@ __device__ __forceinline__ bool traverse(const SceneView& S, float ox, float oy,
             const uint32_t v = ~(uint32_t)node;
             const uint32_t start = v & 0x3FFFFFFu;
             const int cnt = (int)((v >> 26) & 15u) + 1;
-            if (((v >> 30) & 1u) == 0) {
-                if (test_spheres<ANY, STATS>(S, q, start, cnt, st)) return true;
-            } else {
-                if (test_tris<ANY, STATS>(S, q, start, cnt, st)) return true;
-            }
-            if (sp == 0) break;
+            if (((v >> 30) & 1u) == 0) test_spheres<STATS>(S, q, start, cnt, st);
+            else test_tris<STATS>(S, q, start, cnt, st);
+            if ((q.found && any) || sp == 0) break;
             node = stack[--sp];
         }
     }
-    if (ANY) return false;
     t_out = q.tbest;
     prim_out = q.best;
     return q.found;
 }
 
 // ---------------------------------------------------------------------------------------------
-// per-warp path queue in shared memory (structure of arrays, one column per queued path)
+// tiny sphere-only scenes (<= kSmallMax spheres, no triangles): the reference's own linear scan
+// (hitWorld renderer.go:337-343), fully unrolled, with the spheres read straight from the kernel
+// parameter bank (constant-bank operands: no load, no address arithmetic).  All tests of a ray are
+// independent instruction streams; the closest-hit reduction keeps the scan order, which makes `<=`
+// the reference's last-wins tie rule.  A shadow query is the same code: "some root lies in
+// [tMin, tMax]" is exactly `found`.
 // ---------------------------------------------------------------------------------------------
-constexpr int kWarpsPerCta = 8;
-constexpr int kQueueCap = 64;  // occupancy never exceeds 63: FILL stops at >= 32, SHADE pops 32, EXTEND pushes <= 32
+template <bool STATS>
+__device__ __forceinline__ bool small_query(const TraceParams& P, float ox, float oy, float oz, float dx, float dy, float dz, float tmin,
+                                            float tmax, bool any, float& t_out, int& prim_out, Stats& st) {
+    stat_add<STATS>(st, any ? kStatShadow : kStatClosest);
+    const float a = dot3(dx, dy, dz, dx, dy, dz);
+    const float inv_a = rcp_fast(a);
+    float tbest = tmax;
+    int best = -1;
+#pragma unroll
+    for (int i = 0; i < kSmallMax; i++) {
+        if (i < P.small_n) {
+            stat_add<STATS>(st, kStatSphereTests);
+            const float4 s = P.small_sph[i];
+            const float ocx = ox - s.x, ocy = oy - s.y, ocz = oz - s.z;
+            const float hb = dot3(ocx, ocy, ocz, dx, dy, dz);
+            const float k = hb * inv_a;
+            const float lx = fmaf(-k, dx, ocx), ly = fmaf(-k, dy, ocy), lz = fmaf(-k, dz, ocz);
+            const float dn = fmaf(s.w, s.w, -dot3(lx, ly, lz, lx, ly, lz));  // discriminant / a (sphere.go:28)
+            if (dn >= 0.f) {  // most tests miss: the roots are only worked out for the few that do not
+                const float sq = sqrt_fast(dn * a);
+                const float r0 = (-hb - sq) * inv_a, r1 = (-hb + sq) * inv_a;
+                // sphere.go:35-40 with tMax = closestT: the near root if it is >= tMin, else the far root
+                const float cand = (r0 < tmin) ? r1 : r0;
+                const bool h = !(cand < tmin || tbest < cand);
+                if (STATS && h) stat_add<STATS>(st, kStatSphereHits);
+                tbest = h ? cand : tbest;
+                best = h ? i : best;
+            }
+        }
+    }
+    t_out = tbest;
+    prim_out = best;
+    return best >= 0;
+}
+
+template <bool STATS, bool SMALL>
+__device__ __forceinline__ bool query(const TraceParams& P, float ox, float oy, float oz, float dx, float dy, float dz, float tmin,
+                                      float tmax, bool any, float& t_out, int& prim_out, Stats& st) {
+    if (SMALL) return small_query<STATS>(P, ox, oy, oz, dx, dy, dz, tmin, tmax, any, t_out, prim_out, st);
+    return traverse<STATS>(P.scene, ox, oy, oz, dx, dy, dz, tmin, tmax, any, t_out, prim_out, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-warp state in shared memory: the path queue (structure of arrays, one column per queued path)
+// and the scratch of the round being shaded
+// ---------------------------------------------------------------------------------------------
+constexpr int kWarpsPerCta = 4;
+constexpr int kQueueCap = 64;   // occupancy never exceeds 63: FILL stops at >= 32, a round pops <= 32 and returns <= 32
+constexpr int kLightChunk = 8;  // lights handled per pass of a round
 enum QField {
     QF_OX, QF_OY, QF_OZ, QF_DX, QF_DY, QF_DZ, QF_T, QF_PRIM,
     QF_TR, QF_TG, QF_TB, QF_LR, QF_LG, QF_LB,
     QF_PIXG, QF_PIXL, QF_SAMPLE, QF_DEPTH, QF_FOG, QF_COUNT
+};
+
+struct WarpShared {
+    uint32_t q[QF_COUNT][kQueueCap];
+    // round scratch, one column per path of the round
+    float n[3][32];        // shading normal (faces the incoming ray)
+    float att[3][32];      // Scatter attenuation x reflection weight
+    float direct[3][32];   // calculateDirectLighting running total
+    float t2[32];          // closest hit of the scattered ray
+    int prim2[32];
+    uint32_t flags[32];    // bit0 scattered, bit1 continues, bit2 scattered ray hit; bits 8.. material index
+    uint8_t lit[kLightChunk][32];  // hard shadow ray unoccluded
+    uint8_t cnt[kLightChunk][32];  // unoccluded soft shadow rays (of 16)
+    uint16_t pairs[kLightChunk * 32];  // lit (light, path) pairs of the chunk: (light << 8) | path
 };
 
 struct PathState {
@@ -328,17 +383,17 @@ __device__ __forceinline__ void queue_load(uint32_t (*Q)[kQueueCap], int slot, P
     s.fog = __uint_as_float(Q[QF_FOG][slot]);
 }
 
+__device__ __forceinline__ float qf(uint32_t (*Q)[kQueueCap], int f, int slot) { return __uint_as_float(Q[f][slot]); }
+
 // Path finished: add its radiance to the pixel's fixed-point accumulators (tracePixel's
 // color.Add, renderer.go:159).  Integer adds commute, so the sum is schedule independent.
-__device__ __forceinline__ void flush_path(const TraceParams& P, const PathState& s) {
-    float r = s.lr, g = s.lg, b = s.lb;
+__device__ __forceinline__ void flush_radiance(const TraceParams& P, uint32_t pixl, float fog, float r, float g, float b) {
     if (P.fog_enabled) {  // extension: exponential fog on the primary-hit distance
-        const float f = s.fog;
-        r = fmaf(r, 1.0f - f, P.fog_r * f);
-        g = fmaf(g, 1.0f - f, P.fog_g * f);
-        b = fmaf(b, 1.0f - f, P.fog_b * f);
+        r = fmaf(r, 1.0f - fog, P.fog_r * fog);
+        g = fmaf(g, 1.0f - fog, P.fog_g * fog);
+        b = fmaf(b, 1.0f - fog, P.fog_b * fog);
     }
-    unsigned long long* acc = P.accum + 3 * (size_t)s.pixl;
+    unsigned long long* acc = P.accum + 3 * (size_t)pixl;
     const float scale = (float)(1u << kAccumFracBits);
     // NaN contributions are dropped (a NaN sample makes the reference's pixel NaN -> undefined uint8)
     if (r != 0.f && r == r) atomicAdd(acc + 0, (unsigned long long)__float2ll_rn(fminf(fmaxf(r, -kSampleClamp), kSampleClamp) * scale));
@@ -352,76 +407,29 @@ __device__ __forceinline__ float pow5(float x) {  // math.Pow(x, 5): sign-preser
 }
 
 // ---------------------------------------------------------------------------------------------
-// tiny sphere-only scenes (<= kSmallMax spheres, no triangles): the reference's own linear scan
-// (hitWorld renderer.go:337-343), fully unrolled, with the spheres read straight from the kernel
-// parameter bank (constant-bank operands: no load, no address arithmetic).  All tests of a ray are
-// independent instruction streams, so the scheduler overlaps them; the closest-hit reduction keeps the
-// scan order, which makes `<=` the reference's last-wins tie rule.
-// ---------------------------------------------------------------------------------------------
-template <bool ANY, bool STATS>
-__device__ __forceinline__ bool small_query(const TraceParams& P, float ox, float oy, float oz, float dx, float dy, float dz, float tmin,
-                                            float tmax, float& t_out, int& prim_out, Stats& st) {
-    stat_add<STATS>(st, ANY ? kStatShadow : kStatClosest);
-    const float a = dot3(dx, dy, dz, dx, dy, dz);
-    const float inv_a = rcp_fast(a);
-    float tbest = tmax;
-    int best = -1;
-    bool any = false;
-#pragma unroll
-    for (int i = 0; i < kSmallMax; i++) {
-        if (i < P.small_n) {
-            stat_add<STATS>(st, kStatSphereTests);
-            const float4 s = P.small_sph[i];
-            const float ocx = ox - s.x, ocy = oy - s.y, ocz = oz - s.z;
-            const float hb = dot3(ocx, ocy, ocz, dx, dy, dz);
-            const float k = hb * inv_a;
-            const float lx = fmaf(-k, dx, ocx), ly = fmaf(-k, dy, ocy), lz = fmaf(-k, dz, ocz);
-            const float dn = fmaf(s.w, s.w, -dot3(lx, ly, lz, lx, ly, lz));  // discriminant / a (sphere.go:28)
-            if (dn >= 0.f) {  // most tests miss: the roots are only worked out for the few that do not
-                const float sq = sqrt_fast(dn * a);
-                const float r0 = (-hb - sq) * inv_a, r1 = (-hb + sq) * inv_a;
-                if (ANY) {
-                    const bool h = !(r0 < tmin || tmax < r0) || !(r1 < tmin || tmax < r1);
-                    if (STATS && h) stat_add<STATS>(st, kStatSphereHits);
-                    any |= h;
-                } else {
-                    // sphere.go:35-40 with tMax = closestT: the near root if it is >= tMin, else the far root
-                    const float cand = (r0 < tmin) ? r1 : r0;
-                    const bool h = !(cand < tmin || tbest < cand);
-                    if (STATS && h) stat_add<STATS>(st, kStatSphereHits);
-                    tbest = h ? cand : tbest;
-                    best = h ? i : best;
-                }
-            }
-        }
-    }
-    if (ANY) return any;
-    t_out = tbest;
-    prim_out = best;
-    return best >= 0;
-}
-
-template <bool ANY, bool STATS, bool SMALL>
-__device__ __forceinline__ bool query(const TraceParams& P, float ox, float oy, float oz, float dx, float dy, float dz, float tmin,
-                                      float tmax, float& t_out, int& prim_out, Stats& st) {
-    if (SMALL) return small_query<ANY, STATS>(P, ox, oy, oz, dx, dy, dz, tmin, tmax, t_out, prim_out, st);
-    return traverse<ANY, STATS>(P.scene, ox, oy, oz, dx, dy, dz, tmin, tmax, t_out, prim_out, st);
-}
-
-// ---------------------------------------------------------------------------------------------
 // the trace kernel
+//
+// One round of a warp shades up to 32 queued hits.  The recursion of traceRay (renderer.go:165-227)
+// is turned inside out so that the rays of a bounce do not wait for one another:
+//   A  per path: hit record + Material.Scatter (direction and attenuation do not depend on the
+//      lighting), results parked in shared memory;
+//   B  ONE packed batch of rays: the hard shadow ray of every (path, light) and the scattered ray of
+//      every continuing path, 32 per step whatever the number of paths;
+//   C  the 16 soft-shadow rays of every lit (path, light) pair, two pairs per step;
+//   D  per path: calculateDirectLighting's arithmetic, traceRay's weighting, flush or re-queue.
+// A bounce is two dependent ray phases (B, C) instead of 2*lights+1, which bounds the latency of a
+// 50-bounce glass path, and the ray phases hold no shading state in registers.
 // ---------------------------------------------------------------------------------------------
 #ifndef GORT_MIN_CTAS
-#define GORT_MIN_CTAS 3
+#define GORT_MIN_CTAS 6
 #endif
-
-__device__ __forceinline__ float qf(uint32_t (*Q)[kQueueCap], int f, int slot) { return __uint_as_float(Q[f][slot]); }
 
 template <bool STATS, bool SMALL>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel(const __grid_constant__ TraceParams P) {
-    __shared__ uint32_t q_smem[kWarpsPerCta][QF_COUNT][kQueueCap];
+    __shared__ WarpShared wsh[kWarpsPerCta];
     const int lane = threadIdx.x & 31;
-    uint32_t(*Q)[kQueueCap] = q_smem[threadIdx.x >> 5];
+    WarpShared& W = wsh[threadIdx.x >> 5];
+    uint32_t(*Q)[kQueueCap] = W.q;
     const SceneView& S = P.scene;
     Stats st;
     if (STATS) {
@@ -442,7 +450,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
     const uint32_t n_batches = (uint32_t)((P.samples + spu - 1) / spu);
     const uint32_t n_units = n_active * n_batches, deep_units = n_deep * n_batches;
 
-    unsigned long long t_units_done = 0;
+    unsigned long long t_units_done = 0, dbg_rounds = 0, dbg_paths = 0;
     if (P.debug_times && lane == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -456,15 +464,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
     uint32_t pix_xy = 0, pixl = 0;
     bool lane_valid = false, jit_valid = false;
     uint32_t jit_z = 0, jit_w = 0;
-
-    // A warp that holds survivors at depth >= urgent_depth shades them at once instead of first topping
-    // its queue up with fresh primary hits: a 50-bounce glass path then advances every ~3 us instead of
-    // once per full round, and no longer forms the tail of the launch (profiles/r1_tail.md).
-    bool urgent = false;  // warp-uniform
+    const unsigned lt_mask = (1u << lane) - 1u;
 
     for (;;) {
         // ================= FILL: primary rays (tracePixel renderer.go:150-163, getRay :377-390) =========
-        while (qcount < 32 && !urgent) {
+        while (qcount < 32) {
             if (s_cur >= s_end) {
                 if (!more_units) break;
                 uint32_t u = 0;
@@ -528,7 +532,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
                 ps.dz = fmaf(v, P.cam.vz, fmaf(u, P.cam.hz, P.cam.llz));
                 // traceRay depth 0 (renderer.go:166-173); max_depth <= 0 returns black before any hit test
                 if (P.max_depth > 0)
-                    hit = query<false, STATS, SMALL>(P, ps.ox, ps.oy, ps.oz, ps.dx, ps.dy, ps.dz, 0.001f, FLT_MAX * 2.0f, ps.t, ps.prim, st);
+                    hit = query<STATS, SMALL>(P, ps.ox, ps.oy, ps.oz, ps.dx, ps.dy, ps.dz, 0.001f, FLT_MAX * 2.0f, false, ps.t, ps.prim, st);
             }
             const unsigned hm = __ballot_sync(FULL_MASK, hit);
             if (hit) {
@@ -540,7 +544,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
                     const float dist = ps.t * sqrt_fast(dot3(ps.dx, ps.dy, ps.dz, ps.dx, ps.dy, ps.dz));
                     ps.fog = 1.0f - expf(-P.fog_density * dist);
                 }
-                queue_store(Q, qcount + __popc(hm & ((1u << lane) - 1u)), ps);
+                queue_store(Q, qcount + __popc(hm & lt_mask), ps);
             }
             qcount += __popc(hm);
             s_cur++;
@@ -548,24 +552,28 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
         if (qcount == 0) break;
         __syncwarp();
 
-        // ================= SHADE: 32 queued hits =========================================================
-        // Only the hit geometry is pulled into registers here; throughput, radiance and the incoming
-        // direction stay in the queue slot until after the light loop (the slots are not overwritten
-        // before EXTEND), which keeps the register count of the shadow-ray loops down.
+        // ================= one round: the top n <= 32 queued hits =========================================
         const int n = min(32, qcount);
-        qcount -= n;
+        const int base = qcount - n;
+        qcount = base;
+        if (P.debug_times && !more_units) {
+            dbg_rounds++;
+            dbg_paths += n;
+        }
         const bool act = lane < n;
-        const int slot = qcount + (act ? lane : 0);
-        const uint32_t h_pixg = Q[QF_PIXG][slot], h_sample = Q[QF_SAMPLE][slot], h_depth = Q[QF_DEPTH][slot];
-        float px, py, pz, nx, ny, nz;
-        bool front;
-        int mat;
-        {
+        const int slot = base + (act ? lane : 0);
+        const float inv_n = 1.0f / (float)n;
+
+        // ---- A: hit record + Material.Scatter (lane = path) ----
+        if (act) {
+            stat_add<STATS>(st, kStatShaded);
             const float dx = qf(Q, QF_DX, slot), dy = qf(Q, QF_DY, slot), dz = qf(Q, QF_DZ, slot);
             const float t = qf(Q, QF_T, slot);
             const int prim = (int)Q[QF_PRIM][slot];
             // hit record (sphere.go:42-50, triangle.go:69-73)
-            px = fmaf(t, dx, qf(Q, QF_OX, slot)); py = fmaf(t, dy, qf(Q, QF_OY, slot)); pz = fmaf(t, dz, qf(Q, QF_OZ, slot));
+            const float px = fmaf(t, dx, qf(Q, QF_OX, slot)), py = fmaf(t, dy, qf(Q, QF_OY, slot)), pz = fmaf(t, dz, qf(Q, QF_OZ, slot));
+            float nx, ny, nz;
+            int mat;
             if (SMALL) {
                 const float4 s = P.small_sph[prim];
                 const float inv_r = rcp_fast(s.w);
@@ -582,127 +590,32 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
                 const float4 nn = ldg4(tp + 3);
                 nx = nn.x; ny = nn.y; nz = nn.z;
             }
-            front = dot3(dx, dy, dz, nx, ny, nz) < 0.f;
+            const float ddn0 = dot3(dx, dy, dz, nx, ny, nz);
+            const bool front = ddn0 < 0.f;
             if (!front) { nx = -nx; ny = -ny; nz = -nz; }
-        }
-        const float4* mp = S.mats + 4 * (size_t)mat;
+            const float ddn = front ? ddn0 : -ddn0;  // ray.Direction . normal (<= 0)
 
-        // ---- calculateDirectLighting (renderer.go:229-297) ----
-        float dr, dg, db;        // running total, starts at the ambient term
-        float kar, kag, kab;     // diffuseStrength * albedo
-        float spec_w, spec_pow;  // metallic * 3 and the Blinn-Phong exponent (0: no specular term)
-        {
-            const float4 m0 = ldg4(mp), m2 = ldg4(mp + 2);  // (type, color) (ambient, kd, wr, wd)
-            const bool is_light = __float_as_int(m0.x) == 6;
-            // GetAlbedo: DiffuseLight -> 0 (material.go:304); Dielectric -> 1 (packed by the host)
-            kar = is_light ? 0.f : m0.y * m2.y; kag = is_light ? 0.f : m0.z * m2.y; kab = is_light ? 0.f : m0.w * m2.y;
-            dr = dg = db = m2.x;
-            spec_pow = __ldg(&mp[3].x);
-            spec_w = __ldg(&mp[1].y) * 3.0f;
-        }
-        for (int l = 0; l < S.n_lights; l++) {
-            const float4 L0 = ldg4(S.lights + 2 * l);
-            float ldx = L0.x - px, ldy = L0.y - py, ldz = L0.z - pz;
-            const float dist2 = dot3(ldx, ldy, ldz, ldx, ldy, ldz);
-            const float inv_d = dist2 > 0.f ? rsqrt_fast(dist2) : 0.f;
-            const float dist = dist2 * inv_d;
-            ldx *= inv_d; ldy *= inv_d; ldz *= inv_d;
-            const bool consider = act && !(dist < 0.001f);
-            // ---- calculateSmartShadow (renderer.go:299-331): hard ray first ----
-            bool lit = false;
-            if (consider) {
-                float tt;
-                int pp;
-                stat_add<STATS>(st, kStatLightEvals);
-                lit = !query<true, STATS, SMALL>(P, px, py, pz, ldx, ldy, ldz, 0.001f, dist, tt, pp, st);
-            }
-            float factor = lit ? 1.0f : 0.0f;
-            if (P.soft) {
-                // 16 jittered rays per lit (path, light): two pairs per step, one per half warp
-                unsigned m = __ballot_sync(FULL_MASK, lit);
-                int cnt = 0;
-                while (m) {
-                    const int a = __ffs(m) - 1;
-                    m &= m - 1;
-                    int b = -1;
-                    if (m) {
-                        b = __ffs(m) - 1;
-                        m &= m - 1;
-                    }
-                    const int src = (lane < 16) ? a : b;
-                    const int srcc = src < 0 ? 0 : src;
-                    const float spx = __shfl_sync(FULL_MASK, px, srcc), spy = __shfl_sync(FULL_MASK, py, srcc), spz = __shfl_sync(FULL_MASK, pz, srcc);
-                    float sdx = __shfl_sync(FULL_MASK, ldx, srcc), sdy = __shfl_sync(FULL_MASK, ldy, srcc), sdz = __shfl_sync(FULL_MASK, ldz, srcc);
-                    const float sdist = __shfl_sync(FULL_MASK, dist, srcc);
-                    const uint32_t spix = __shfl_sync(FULL_MASK, h_pixg, srcc);
-                    const uint32_t ssamp = __shfl_sync(FULL_MASK, h_sample, srcc);
-                    const uint32_t sdepth = __shfl_sync(FULL_MASK, h_depth, srcc);
-                    bool unocc = false;
-                    if (src >= 0) {
-                        float bx, by, bz;
-                        stat_add<STATS>(st, kStatSoftRays);
-                        rng_ball<STATS>(P, spix, ssamp, (sdepth << 8) | kStreamShadow, ((uint32_t)l << 12) | ((uint32_t)(lane & 15) << 8), bx, by, bz, st);
-                        sdx = fmaf(0.1f, bx, sdx); sdy = fmaf(0.1f, by, sdy); sdz = fmaf(0.1f, bz, sdz);
-                        normalize3(sdx, sdy, sdz);
-                        float tt;
-                        int pp;
-                        unocc = !query<true, STATS, SMALL>(P, spx, spy, spz, sdx, sdy, sdz, 0.001f, sdist, tt, pp, st);
-                    }
-                    const unsigned ub = __ballot_sync(FULL_MASK, unocc);
-                    if (lane == a) cnt = __popc(ub & 0xFFFFu);
-                    if (lane == b) cnt = __popc(ub >> 16);
-                }
-                factor = lit ? (float)cnt * (1.0f / 16.0f) : 0.0f;
-            }
-            if (factor > 0.0f) {
-                stat_add<STATS>(st, kStatDiffuse);
-                const float cosT = fmaxf(0.f, dot3(nx, ny, nz, ldx, ldy, ldz));
-                const float inten = cosT * L0.w * (inv_d * inv_d);
-                const float kdw = inten * factor;
-                dr = fmaf(kar, kdw, dr); dg = fmaf(kag, kdw, dg); db = fmaf(kab, kdw, db);
-                if (spec_pow > 0.f) {  // metallic > 0.5, resolved in float64 on the host
-                    stat_add<STATS>(st, kStatSpec);
-                    const float4 L1 = ldg4(S.lights + 2 * l + 1);
-                    float vx = -px, vy = -py, vz = -pz;  // viewDir toward the world origin (renderer.go:279)
-                    normalize3(vx, vy, vz);
-                    float hx = ldx + vx, hy = ldy + vy, hz = ldz + vz;
-                    normalize3(hx, hy, hz);
-                    const float nh = fmaxf(0.f, dot3(nx, ny, nz, hx, hy, hz));
-                    const float x2 = nh * nh, x4 = x2 * x2, x8 = x4 * x4, x16 = x8 * x8, x32 = x16 * x16;
-                    const float si = (spec_pow > 56.f) ? x32 * x32 : ((spec_pow > 40.f) ? x32 * x16 : x32);
-                    const float sw = si * inten * factor * spec_w;
-                    dr = fmaf(L1.x, sw, dr); dg = fmaf(L1.y, sw, dg); db = fmaf(L1.z, sw, db);
-                }
-            }
-        }
-
-        // ---- Material.Scatter + traceRay's combination (renderer.go:177-226) ----
-        PathState ps;
-        bool cont = false;
-        if (act) {
-            stat_add<STATS>(st, kStatShaded);
-            queue_load(Q, slot, ps);  // the rest of the path state, still intact in the queue slot
+            const float4* mp = S.mats + 4 * (size_t)mat;
             const float4 m0 = ldg4(mp), m1 = ldg4(mp + 1), m2 = ldg4(mp + 2), m3 = ldg4(mp + 3);
             const int mtype = __float_as_int(m0.x);
-            const bool is_light = (mtype == 6);
-            const float er = is_light ? m0.y : 0.f, eg = is_light ? m0.z : 0.f, eb = is_light ? m0.w : 0.f;  // Emitted
+            const uint32_t depth = Q[QF_DEPTH][slot];
+            const uint32_t pixg = Q[QF_PIXG][slot], sample = Q[QF_SAMPLE][slot];
+            const uint32_t bs = (depth << 8) | kStreamScatter;
             bool scattered = true;
             float sx = 0.f, sy = 0.f, sz = 0.f, ar = 0.f, ag = 0.f, ab = 0.f;
-            const uint32_t bs = (ps.depth << 8) | kStreamScatter;
-            const float ddn = dot3(ps.dx, ps.dy, ps.dz, nx, ny, nz);
             if (mtype == 0) {  // Lambertian (material.go:26-35)
                 float bx, by, bz;
-                rng_ball<STATS>(P, ps.pixg, ps.sample, bs, 0u, bx, by, bz, st);
+                rng_ball<STATS>(P, pixg, sample, bs, 0u, bx, by, bz, st);
                 sx = nx + bx; sy = ny + by; sz = nz + bz;
                 if (fabsf(sx) < 1e-8f && fabsf(sy) < 1e-8f && fabsf(sz) < 1e-8f) { sx = nx; sy = ny; sz = nz; }
                 normalize3(sx, sy, sz);
                 ar = m0.y; ag = m0.z; ab = m0.w;
             } else if (mtype <= 3) {  // Metal / Shiny / PerfectMirror (material.go:75-113,169-189; advanced_materials.go:125-144)
-                sx = fmaf(-2.0f * ddn, nx, ps.dx); sy = fmaf(-2.0f * ddn, ny, ps.dy); sz = fmaf(-2.0f * ddn, nz, ps.dz);  // Reflect vector.go:77
+                sx = fmaf(-2.0f * ddn, nx, dx); sy = fmaf(-2.0f * ddn, ny, dy); sz = fmaf(-2.0f * ddn, nz, dz);  // Reflect vector.go:77
                 const bool rough = (mtype == 2) ? (m1.x > 0.f) : (m1.x > 0.001f);
                 if (rough) {
                     float bx, by, bz;
-                    rng_ball<STATS>(P, ps.pixg, ps.sample, bs, 0u, bx, by, bz, st);
+                    rng_ball<STATS>(P, pixg, sample, bs, 0u, bx, by, bz, st);
                     sx = fmaf(m1.x, bx, sx); sy = fmaf(m1.x, by, sy); sz = fmaf(m1.x, bz, sz);
                     normalize3(sx, sy, sz);
                 }
@@ -722,7 +635,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
             } else if (mtype <= 5) {  // Glass / Dielectric (advanced_materials.go:21-46; material.go:235-260)
                 ar = m0.y; ag = m0.z; ab = m0.w;  // Glass colour; Dielectric packed as (1,1,1)
                 const float ratio = front ? m3.z : m1.w;  // 1/ior precomputed in float64 on the host
-                float ux = ps.dx, uy = ps.dy, uz = ps.dz;
+                float ux = dx, uy = dy, uz = dz;
                 normalize3(ux, uy, uz);
                 const float udn = dot3(ux, uy, uz, nx, ny, nz);
                 const float cosT = fminf(-udn, 1.0f);
@@ -731,7 +644,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
                 if (!reflect) {
                     const float r0 = m3.y;  // ((1-x)/(1+x))^2 is the same for x = ior and x = 1/ior
                     const float refl = fmaf(1.0f - r0, pow5(1.0f - cosT), r0);  // reflectance material.go:282-286
-                    const uint4 r = philox(P.rk, ps.pixg, ps.sample, bs, 0u);
+                    const uint4 r = philox(P.rk, pixg, sample, bs, 0u);
                     stat_add<STATS>(st, kStatRngBlocks);
                     reflect = refl > (float)(r.x >> 8) * (1.0f / 16777216.0f);
                 }
@@ -753,35 +666,205 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
             } else {  // DiffuseLight (material.go:296-298)
                 scattered = false;
             }
-            if (!scattered) {
-                ps.lr = fmaf(ps.tr, er + dr, ps.lr); ps.lg = fmaf(ps.tg, eg + dg, ps.lg); ps.lb = fmaf(ps.tb, eb + db, ps.lb);
-                flush_path(P, ps);
-            } else {
-                const float wr = m2.z, wd = m2.w;
-                ps.lr = fmaf(ps.tr, fmaf(dr, wd, er), ps.lr); ps.lg = fmaf(ps.tg, fmaf(dg, wd, eg), ps.lg); ps.lb = fmaf(ps.tb, fmaf(db, wd, eb), ps.lb);
-                ps.tr *= ar * wr; ps.tg *= ag * wr; ps.tb *= ab * wr;
-                ps.depth += 1;
-                if (!P.recursive || (int)ps.depth >= P.max_depth) {
-                    flush_path(P, ps);  // reflectedColor = 0 (renderer.go:166-168,186-189)
+            // traceRay(scattered, depth+1) returns black at once when depth+1 >= maxDepth or when
+            // recursiveReflections is off (renderer.go:166-168,186-189): no ray needed
+            const bool cont = scattered && P.recursive && (int)(depth + 1) < P.max_depth;
+            const float wr = m2.z;
+            W.n[0][lane] = nx; W.n[1][lane] = ny; W.n[2][lane] = nz;
+            W.att[0][lane] = ar * wr; W.att[1][lane] = ag * wr; W.att[2][lane] = ab * wr;
+            W.direct[0][lane] = m2.x; W.direct[1][lane] = m2.x; W.direct[2][lane] = m2.x;  // ambient (renderer.go:236-246)
+            W.flags[lane] = (scattered ? 1u : 0u) | (cont ? 2u : 0u) | ((uint32_t)mat << 8);
+            // the slot now carries the NEXT segment: origin = hit point, direction = scattered direction
+            Q[QF_OX][slot] = __float_as_uint(px); Q[QF_OY][slot] = __float_as_uint(py); Q[QF_OZ][slot] = __float_as_uint(pz);
+            Q[QF_DX][slot] = __float_as_uint(sx); Q[QF_DY][slot] = __float_as_uint(sy); Q[QF_DZ][slot] = __float_as_uint(sz);
+        }
+        __syncwarp();
+
+        // ---- B + C per chunk of lights ----
+        const int nl = S.n_lights;
+        bool ext_done = false;
+        for (int l0 = 0; l0 < nl || !ext_done; l0 += kLightChunk) {
+            const int lc = max(0, min(kLightChunk, nl - l0));
+            // B: rays [0, n*lc) are the hard shadow rays (light-major), rays [n*lc, n*lc+n) the scattered rays
+            const int n_hard = n * lc;
+            const int n_rays = n_hard + (ext_done ? 0 : n);
+            for (int r0 = 0; r0 < n_rays; r0 += 32) {
+                const int r = r0 + lane;
+                const bool valid = r < n_rays;
+                const int li = valid ? (int)(((float)r + 0.5f) * inv_n) : 0;
+                const int j = r - li * n;
+                const int sj = base + (valid ? j : 0);
+                const bool is_ext = li >= lc;
+                float ox = qf(Q, QF_OX, sj), oy = qf(Q, QF_OY, sj), oz = qf(Q, QF_OZ, sj);
+                float dx, dy, dz, tmax;
+                bool go = valid;
+                if (is_ext) {
+                    dx = qf(Q, QF_DX, sj); dy = qf(Q, QF_DY, sj); dz = qf(Q, QF_DZ, sj);
+                    tmax = FLT_MAX * 2.0f;
+                    go = go && (W.flags[valid ? j : 0] & 2u);
                 } else {
-                    ps.ox = px; ps.oy = py; ps.oz = pz;
-                    ps.dx = sx; ps.dy = sy; ps.dz = sz;
-                    cont = true;
+                    const float4 L0 = ldg4(S.lights + 2 * (l0 + li));
+                    dx = L0.x - ox; dy = L0.y - oy; dz = L0.z - oz;
+                    const float dist2 = dot3(dx, dy, dz, dx, dy, dz);
+                    const float inv_d = dist2 > 0.f ? rsqrt_fast(dist2) : 0.f;
+                    tmax = dist2 * inv_d;  // lightDistance
+                    dx *= inv_d; dy *= inv_d; dz *= inv_d;
+                    go = go && !(tmax < 0.001f);  // renderer.go:252-254
+                    if (go) stat_add<STATS>(st, kStatLightEvals);
+                }
+                float tt = 0.f;
+                int pp = 0;
+                bool h = false;
+                if (go) h = query<STATS, SMALL>(P, ox, oy, oz, dx, dy, dz, 0.001f, tmax, !is_ext, tt, pp, st);
+                if (valid) {
+                    if (is_ext) {
+                        if (h) {
+                            W.t2[j] = tt;
+                            W.prim2[j] = pp;
+                            W.flags[j] |= 4u;
+                        }
+                    } else {
+                        W.lit[li][j] = (go && !h) ? 1 : 0;
+                    }
+                }
+            }
+            ext_done = true;
+            __syncwarp();
+            if (lc == 0) break;
+
+            // C: calculateSmartShadow's 16 jittered rays (renderer.go:311-328) for every lit pair of the chunk
+            if (P.soft) {
+                int np = 0;
+                for (int li = 0; li < lc; li++) {
+                    const bool bit = act && W.lit[li][lane];
+                    const unsigned m = __ballot_sync(FULL_MASK, bit);
+                    if (bit) W.pairs[np + __popc(m & lt_mask)] = (uint16_t)((li << 8) | lane);
+                    np += __popc(m);
+                }
+                __syncwarp();
+                for (int q0 = 0; q0 < np; q0 += 2) {
+                    const int qi = q0 + (lane >> 4);
+                    const bool valid = qi < np;
+                    const int pr = valid ? (int)W.pairs[qi] : 0;
+                    const int li = pr >> 8, j = pr & 31;
+                    const int sj = base + j;
+                    bool unocc = false;
+                    if (valid) {
+                        const float ox = qf(Q, QF_OX, sj), oy = qf(Q, QF_OY, sj), oz = qf(Q, QF_OZ, sj);
+                        const float4 L0 = ldg4(S.lights + 2 * (l0 + li));
+                        float dx = L0.x - ox, dy = L0.y - oy, dz = L0.z - oz;
+                        const float dist2 = dot3(dx, dy, dz, dx, dy, dz);
+                        const float inv_d = rsqrt_fast(dist2);
+                        const float dist = dist2 * inv_d;
+                        float bx, by, bz;
+                        stat_add<STATS>(st, kStatSoftRays);
+                        rng_ball<STATS>(P, Q[QF_PIXG][sj], Q[QF_SAMPLE][sj], (Q[QF_DEPTH][sj] << 8) | kStreamShadow,
+                                        ((uint32_t)(l0 + li) << 12) | ((uint32_t)(lane & 15) << 8), bx, by, bz, st);
+                        dx = fmaf(dx, inv_d, 0.1f * bx); dy = fmaf(dy, inv_d, 0.1f * by); dz = fmaf(dz, inv_d, 0.1f * bz);
+                        normalize3(dx, dy, dz);
+                        float tt;
+                        int pp;
+                        unocc = !query<STATS, SMALL>(P, ox, oy, oz, dx, dy, dz, 0.001f, dist, true, tt, pp, st);
+                    }
+                    const unsigned ub = __ballot_sync(FULL_MASK, unocc);
+                    if (valid && (lane & 15) == 0) W.cnt[li][j] = (uint8_t)__popc((lane < 16) ? (ub & 0xFFFFu) : (ub >> 16));
+                }
+                __syncwarp();
+            }
+
+            // D (lighting part): calculateDirectLighting's arithmetic for the chunk (renderer.go:258-293), lane = path
+            if (act) {
+                const float4* mp = S.mats + 4 * (size_t)(W.flags[lane] >> 8);
+                const float4 m0 = ldg4(mp), m2 = ldg4(mp + 2);
+                const bool is_light = __float_as_int(m0.x) == 6;
+                // GetAlbedo: DiffuseLight -> 0 (material.go:304); Dielectric -> 1 (packed by the host)
+                const float kar = is_light ? 0.f : m0.y * m2.y, kag = is_light ? 0.f : m0.z * m2.y, kab = is_light ? 0.f : m0.w * m2.y;
+                const float spec_pow = __ldg(&mp[3].x);         // 0: metallic <= 0.5, no specular term
+                const float spec_w = __ldg(&mp[1].y) * 3.0f;    // metallic * 3
+                const float px = qf(Q, QF_OX, slot), py = qf(Q, QF_OY, slot), pz = qf(Q, QF_OZ, slot);
+                const float nx = W.n[0][lane], ny = W.n[1][lane], nz = W.n[2][lane];
+                float dr = W.direct[0][lane], dg = W.direct[1][lane], db = W.direct[2][lane];
+                for (int li = 0; li < lc; li++) {
+                    if (!W.lit[li][lane]) continue;
+                    const float factor = P.soft ? (float)W.cnt[li][lane] * (1.0f / 16.0f) : 1.0f;
+                    if (!(factor > 0.0f)) continue;
+                    stat_add<STATS>(st, kStatDiffuse);
+                    const float4 L0 = ldg4(S.lights + 2 * (l0 + li));
+                    float ldx = L0.x - px, ldy = L0.y - py, ldz = L0.z - pz;
+                    const float dist2 = dot3(ldx, ldy, ldz, ldx, ldy, ldz);
+                    const float inv_d = rsqrt_fast(dist2);
+                    ldx *= inv_d; ldy *= inv_d; ldz *= inv_d;
+                    const float cosT = fmaxf(0.f, dot3(nx, ny, nz, ldx, ldy, ldz));
+                    const float inten = cosT * L0.w * (inv_d * inv_d);
+                    const float kdw = inten * factor;
+                    dr = fmaf(kar, kdw, dr); dg = fmaf(kag, kdw, dg); db = fmaf(kab, kdw, db);
+                    if (spec_pow > 0.f) {  // metallic > 0.5, resolved in float64 on the host
+                        stat_add<STATS>(st, kStatSpec);
+                        const float4 L1 = ldg4(S.lights + 2 * (l0 + li) + 1);
+                        float vx = -px, vy = -py, vz = -pz;  // viewDir toward the world origin (renderer.go:279)
+                        normalize3(vx, vy, vz);
+                        float hx = ldx + vx, hy = ldy + vy, hz = ldz + vz;
+                        normalize3(hx, hy, hz);
+                        const float nh = fmaxf(0.f, dot3(nx, ny, nz, hx, hy, hz));
+                        const float x2 = nh * nh, x4 = x2 * x2, x8 = x4 * x4, x16 = x8 * x8, x32 = x16 * x16;
+                        const float si = (spec_pow > 56.f) ? x32 * x32 : ((spec_pow > 40.f) ? x32 * x16 : x32);
+                        const float sw = si * inten * factor * spec_w;
+                        dr = fmaf(L1.x, sw, dr); dg = fmaf(L1.y, sw, dg); db = fmaf(L1.z, sw, db);
+                    }
+                }
+                W.direct[0][lane] = dr; W.direct[1][lane] = dg; W.direct[2][lane] = db;
+            }
+        }
+
+        // ---- D (combination): traceRay's weighting (renderer.go:177-226), flush or re-queue ----
+        PathState ps;
+        bool survive = false;
+        if (act) {
+            queue_load(Q, slot, ps);  // origin/direction already describe the scattered ray
+            const uint32_t fl = W.flags[lane];
+            const float4* mp = S.mats + 4 * (size_t)(fl >> 8);
+            const float4 m0 = ldg4(mp), m2 = ldg4(mp + 2);
+            const bool is_light = __float_as_int(m0.x) == 6;
+            const float er = is_light ? m0.y : 0.f, eg = is_light ? m0.z : 0.f, eb = is_light ? m0.w : 0.f;  // Emitted
+            const float dr = W.direct[0][lane], dg = W.direct[1][lane], db = W.direct[2][lane];
+            if (!(fl & 1u)) {  // no scatter: emitted + direct (renderer.go:182-184)
+                ps.lr = fmaf(ps.tr, er + dr, ps.lr); ps.lg = fmaf(ps.tg, eg + dg, ps.lg); ps.lb = fmaf(ps.tb, eb + db, ps.lb);
+            } else {
+                const float wd = m2.w;
+                ps.lr = fmaf(ps.tr, fmaf(dr, wd, er), ps.lr); ps.lg = fmaf(ps.tg, fmaf(dg, wd, eg), ps.lg); ps.lb = fmaf(ps.tb, fmaf(db, wd, eb), ps.lb);
+                ps.tr *= W.att[0][lane]; ps.tg *= W.att[1][lane]; ps.tb *= W.att[2][lane];
+                ps.depth += 1;
+                if (fl & 4u) {  // the scattered ray hit something: the path goes on
+                    ps.t = W.t2[lane];
+                    ps.prim = W.prim2[lane];
+                    survive = true;
+                    // Exact dead-path test.  Whatever the remaining bounces return, it reaches this
+                    // sample as fma(T, c, L) terms with |T c| <= T * dead_bound.  If that is below
+                    // 2^-25 |L| in every channel, each such term is less than half an ulp of L and
+                    // round-to-nearest leaves L bit-for-bit unchanged: tracing on cannot alter the
+                    // result.  (Rays trapped inside a rough-metal sphere keep bouncing to max_depth
+                    // in the reference with throughput ~0.03^k; 95 such paths were the 30 % tail of
+                    // the C1 frame, profiles/r1_tail.md.)
+                    const float db = P.dead_bound;
+                    if (db > 0.f && fabsf(ps.tr) * db < 2.98023224e-8f * fabsf(ps.lr) && fabsf(ps.tg) * db < 2.98023224e-8f * fabsf(ps.lg) &&
+                        fabsf(ps.tb) * db < 2.98023224e-8f * fabsf(ps.lb))
+                        survive = false;
+                }
+            }
+            // miss, depth limit, no scatter: the reflected colour is black and the sample is complete
+            if (!survive) {
+                flush_radiance(P, ps.pixl, ps.fog, ps.lr, ps.lg, ps.lb);
+                if (STATS) {
+                    if (ps.depth >= 5) stat_add<STATS>(st, kStatDepth5);
+                    if (ps.depth >= 20) stat_add<STATS>(st, kStatDepth20);
+                    if ((int)ps.depth >= P.max_depth) stat_add<STATS>(st, kStatDepthMax);
                 }
             }
         }
-        __syncwarp();  // every lane has read its slot before EXTEND overwrites the popped region
-
-        // ================= EXTEND: hitWorld for the scattered rays =======================================
-        bool hit = false;
-        if (cont) {
-            hit = query<false, STATS, SMALL>(P, ps.ox, ps.oy, ps.oz, ps.dx, ps.dy, ps.dz, 0.001f, FLT_MAX * 2.0f, ps.t, ps.prim, st);
-            if (!hit) flush_path(P, ps);  // miss returns black (renderer.go:171-173)
-        }
-        const unsigned hm = __ballot_sync(FULL_MASK, hit);
-        if (hit) queue_store(Q, qcount + __popc(hm & ((1u << lane) - 1u)), ps);
-        qcount += __popc(hm);
-        urgent = __any_sync(FULL_MASK, hit && (int)ps.depth >= P.urgent_depth);
+        __syncwarp();  // every lane has read its slot before the survivors are compacted over the popped region
+        const unsigned hm = __ballot_sync(FULL_MASK, survive);
+        if (survive) queue_store(Q, base + __popc(hm & lt_mask), ps);
+        qcount = base + __popc(hm);
         __syncwarp();
     }
 
@@ -789,8 +872,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         const unsigned int w = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-        P.debug_times[1 + 2 * w] = t_units_done;
-        P.debug_times[2 + 2 * w] = t;
+        P.debug_times[1 + 4 * w] = t_units_done;
+        P.debug_times[2 + 4 * w] = t;
+        P.debug_times[3 + 4 * w] = dbg_rounds;
+        P.debug_times[4 + 4 * w] = dbg_paths;
     }
     if (STATS && P.stats) {
 #pragma unroll
@@ -967,22 +1052,26 @@ static cudaError_t launch_trace_variant(const TraceParams& p, int sm_count, cuda
     if (p.debug_times) {  // GORT_DEBUG_TIMES: per-warp finish times of this launch on stderr
         const int nw = sm_count * ctas_per_sm * kWarpsPerCta;
         cudaMemsetAsync(p.debug_times, 0xff, 8, stream);
-        cudaMemsetAsync(p.debug_times + 1, 0, (size_t)nw * 16, stream);
+        cudaMemsetAsync(p.debug_times + 1, 0, (size_t)nw * 32, stream);
         trace_kernel<STATS, SMALL><<<sm_count * ctas_per_sm, kWarpsPerCta * 32, 0, stream>>>(p);
-        std::vector<unsigned long long> h(1 + 2 * (size_t)nw);
+        std::vector<unsigned long long> h(1 + 4 * (size_t)nw);
         cudaMemcpyAsync(h.data(), p.debug_times, h.size() * 8, cudaMemcpyDeviceToHost, stream);
         cudaStreamSynchronize(stream);
-        std::vector<double> units, drain;
+        struct Rec { double units, end; unsigned long long rounds, paths; };
+        std::vector<Rec> recs;
         for (int w = 0; w < nw; w++) {
-            if (!h[2 + 2 * w]) continue;
-            units.push_back((double)(h[1 + 2 * w] - h[0]) * 1e-3);
-            drain.push_back((double)(h[2 + 2 * w] - h[0]) * 1e-3);
+            if (!h[2 + 4 * w]) continue;
+            recs.push_back(Rec{(double)(h[1 + 4 * w] - h[0]) * 1e-3, (double)(h[2 + 4 * w] - h[0]) * 1e-3, h[3 + 4 * w], h[4 + 4 * w]});
         }
-        std::sort(units.begin(), units.end());
-        std::sort(drain.begin(), drain.end());
-        auto pct = [](const std::vector<double>& v, double q) { return v.empty() ? 0.0 : v[(size_t)(q * (v.size() - 1))]; };
-        fprintf(stderr, "[gort debug] warps %zu  units-exhausted us: p0 %.1f p50 %.1f p100 %.1f | warp-finished us: p0 %.1f p10 %.1f p50 %.1f p90 %.1f p99 %.1f p100 %.1f\n",
-                drain.size(), pct(units, 0), pct(units, 0.5), pct(units, 1), pct(drain, 0), pct(drain, 0.1), pct(drain, 0.5), pct(drain, 0.9), pct(drain, 0.99), pct(drain, 1));
+        std::sort(recs.begin(), recs.end(), [](const Rec& a, const Rec& b) { return a.end < b.end; });
+        auto at = [&](double q) -> const Rec& { return recs[(size_t)(q * (recs.size() - 1))]; };
+        if (!recs.empty()) {
+            fprintf(stderr, "[gort debug] warps %zu finish us p0 %.1f p10 %.1f p50 %.1f p90 %.1f p99 %.1f p100 %.1f\n", recs.size(), at(0).end, at(0.1).end,
+                    at(0.5).end, at(0.9).end, at(0.99).end, at(1).end);
+            for (size_t i = recs.size() > 8 ? recs.size() - 8 : 0; i < recs.size(); i++)
+                fprintf(stderr, "[gort debug]   slow warp: units exhausted %.1f us, end %.1f us, rounds after %llu, paths after %llu\n", recs[i].units, recs[i].end,
+                        recs[i].rounds, recs[i].paths);
+        }
         return cudaGetLastError();
     }
     trace_kernel<STATS, SMALL><<<sm_count * ctas_per_sm, kWarpsPerCta * 32, 0, stream>>>(p);
@@ -1077,8 +1166,8 @@ __global__ void trace_rays_kernel(const SceneView S, int n, const float* __restr
     float t = -1.f;
     int prim = 0;
     bool hit;
-    if (any_hit) hit = traverse<true, false>(S, o[3 * i], o[3 * i + 1], o[3 * i + 2], d[3 * i], d[3 * i + 1], d[3 * i + 2], tmin, tmax, t, prim, st);
-    else hit = traverse<false, false>(S, o[3 * i], o[3 * i + 1], o[3 * i + 2], d[3 * i], d[3 * i + 1], d[3 * i + 2], tmin, tmax, t, prim, st);
+    if (any_hit) hit = traverse<false>(S, o[3 * i], o[3 * i + 1], o[3 * i + 2], d[3 * i], d[3 * i + 1], d[3 * i + 2], tmin, tmax, true, t, prim, st);
+    else hit = traverse<false>(S, o[3 * i], o[3 * i + 1], o[3 * i + 2], d[3 * i], d[3 * i + 1], d[3 * i + 2], tmin, tmax, false, t, prim, st);
     if (any_hit) {
         out_t[i] = hit ? 1.f : -1.f;
         out_order[i] = -1;

@@ -33,6 +33,9 @@ enum StatIndex {
     kStatSoftRays = 14,    // soft shadow rays
     kStatDiffuse = 15,     // (hit, light) pairs with shadowFactor > 0
     kStatSpec = 16,        // ... that also evaluate the Blinn-Phong term
+    kStatDepth5 = 17,      // samples whose path reached depth >= 5 / >= 20 / max_depth
+    kStatDepth20 = 18,
+    kStatDepthMax = 19,
     kStatCount = 20
 };
 
@@ -67,7 +70,6 @@ struct TraceParams {
     const uint32_t* active_list;     // pixel blocks kept by the cull pass: (local tile << 5) | block;
                                      // [0, n_deep) from the front, n_norm more from the back of [0, 32*n_local_tiles)
     const unsigned int* active_count;  // {n_deep, n_norm}
-    int urgent_depth;                // survivors at this depth or deeper are shaded before the queue is refilled
     unsigned long long* accum;   // [n_local_tiles][1024][3] int64 fixed point
     unsigned int* work_counter;  // zeroed before launch
     unsigned long long* stats;   // [kStatCount] or nullptr
@@ -75,6 +77,9 @@ struct TraceParams {
     uint32_t rk[20];             // Philox4x32-10 round keys: rk[2r] = key0 + r*W0, rk[2r+1] = key1 + r*W1
     int fog_enabled;
     float fog_density, fog_r, fog_g, fog_b;
+    // Upper bound on |radiance| any further bounce sequence can return per unit of throughput (host,
+    // float64, deliberately loose): used by the exact dead-path test in trace_kernel.  0 disables it.
+    float dead_bound;
     // tiny sphere-only scene, in the reference's scan order (small_n == 0: use the BVH)
     int small_n;
     int small_mat[kSmallMax];

@@ -159,6 +159,7 @@ typedef struct gort_stats {
     uint64_t soft_shadow_rays;
     uint64_t diffuse_evals;   /* (hit, light) pairs with shadowFactor > 0 */
     uint64_t specular_evals;  /* ... of which metallic > 0.5 (Blinn-Phong term) */
+    uint64_t paths_depth_ge5, paths_depth_ge20, paths_depth_max; /* samples whose path reached that depth */
     double algorithmic_flops; /* SURVEY §8d per-operation costs applied to the counters above */
 } gort_stats;
 
