@@ -92,6 +92,7 @@ class Stats(C.Structure):
         ("shaded_hits", C.c_uint64), ("rng_blocks", C.c_uint64), ("light_evals", C.c_uint64), ("soft_shadow_rays", C.c_uint64),
         ("diffuse_evals", C.c_uint64), ("specular_evals", C.c_uint64),
         ("paths_depth_ge5", C.c_uint64), ("paths_depth_ge20", C.c_uint64), ("paths_depth_max", C.c_uint64),
+        ("cone_tests", C.c_uint64),
         ("algorithmic_flops", C.c_double),
     ]
 

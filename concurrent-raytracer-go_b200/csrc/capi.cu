@@ -285,7 +285,7 @@ int validate(gort_ctx* ctx, const gort_render_params* p) {
     if ((int64_t)p->width * p->height > (int64_t)1 << 28) return fail(ctx, GORT_ERR_INVALID, "image too large");
     if (p->width > 65535 || p->height > 65535) return fail(ctx, GORT_ERR_INVALID, "width/height must be <= 65535");
     if (p->samples <= 0 || p->samples > 65535) return fail(ctx, GORT_ERR_INVALID, "samples must be in 1..65535");
-    if (p->max_depth < 0 || p->max_depth > (1 << 20)) return fail(ctx, GORT_ERR_INVALID, "max_depth out of range");
+    if (p->max_depth < 0 || p->max_depth > 65535) return fail(ctx, GORT_ERR_INVALID, "max_depth must be in 0..65535");
     const int sc = p->shard_count <= 0 ? 1 : p->shard_count;
     if (p->shard_rank < 0 || p->shard_rank >= sc) return fail(ctx, GORT_ERR_INVALID, "shard_rank out of range");
     if (p->camera_mode != GORT_CAMERA_REFERENCE && p->camera_mode != GORT_CAMERA_LOOKAT) return fail(ctx, GORT_ERR_INVALID, "camera_mode");
@@ -361,6 +361,11 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
         tp.rk[2 * r + 1] = k1 + (uint32_t)r * 0xBB67AE85u;
     }
     tp.dead_bound = getenv("GORT_NO_DEAD_PATH") ? 0.f : dead_path_bound(ctx->scene, tp.cam, p->max_depth);
+    tp.no_cone_cull = getenv("GORT_NO_CONE_CULL") ? 1 : 0;
+    {
+        const char* ud = getenv("GORT_URGENT_DEPTH");
+        tp.urgent_depth = ud ? atoi(ud) : 3;
+    }
     tp.fog_enabled = ctx->scene.fog_enabled;
     tp.fog_density = (float)ctx->scene.fog_density;
     tp.fog_r = (float)ctx->scene.fog_color[0]; tp.fog_g = (float)ctx->scene.fog_color[1]; tp.fog_b = (float)ctx->scene.fog_color[2];
@@ -427,16 +432,18 @@ int collect_stats(gort_ctx* ctx, const gort_render_params* p, gort_stats* s, dou
         s->shaded_hits = tot[kStatShaded]; s->rng_blocks = tot[kStatRngBlocks]; s->light_evals = tot[kStatLightEvals];
         s->soft_shadow_rays = tot[kStatSoftRays]; s->diffuse_evals = tot[kStatDiffuse]; s->specular_evals = tot[kStatSpec];
         s->paths_depth_ge5 = tot[kStatDepth5]; s->paths_depth_ge20 = tot[kStatDepth20]; s->paths_depth_max = tot[kStatDepthMax];
+        s->cone_tests = tot[kStatConeTests];
         // SURVEY §8d operation costs (FMA = 2 flops): ray generation 12, AABB slab 24 (two per node),
         // sphere 23 miss / 47 hit, triangle 20/30/46/52 staged rejects / 92 accept, 30 per (hit, light)
         // set-up, 36 per soft-shadow direction, 50 per diffuse term, 45 per specular term, ~70 per
-        // scatter, 20 per pixel of tone-map.
+        // scatter, 20 per pixel of tone-map; 30 per cone test of the soft-shadow candidate pass (this
+        // implementation's own pruning work, like the BVH slabs).
         s->algorithmic_flops = 12.0 * (double)s->primary_rays + 48.0 * (double)s->nodes_visited +
                                23.0 * (double)(s->sphere_tests - s->sphere_hits) + 47.0 * (double)s->sphere_hits +
                                20.0 * (double)s->tri_rejects[0] + 30.0 * (double)s->tri_rejects[1] + 46.0 * (double)s->tri_rejects[2] +
                                52.0 * (double)s->tri_rejects[3] + 92.0 * (double)s->tri_hits + 30.0 * (double)s->light_evals +
                                36.0 * (double)s->soft_shadow_rays + 50.0 * (double)s->diffuse_evals + 45.0 * (double)s->specular_evals +
-                               70.0 * (double)s->shaded_hits + 20.0 * (double)pixels;
+                               70.0 * (double)s->shaded_hits + 20.0 * (double)pixels + 30.0 * (double)s->cone_tests;
     }
     s->total_ms = now_ms() - t_start_ms;
     return GORT_OK;

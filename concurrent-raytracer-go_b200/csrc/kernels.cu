@@ -3,18 +3,13 @@
 // wavefront executed by persistent warps.
 //
 //   trace_kernel   : persistent warps pull (tile, 8x4 pixel block, sample batch) work units from an
-//                    atomic counter.  Each warp keeps a queue of live paths in shared memory:
-//                      FILL    32 primary rays per step (getRay + hitWorld), hits are compacted
-//                              into the queue (misses contribute black and cost nothing more);
-//                      SHADE   32 queued hits: calculateDirectLighting with the hard shadow ray per
-//                              (path, light) on one lane each, then the 16 soft-shadow rays of each
-//                              lit (path, light) pair spread over a HALF WARP (two pairs per step,
-//                              occlusion counted with one ballot), then Material.Scatter;
-//                      EXTEND  the scattered rays' hitWorld; survivors go back to the queue.
-//                    The recursion of traceRay is unrolled into throughput/radiance registers
-//                    (the result is affine in the reflected colour — SURVEY §3.2).  Finished paths
-//                    add their radiance to per-pixel int64 fixed-point accumulators (order
-//                    independent => the image is bit-reproducible for any schedule / GPU count).
+//                    atomic counter and run three decoupled stages over two per-warp queues in shared
+//                    memory (see the comment above the kernel): FILL (primary rays), EXTEND (Scatter +
+//                    scattered ray; the recursion of traceRay as a throughput chain) and SHADE
+//                    (calculateDirectLighting: hard shadow rays, cone-culled soft-shadow rays, shading
+//                    arithmetic).  Every shaded hit adds T * (emitted + w * direct) to per-pixel int64
+//                    fixed-point accumulators (order independent => the image is bit-reproducible for
+//                    any schedule / GPU count).
 //   resolve_kernel : toneMap + ToRGB + img.Set (renderer.go:92-97,348-367) in float64 from the exact
 //                    accumulator, packed as RGBA8 (row-major frame or tile-major shard slab).
 //
@@ -329,73 +324,189 @@ __device__ __forceinline__ bool query(const TraceParams& P, float ox, float oy, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// per-warp state in shared memory: the path queue (structure of arrays, one column per queued path)
-// and the scratch of the round being shaded
+// Soft-shadow candidate culling.
+//
+// calculateSmartShadow casts 16 rays normalize(L + 0.1 * ball) from one hit point toward one light
+// (renderer.go:311-328).  |ball| < 1, so every one of them lies inside the cone of half angle
+// asin(0.1) about L, and only t in [0.001, lightDistance] counts.  A primitive that no ray of that
+// cone can reach within that range cannot occlude any of the 16: it is dropped ONCE per (hit, light)
+// pair and the 16 rays test only the survivors (most pairs keep 0-2 primitives).  The answer of every
+// ray is unchanged; only tests that must fail are skipped.
+// ---------------------------------------------------------------------------------------------
+constexpr float kConeSin = 0.1f;
+constexpr float kConeCos = 0.99498743710662f;  // sqrt(1 - 0.1^2)
+
+// v = centre - apex, r >= 0, a = unit axis.  Conservative: false only if no cone ray can hit.
+__device__ __forceinline__ bool cone_sphere_candidate(float vx, float vy, float vz, float r, float ax, float ay, float az, float tmax) {
+    const float dv2 = dot3(vx, vy, vz, vx, vy, vz);
+    const float inv_dv = rsqrt_fast(fmaxf(dv2, 1e-30f));
+    const float dv = dv2 * inv_dv;
+    const float ca = dot3(ax, ay, az, vx, vy, vz) * inv_dv;  // cos(angle between the axis and the centre)
+    // exterior apex: the sphere subtends asin(r/dv); it meets the cone iff angle <= asin(0.1) + asin(r/dv)
+    const float sp = fminf(1.0f, r * inv_dv);
+    const float cp = sqrt_fast(fmaxf(0.f, fmaf(-sp, sp, 1.0f)));
+    const bool ext = ca >= fmaf(kConeCos, cp, -kConeSin * sp) - 1e-4f;
+    // apex on the surface up to rounding (the hit point's own sphere): a ray leaving the surface outward
+    // at cos >= delta can only "hit" at t <= shell/delta < tMin = 0.001, which Sphere.Hit rejects (sphere.go:35).
+    // -ca = axis . outward normal; the least outward cone ray has cos >= -ca - 0.105.
+    const float shell = 2e-5f + 1e-6f * (r + dv);
+    const bool sur = !(-ca - 0.105f > fmaxf(0.03f, 1000.0f * shell));
+    bool cand = (dv < r - shell) ? true : ((dv <= r + shell) ? sur : ext);
+    // entirely beyond the light
+    if (dv - r > fmaf(tmax, 1.00001f, 1e-5f)) cand = false;
+    return cand;
+}
+
+// Sphere.Hit (sphere.go:22-59) as a boolean for a UNIT direction: some root in [tmin, tmax]
+__device__ __forceinline__ bool sphere_occludes_unit(const float4 s, float ox, float oy, float oz, float dx, float dy, float dz, float tmin,
+                                                     float tmax) {
+    const float ocx = ox - s.x, ocy = oy - s.y, ocz = oz - s.z;
+    const float hb = dot3(ocx, ocy, ocz, dx, dy, dz);
+    const float lx = fmaf(-hb, dx, ocx), ly = fmaf(-hb, dy, ocy), lz = fmaf(-hb, dz, ocz);
+    const float dn = fmaf(s.w, s.w, -dot3(lx, ly, lz, lx, ly, lz));
+    if (dn < 0.f) return false;
+    const float sq = sqrt_fast(dn);
+    const float r0 = -hb - sq, r1 = -hb + sq;
+    return !(r0 < tmin || tmax < r0) || !(r1 < tmin || tmax < r1);
+}
+
+// Triangle.Hit (triangle.go:36-88) as a boolean
+__device__ __forceinline__ bool tri_occludes(const float4* __restrict__ tp, float ox, float oy, float oz, float dx, float dy, float dz,
+                                             float tmin, float tmax) {
+    const float4 v0 = ldg4(tp), e1 = ldg4(tp + 1), e2 = ldg4(tp + 2);
+    const float hx = dy * e2.z - dz * e2.y, hy = dz * e2.x - dx * e2.z, hz = dx * e2.y - dy * e2.x;
+    const float aa = dot3(e1.x, e1.y, e1.z, hx, hy, hz);
+    if (aa > -1e-6f && aa < 1e-6f) return false;
+    const float f = rcp_fast(aa);
+    const float sx = ox - v0.x, sy = oy - v0.y, sz = oz - v0.z;
+    const float u = f * dot3(sx, sy, sz, hx, hy, hz);
+    if (u < 0.0f || u > 1.0f) return false;
+    const float qx = sy * e1.z - sz * e1.y, qy = sz * e1.x - sx * e1.z, qz = sx * e1.y - sy * e1.x;
+    const float vv = f * dot3(dx, dy, dz, qx, qy, qz);
+    if (vv < 0.0f || u + vv > 1.0f) return false;
+    const float t = f * dot3(e2.x, e2.y, e2.z, qx, qy, qz);
+    return !(t < tmin || t > tmax);
+}
+
+constexpr int kMaxCand = 8;           // candidate primitives kept per (hit, light) pair on BVH scenes
+constexpr uint32_t kCandOverflow = 0xFFu;  // more than kMaxCand: the pair's rays walk the BVH themselves
+
+// Walk the BVH with the cone (apex o, unit axis a, range tmax); boxes are tested through their bounding
+// spheres.  Writes up to kMaxCand primitive references (sphere: index; triangle: index | 0x80000000) and
+// returns their number, or kCandOverflow.
+template <bool STATS>
+__device__ __forceinline__ uint32_t cone_candidates(const SceneView& S, float ox, float oy, float oz, float ax, float ay, float az, float tmax,
+                                                    uint32_t* __restrict__ out, Stats& st) {
+    if (S.n_nodes == 0) return 0;
+    int stack[64];
+    int sp = 0;
+    int node = 0;
+    uint32_t n = 0;
+    for (;;) {
+        if (node >= 0) {
+            stat_add<STATS>(st, kStatConeTests, 2);
+            const float4* np = S.nodes + 4 * (size_t)node;
+            const float4 n0 = ldg4(np), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3);
+            bool h[2];
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const float lox = c ? n1.x : n0.x, hix = c ? n1.y : n0.y, loy = c ? n1.z : n0.z, hiy = c ? n1.w : n0.w;
+                const float loz = c ? n2.z : n2.x, hiz = c ? n2.w : n2.y;
+                const float ex = 0.5f * (hix - lox), ey = 0.5f * (hiy - loy), ez = 0.5f * (hiz - loz);
+                const float vx = fmaf(0.5f, hix + lox, -ox), vy = fmaf(0.5f, hiy + loy, -oy), vz = fmaf(0.5f, hiz + loz, -oz);
+                const float rb2 = dot3(ex, ey, ez, ex, ey, ez);
+                const float rb = rb2 * rsqrt_fast(fmaxf(rb2, 1e-30f)) * 1.00001f + 1e-6f;
+                const float dv2 = dot3(vx, vy, vz, vx, vy, vz);
+                const float inv_dv = rsqrt_fast(fmaxf(dv2, 1e-30f));
+                const float dv = dv2 * inv_dv;
+                const float ca = dot3(ax, ay, az, vx, vy, vz) * inv_dv;
+                const float sphi = fminf(1.0f, rb * inv_dv);
+                const float cphi = sqrt_fast(fmaxf(0.f, fmaf(-sphi, sphi, 1.0f)));
+                bool hit = (dv <= rb) || (ca >= fmaf(kConeCos, cphi, -kConeSin * sphi) - 1e-4f);
+                if (dv - rb > fmaf(tmax, 1.00001f, 1e-5f)) hit = false;
+                if (!(ex >= 0.f)) hit = false;  // inverted box = empty child
+                h[c] = hit;
+            }
+            const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+            if (h[0] && h[1]) {
+                stack[sp++] = c1;
+                node = c0;
+            } else if (h[0]) {
+                node = c0;
+            } else if (h[1]) {
+                node = c1;
+            } else {
+                if (sp == 0) break;
+                node = stack[--sp];
+            }
+        } else {
+            const uint32_t v = ~(uint32_t)node;
+            const uint32_t start = v & 0x3FFFFFFu;
+            const int cnt = (int)((v >> 26) & 15u) + 1;
+            const bool is_tri = ((v >> 30) & 1u) != 0;
+            for (int i = 0; i < cnt; i++) {
+                bool keep = true;
+                stat_add<STATS>(st, kStatConeTests);
+                if (!is_tri) {
+                    const float4 s = ldg4(S.spheres + start + i);
+                    keep = cone_sphere_candidate(s.x - ox, s.y - oy, s.z - oz, fabsf(s.w), ax, ay, az, tmax);
+                } else {
+                    // the triangle's plane: a cone whose every ray moves away from it (or crosses it below
+                    // tMin when the apex lies on it — the hit point's own face) cannot hit the triangle
+                    const float4* tp = S.tris + 4 * (size_t)(start + i);
+                    const float4 v0 = ldg4(tp), nn = ldg4(tp + 3);
+                    const float hgt = dot3(nn.x, nn.y, nn.z, ox - v0.x, oy - v0.y, oz - v0.z);
+                    const float x = dot3(nn.x, nn.y, nn.z, ax, ay, az);  // n . d ranges over [x - 0.105, x + 0.105]
+                    const float eps = 2e-5f + 1e-6f * (fabsf(ox) + fabsf(oy) + fabsf(oz) + fabsf(v0.x) + fabsf(v0.y) + fabsf(v0.z));
+                    if (hgt > eps) keep = !(x - 0.105f >= 0.f);
+                    else if (hgt < -eps) keep = !(x + 0.105f <= 0.f);
+                    else keep = !(fabsf(x) - 0.105f > fmaxf(0.03f, 1000.0f * eps));
+                }
+                if (keep) {
+                    if (n >= (uint32_t)kMaxCand) return kCandOverflow;
+                    out[n++] = (start + i) | (is_tri ? 0x80000000u : 0u);
+                }
+            }
+            if (sp == 0) break;
+            node = stack[--sp];
+        }
+    }
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-warp state in shared memory: two queues (structure of arrays, one column per entry)
+//   PQ  paths that hit something and wait for Material.Scatter + the scattered ray   (EXTEND)
+//   SQ  hit records that wait for calculateDirectLighting                             (SHADE)
+// and the scratch of the shade round.
 // ---------------------------------------------------------------------------------------------
 constexpr int kWarpsPerCta = 4;
-constexpr int kQueueCap = 64;   // occupancy never exceeds 63: FILL stops at >= 32, a round pops <= 32 and returns <= 32
-constexpr int kLightChunk = 8;  // lights handled per pass of a round
-enum QField {
-    QF_OX, QF_OY, QF_OZ, QF_DX, QF_DY, QF_DZ, QF_T, QF_PRIM,
-    QF_TR, QF_TG, QF_TB, QF_LR, QF_LG, QF_LB,
-    QF_PIXG, QF_PIXL, QF_SAMPLE, QF_DEPTH, QF_FOG, QF_COUNT
-};
+constexpr int kQueueCap = 64;   // neither queue exceeds 63: an action that pushes <= 32 only runs below 32
+constexpr int kLightChunk = 8;  // lights handled per pass of a shade round
+enum PField { PF_PX, PF_PY, PF_PZ, PF_DX, PF_DY, PF_DZ, PF_PRIM, PF_TR, PF_TG, PF_TB, PF_PIXG, PF_PIXL, PF_SD, PF_FOG, PF_COUNT };
+enum SField { SF_PX, SF_PY, SF_PZ, SF_NX, SF_NY, SF_NZ, SF_TR, SF_TG, SF_TB, SF_MAT, SF_PIXG, SF_PIXL, SF_SD, SF_FOG, SF_COUNT };
+// *_SD = sample | depth << 16;  *_FOG = fog factor of the path's primary hit (extension)
 
+template <bool SMALL>
 struct WarpShared {
-    uint32_t q[QF_COUNT][kQueueCap];
-    // round scratch, one column per path of the round
-    float n[3][32];        // shading normal (faces the incoming ray)
-    float att[3][32];      // Scatter attenuation x reflection weight
-    float direct[3][32];   // calculateDirectLighting running total
-    float t2[32];          // closest hit of the scattered ray
-    int prim2[32];
-    uint32_t flags[32];    // bit0 scattered, bit1 continues, bit2 scattered ray hit; bits 8.. material index
-    uint8_t lit[kLightChunk][32];  // hard shadow ray unoccluded
-    uint8_t cnt[kLightChunk][32];  // unoccluded soft shadow rays (of 16)
-    uint16_t pairs[kLightChunk * 32];  // lit (light, path) pairs of the chunk: (light << 8) | path
+    uint32_t pq[PF_COUNT][kQueueCap];
+    uint32_t sq[SF_COUNT][kQueueCap];
+    uint8_t lit[kLightChunk][32];        // hard shadow ray unoccluded
+    uint8_t cnt[kLightChunk][32];        // unoccluded soft shadow rays (of 16)
+    uint16_t pairs[kLightChunk * 32];    // lit (light, item) pairs of the chunk: (light << 8) | item
+    uint16_t cmask[SMALL ? kLightChunk : 1][32];  // tiny scenes: spheres the pair's shadow cone can reach
+    uint8_t ncand[SMALL ? 4 : 32];                // BVH scenes: candidates of the 32 pairs in flight (or kCandOverflow)
+    uint32_t cand[SMALL ? 1 : 32][kMaxCand];
 };
 
-struct PathState {
-    float ox, oy, oz, dx, dy, dz, t;
-    int prim;
-    float tr, tg, tb, lr, lg, lb;
-    uint32_t pixg, pixl, sample, depth;
-    float fog;
-};
+__device__ __forceinline__ float qf(const uint32_t (*Q)[kQueueCap], int f, int slot) { return __uint_as_float(Q[f][slot]); }
 
-__device__ __forceinline__ void queue_store(uint32_t (*Q)[kQueueCap], int slot, const PathState& s) {
-    Q[QF_OX][slot] = __float_as_uint(s.ox); Q[QF_OY][slot] = __float_as_uint(s.oy); Q[QF_OZ][slot] = __float_as_uint(s.oz);
-    Q[QF_DX][slot] = __float_as_uint(s.dx); Q[QF_DY][slot] = __float_as_uint(s.dy); Q[QF_DZ][slot] = __float_as_uint(s.dz);
-    Q[QF_T][slot] = __float_as_uint(s.t); Q[QF_PRIM][slot] = (uint32_t)s.prim;
-    Q[QF_TR][slot] = __float_as_uint(s.tr); Q[QF_TG][slot] = __float_as_uint(s.tg); Q[QF_TB][slot] = __float_as_uint(s.tb);
-    Q[QF_LR][slot] = __float_as_uint(s.lr); Q[QF_LG][slot] = __float_as_uint(s.lg); Q[QF_LB][slot] = __float_as_uint(s.lb);
-    Q[QF_PIXG][slot] = s.pixg; Q[QF_PIXL][slot] = s.pixl; Q[QF_SAMPLE][slot] = s.sample; Q[QF_DEPTH][slot] = s.depth;
-    Q[QF_FOG][slot] = __float_as_uint(s.fog);
-}
-
-__device__ __forceinline__ void queue_load(uint32_t (*Q)[kQueueCap], int slot, PathState& s) {
-    s.ox = __uint_as_float(Q[QF_OX][slot]); s.oy = __uint_as_float(Q[QF_OY][slot]); s.oz = __uint_as_float(Q[QF_OZ][slot]);
-    s.dx = __uint_as_float(Q[QF_DX][slot]); s.dy = __uint_as_float(Q[QF_DY][slot]); s.dz = __uint_as_float(Q[QF_DZ][slot]);
-    s.t = __uint_as_float(Q[QF_T][slot]); s.prim = (int)Q[QF_PRIM][slot];
-    s.tr = __uint_as_float(Q[QF_TR][slot]); s.tg = __uint_as_float(Q[QF_TG][slot]); s.tb = __uint_as_float(Q[QF_TB][slot]);
-    s.lr = __uint_as_float(Q[QF_LR][slot]); s.lg = __uint_as_float(Q[QF_LG][slot]); s.lb = __uint_as_float(Q[QF_LB][slot]);
-    s.pixg = Q[QF_PIXG][slot]; s.pixl = Q[QF_PIXL][slot]; s.sample = Q[QF_SAMPLE][slot]; s.depth = Q[QF_DEPTH][slot];
-    s.fog = __uint_as_float(Q[QF_FOG][slot]);
-}
-
-__device__ __forceinline__ float qf(uint32_t (*Q)[kQueueCap], int f, int slot) { return __uint_as_float(Q[f][slot]); }
-
-// Path finished: add its radiance to the pixel's fixed-point accumulators (tracePixel's
-// color.Add, renderer.go:159).  Integer adds commute, so the sum is schedule independent.
-__device__ __forceinline__ void flush_radiance(const TraceParams& P, uint32_t pixl, float fog, float r, float g, float b) {
-    if (P.fog_enabled) {  // extension: exponential fog on the primary-hit distance
-        r = fmaf(r, 1.0f - fog, P.fog_r * fog);
-        g = fmaf(g, 1.0f - fog, P.fog_g * fog);
-        b = fmaf(b, 1.0f - fog, P.fog_b * fog);
-    }
+// tracePixel's color.Add (renderer.go:159) into the pixel's fixed-point accumulators.  Integer adds
+// commute, so the sum is independent of the schedule.  NaN contributions are dropped (a NaN sample
+// makes the reference's pixel NaN -> undefined uint8).
+__device__ __forceinline__ void add_radiance(const TraceParams& P, uint32_t pixl, float r, float g, float b) {
     unsigned long long* acc = P.accum + 3 * (size_t)pixl;
     const float scale = (float)(1u << kAccumFracBits);
-    // NaN contributions are dropped (a NaN sample makes the reference's pixel NaN -> undefined uint8)
     if (r != 0.f && r == r) atomicAdd(acc + 0, (unsigned long long)__float2ll_rn(fminf(fmaxf(r, -kSampleClamp), kSampleClamp) * scale));
     if (g != 0.f && g == g) atomicAdd(acc + 1, (unsigned long long)__float2ll_rn(fminf(fmaxf(g, -kSampleClamp), kSampleClamp) * scale));
     if (b != 0.f && b == b) atomicAdd(acc + 2, (unsigned long long)__float2ll_rn(fminf(fmaxf(b, -kSampleClamp), kSampleClamp) * scale));
@@ -406,19 +517,38 @@ __device__ __forceinline__ float pow5(float x) {  // math.Pow(x, 5): sign-preser
     return x2 * x2 * x;
 }
 
+// Two uniform-ball points from ONE Philox block (the 16 soft-shadow samples of a (hit, light) pair take
+// 8 blocks): sample A from (x,y), sample B from (z,w); u1 = 21 bits, u2 = 21 bits, u3 = 22 bits
+// (oracle.cpp Rng::in_unit_sphere_half).
+__device__ __forceinline__ void ball_from_bits(uint32_t a, uint32_t b, float& bx, float& by, float& bz) {
+    const float u1 = (float)(a >> 11) * (1.0f / 2097152.0f), u2 = (float)(b >> 11) * (1.0f / 2097152.0f);
+    const float u3 = (float)(((a & 0x7FFu) << 11) | (b & 0x7FFu)) * (1.0f / 4194304.0f);
+    const float z = fmaf(-2.0f, u1, 1.0f);
+    const float sxy = sqrt_fast(fmaxf(0.f, fmaf(-z, z, 1.0f)));
+    float sn, cs;
+    __sincosf(6.2831853071795864769f * u2, &sn, &cs);
+    const float rad = ex2_fast(lg2_fast(u3) * (1.0f / 3.0f));  // cbrt; u3 = 0 -> 0
+    const float rs = rad * sxy;
+    bx = rs * cs;
+    by = rs * sn;
+    bz = rad * z;
+}
+
 // ---------------------------------------------------------------------------------------------
 // the trace kernel
 //
-// One round of a warp shades up to 32 queued hits.  The recursion of traceRay (renderer.go:165-227)
-// is turned inside out so that the rays of a bounce do not wait for one another:
-//   A  per path: hit record + Material.Scatter (direction and attenuation do not depend on the
-//      lighting), results parked in shared memory;
-//   B  ONE packed batch of rays: the hard shadow ray of every (path, light) and the scattered ray of
-//      every continuing path, 32 per step whatever the number of paths;
-//   C  the 16 soft-shadow rays of every lit (path, light) pair, two pairs per step;
-//   D  per path: calculateDirectLighting's arithmetic, traceRay's weighting, flush or re-queue.
-// A bounce is two dependent ray phases (B, C) instead of 2*lights+1, which bounds the latency of a
-// 50-bounce glass path, and the ray phases hold no shading state in registers.
+// traceRay (renderer.go:165-227) returns  emitted + w_d*direct + w_r*atten*traceRay(scattered): affine in
+// the recursive term.  Unrolled, a sample's radiance is  sum_k T_k * (emitted_k + w_k*direct_k)  with the
+// throughput T_k = prod_{i<k} w_r,i*atten_i, and T_k depends only on the chain of Scatter calls — not on
+// any lighting.  So each warp runs two decoupled stages over its queues:
+//   FILL    32 primary rays (tracePixel/getRay + hitWorld); hits enter PQ, misses are black and done;
+//   EXTEND  <= 32 paths of PQ: hit record + Material.Scatter + the scattered ray's hitWorld.  Every path
+//           leaves one hit record (point, normal, material, T_k) in SQ; survivors return to PQ.  A
+//           50-bounce glass path is a chain of these short rounds and never waits for a shadow ray;
+//   SHADE   32 records of SQ: one packed batch of hard shadow rays for every (record, light), then the 16
+//           soft-shadow rays of every lit pair (a quarter warp per pair, two rays per lane, candidates
+//           pre-culled with the pair's cone), then calculateDirectLighting's arithmetic and ONE
+//           fixed-point add of T_k * (...) to the pixel.
 // ---------------------------------------------------------------------------------------------
 #ifndef GORT_MIN_CTAS
 #define GORT_MIN_CTAS 6
@@ -426,10 +556,11 @@ __device__ __forceinline__ float pow5(float x) {  // math.Pow(x, 5): sign-preser
 
 template <bool STATS, bool SMALL>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel(const __grid_constant__ TraceParams P) {
-    __shared__ WarpShared wsh[kWarpsPerCta];
+    __shared__ WarpShared<SMALL> wsh[kWarpsPerCta];
     const int lane = threadIdx.x & 31;
-    WarpShared& W = wsh[threadIdx.x >> 5];
-    uint32_t(*Q)[kQueueCap] = W.q;
+    WarpShared<SMALL>& W = wsh[threadIdx.x >> 5];
+    uint32_t(*PQ)[kQueueCap] = W.pq;
+    uint32_t(*SQ)[kQueueCap] = W.sq;
     const SceneView& S = P.scene;
     Stats st;
     if (STATS) {
@@ -457,8 +588,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
         atomicMin(P.debug_times, t);
     }
 
-    int qcount = 0;          // warp-uniform
+    int pqn = 0, sqn = 0;    // warp-uniform queue sizes
     bool more_units = true;  // warp-uniform
+    bool urgent = false;     // warp-uniform: PQ's top holds a path at depth >= urgent_depth
     int s_cur = 0, s_end = 0;
     // this lane's pixel in the current work unit: (y << 16) | x, local accumulator index
     uint32_t pix_xy = 0, pixl = 0;
@@ -467,17 +599,25 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
     const unsigned lt_mask = (1u << lane) - 1u;
 
     for (;;) {
-        // ================= FILL: primary rays (tracePixel renderer.go:150-163, getRay :377-390) =========
-        while (qcount < 32) {
+        const bool can_fill = (s_cur < s_end) || more_units;
+        int action;  // 0 FILL, 1 EXTEND, 2 SHADE
+        if (sqn >= 32) action = 2;
+        else if (pqn >= 32 || (pqn > 0 && urgent)) action = 1;
+        else if (can_fill) action = 0;
+        else if (pqn > 0) action = 1;
+        else if (sqn > 0) action = 2;
+        else break;
+
+        if (action == 0) {
+            // ================= FILL: primary rays (tracePixel renderer.go:150-163, getRay :377-390) =========
             if (s_cur >= s_end) {
-                if (!more_units) break;
                 uint32_t u = 0;
                 if (lane == 0) u = atomicAdd(P.work_counter, 1u);
                 u = __shfl_sync(FULL_MASK, u, 0);
                 if (u >= n_units) {
                     more_units = false;
                     if (P.debug_times) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_units_done));
-                    break;
+                    continue;
                 }
                 // unit = (sample batch, active 8x4 block), batch-major; all units of the blocks that can see
                 // glass (deep paths) come first, the other blocks follow
@@ -503,8 +643,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
                 s_end = min(s_cur + spu, P.samples);
                 jit_valid = false;
             }
-            PathState ps;
             bool hit = false;
+            float t = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
+            int prim = 0;
             const uint32_t x = pix_xy & 0xffffu, y = pix_xy >> 16;
             const uint32_t pixg = y * (uint32_t)P.width + x;
             if (lane_valid) {
@@ -526,213 +667,271 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
                     jv = (float)(jy >> 8) * (1.0f / 16777216.0f);
                 }
                 const float u = ((float)x + ju) * P.inv_w, v = ((float)y + jv) * P.inv_h;
-                ps.ox = P.cam.ox; ps.oy = P.cam.oy; ps.oz = P.cam.oz;
-                ps.dx = fmaf(v, P.cam.vx, fmaf(u, P.cam.hx, P.cam.llx));
-                ps.dy = fmaf(v, P.cam.vy, fmaf(u, P.cam.hy, P.cam.lly));
-                ps.dz = fmaf(v, P.cam.vz, fmaf(u, P.cam.hz, P.cam.llz));
+                dx = fmaf(v, P.cam.vx, fmaf(u, P.cam.hx, P.cam.llx));
+                dy = fmaf(v, P.cam.vy, fmaf(u, P.cam.hy, P.cam.lly));
+                dz = fmaf(v, P.cam.vz, fmaf(u, P.cam.hz, P.cam.llz));
                 // traceRay depth 0 (renderer.go:166-173); max_depth <= 0 returns black before any hit test
                 if (P.max_depth > 0)
-                    hit = query<STATS, SMALL>(P, ps.ox, ps.oy, ps.oz, ps.dx, ps.dy, ps.dz, 0.001f, FLT_MAX * 2.0f, false, ps.t, ps.prim, st);
+                    hit = query<STATS, SMALL>(P, P.cam.ox, P.cam.oy, P.cam.oz, dx, dy, dz, 0.001f, FLT_MAX * 2.0f, false, t, prim, st);
             }
             const unsigned hm = __ballot_sync(FULL_MASK, hit);
             if (hit) {
-                ps.tr = ps.tg = ps.tb = 1.0f;
-                ps.lr = ps.lg = ps.lb = 0.0f;
-                ps.pixg = pixg; ps.pixl = pixl; ps.sample = (uint32_t)s_cur; ps.depth = 0;
-                ps.fog = 0.f;
-                if (P.fog_enabled) {
-                    const float dist = ps.t * sqrt_fast(dot3(ps.dx, ps.dy, ps.dz, ps.dx, ps.dy, ps.dz));
-                    ps.fog = 1.0f - expf(-P.fog_density * dist);
+                const int slot = pqn + __popc(hm & lt_mask);
+                PQ[PF_PX][slot] = __float_as_uint(fmaf(t, dx, P.cam.ox));  // rec.Point = ray.At(t) (sphere.go:43, triangle.go:69)
+                PQ[PF_PY][slot] = __float_as_uint(fmaf(t, dy, P.cam.oy));
+                PQ[PF_PZ][slot] = __float_as_uint(fmaf(t, dz, P.cam.oz));
+                PQ[PF_DX][slot] = __float_as_uint(dx); PQ[PF_DY][slot] = __float_as_uint(dy); PQ[PF_DZ][slot] = __float_as_uint(dz);
+                PQ[PF_PRIM][slot] = (uint32_t)prim;
+                PQ[PF_TR][slot] = PQ[PF_TG][slot] = PQ[PF_TB][slot] = __float_as_uint(1.0f);
+                PQ[PF_PIXG][slot] = pixg; PQ[PF_PIXL][slot] = pixl; PQ[PF_SD][slot] = (uint32_t)s_cur;
+                float fog = 0.f;
+                if (P.fog_enabled) {  // extension: exponential fog on the primary-hit distance
+                    const float dist = t * sqrt_fast(dot3(dx, dy, dz, dx, dy, dz));
+                    fog = 1.0f - expf(-P.fog_density * dist);
                 }
-                queue_store(Q, qcount + __popc(hm & lt_mask), ps);
+                PQ[PF_FOG][slot] = __float_as_uint(fog);
             }
-            qcount += __popc(hm);
+            pqn += __popc(hm);
             s_cur++;
+            __syncwarp();
+            continue;
         }
-        if (qcount == 0) break;
-        __syncwarp();
 
-        // ================= one round: the top n <= 32 queued hits =========================================
-        const int n = min(32, qcount);
-        const int base = qcount - n;
-        qcount = base;
-        if (P.debug_times && !more_units) {
-            dbg_rounds++;
-            dbg_paths += n;
+        if (action == 1) {
+            // ================= EXTEND: hit record + Material.Scatter + scattered ray (lane = path) ============
+            const int n = min(32, pqn);
+            const int base = pqn - n;
+            const bool act = lane < n;
+            const int slot = base + (act ? lane : 0);
+            if (P.debug_times && !more_units) {
+                dbg_rounds++;
+                dbg_paths += n;
+            }
+            bool survive = false;
+            float px = 0.f, py = 0.f, pz = 0.f, sx = 0.f, sy = 0.f, sz = 0.f, tr = 0.f, tg = 0.f, tb = 0.f, fog = 0.f;
+            uint32_t pixg = 0, pixl2 = 0, sd = 0;
+            int prim2 = 0;
+            if (act) {
+                stat_add<STATS>(st, kStatShaded);
+                px = qf(PQ, PF_PX, slot); py = qf(PQ, PF_PY, slot); pz = qf(PQ, PF_PZ, slot);
+                const float dx = qf(PQ, PF_DX, slot), dy = qf(PQ, PF_DY, slot), dz = qf(PQ, PF_DZ, slot);
+                const int prim = (int)PQ[PF_PRIM][slot];
+                tr = qf(PQ, PF_TR, slot); tg = qf(PQ, PF_TG, slot); tb = qf(PQ, PF_TB, slot);
+                pixg = PQ[PF_PIXG][slot]; pixl2 = PQ[PF_PIXL][slot]; sd = PQ[PF_SD][slot];
+                fog = qf(PQ, PF_FOG, slot);
+                // hit record (sphere.go:42-50, triangle.go:69-73)
+                float nx, ny, nz;
+                int mat;
+                if (SMALL) {
+                    const float4 s = P.small_sph[prim];
+                    const float inv_r = rcp_fast(s.w);
+                    nx = (px - s.x) * inv_r; ny = (py - s.y) * inv_r; nz = (pz - s.z) * inv_r;
+                    mat = P.small_mat[prim];
+                } else if (prim >= 0) {
+                    const float4 s = ldg4(S.spheres + prim);
+                    const float inv_r = rcp_fast(s.w);
+                    nx = (px - s.x) * inv_r; ny = (py - s.y) * inv_r; nz = (pz - s.z) * inv_r;
+                    mat = __ldg(&S.sphere_meta[prim]).x;
+                } else {
+                    const float4* tp = S.tris + 4 * (size_t)(prim & 0x7fffffff);
+                    mat = __float_as_int(ldg4(tp).w);
+                    const float4 nn = ldg4(tp + 3);
+                    nx = nn.x; ny = nn.y; nz = nn.z;
+                }
+                const float ddn0 = dot3(dx, dy, dz, nx, ny, nz);
+                const bool front = ddn0 < 0.f;
+                if (!front) { nx = -nx; ny = -ny; nz = -nz; }
+                const float ddn = front ? ddn0 : -ddn0;  // ray.Direction . normal (<= 0)
+
+                // the hit record goes to the shade queue with the throughput it is seen through
+                {
+                    const int ss = sqn + lane;
+                    SQ[SF_PX][ss] = __float_as_uint(px); SQ[SF_PY][ss] = __float_as_uint(py); SQ[SF_PZ][ss] = __float_as_uint(pz);
+                    SQ[SF_NX][ss] = __float_as_uint(nx); SQ[SF_NY][ss] = __float_as_uint(ny); SQ[SF_NZ][ss] = __float_as_uint(nz);
+                    SQ[SF_TR][ss] = __float_as_uint(tr); SQ[SF_TG][ss] = __float_as_uint(tg); SQ[SF_TB][ss] = __float_as_uint(tb);
+                    SQ[SF_MAT][ss] = (uint32_t)mat; SQ[SF_PIXG][ss] = pixg; SQ[SF_PIXL][ss] = pixl2; SQ[SF_SD][ss] = sd;
+                    SQ[SF_FOG][ss] = __float_as_uint(fog);
+                }
+
+                const float4* mp = S.mats + 4 * (size_t)mat;
+                const float4 m0 = ldg4(mp), m1 = ldg4(mp + 1), m2 = ldg4(mp + 2), m3 = ldg4(mp + 3);
+                const int mtype = __float_as_int(m0.x);
+                const uint32_t depth = sd >> 16, sample = sd & 0xffffu;
+                const uint32_t bs = (depth << 8) | kStreamScatter;
+                bool scattered = true;
+                float ar = 0.f, ag = 0.f, ab = 0.f;
+                if (mtype == 0) {  // Lambertian (material.go:26-35)
+                    float bx, by, bz;
+                    rng_ball<STATS>(P, pixg, sample, bs, 0u, bx, by, bz, st);
+                    sx = nx + bx; sy = ny + by; sz = nz + bz;
+                    if (fabsf(sx) < 1e-8f && fabsf(sy) < 1e-8f && fabsf(sz) < 1e-8f) { sx = nx; sy = ny; sz = nz; }
+                    normalize3(sx, sy, sz);
+                    ar = m0.y; ag = m0.z; ab = m0.w;
+                } else if (mtype <= 3) {  // Metal / Shiny / PerfectMirror (material.go:75-113,169-189; advanced_materials.go:125-144)
+                    sx = fmaf(-2.0f * ddn, nx, dx); sy = fmaf(-2.0f * ddn, ny, dy); sz = fmaf(-2.0f * ddn, nz, dz);  // Reflect vector.go:77
+                    const bool rough = (mtype == 2) ? (m1.x > 0.f) : (m1.x > 0.001f);
+                    if (rough) {
+                        float bx, by, bz;
+                        rng_ball<STATS>(P, pixg, sample, bs, 0u, bx, by, bz, st);
+                        sx = fmaf(m1.x, bx, sx); sy = fmaf(m1.x, by, sy); sz = fmaf(m1.x, bz, sz);
+                        normalize3(sx, sy, sz);
+                    }
+                    const float cosT = fabsf(ddn);  // ray direction is NOT normalised here (material.go:85)
+                    const float fres = fmaf(1.0f - m3.y, pow5(1.0f - cosT), m3.y);
+                    const float fs = m3.z;
+                    ar = fmaf(m0.y, 1.0f - fs, fres * fs); ag = fmaf(m0.z, 1.0f - fs, fres * fs); ab = fmaf(m0.w, 1.0f - fs, fres * fs);
+                    if (mtype == 1) {
+                        ar = fmaxf(0.f, fminf(1.f, ar)); ag = fmaxf(0.f, fminf(1.f, ag)); ab = fmaxf(0.f, fminf(1.f, ab));
+                        if (m3.w >= 0.f) {  // metallic > 0.8 (material.go:102-109)
+                            const float mf = m3.w;
+                            ar = fmaf(ar, 1.0f - mf, fres * mf); ag = fmaf(ag, 1.0f - mf, fres * mf); ab = fmaf(ab, 1.0f - mf, fres * mf);
+                        }
+                    } else if (mtype == 2) {
+                        ar = fminf(1.f, ar); ag = fminf(1.f, ag); ab = fminf(1.f, ab);
+                    }
+                } else if (mtype <= 5) {  // Glass / Dielectric (advanced_materials.go:21-46; material.go:235-260)
+                    ar = m0.y; ag = m0.z; ab = m0.w;  // Glass colour; Dielectric packed as (1,1,1)
+                    const float ratio = front ? m3.z : m1.w;  // 1/ior precomputed in float64 on the host
+                    float ux = dx, uy = dy, uz = dz;
+                    normalize3(ux, uy, uz);
+                    const float udn = dot3(ux, uy, uz, nx, ny, nz);
+                    const float cosT = fminf(-udn, 1.0f);
+                    const float sinT = sqrt_fast(1.0f - cosT * cosT);
+                    bool reflect = ratio * sinT > 1.0f;  // cannotRefract
+                    if (!reflect) {
+                        const float r0 = m3.y;  // ((1-x)/(1+x))^2 is the same for x = ior and x = 1/ior
+                        const float refl = fmaf(1.0f - r0, pow5(1.0f - cosT), r0);  // reflectance material.go:282-286
+                        const uint4 r = philox(P.rk, pixg, sample, bs, 0u);
+                        stat_add<STATS>(st, kStatRngBlocks);
+                        reflect = refl > (float)(r.x >> 8) * (1.0f / 16777216.0f);
+                    }
+                    if (reflect) {
+                        sx = fmaf(-2.0f * udn, nx, ux); sy = fmaf(-2.0f * udn, ny, uy); sz = fmaf(-2.0f * udn, nz, uz);
+                    } else {
+                        // Vec3.Refract (vector.go:81-96) with v = unit direction, normal against the ray
+                        float cn = udn, eta = ratio, rnx = nx, rny = ny, rnz = nz;
+                        if (cn > 0.f) { rnx = -nx; rny = -ny; rnz = -nz; eta = rcp_fast(eta); cn = -cn; }
+                        const float sin2 = eta * eta * (1.0f - cn * cn);
+                        if (sin2 > 1.0f) {
+                            const float d2 = dot3(ux, uy, uz, rnx, rny, rnz);
+                            sx = fmaf(-2.0f * d2, rnx, ux); sy = fmaf(-2.0f * d2, rny, uy); sz = fmaf(-2.0f * d2, rnz, uz);
+                        } else {
+                            const float k = fmaf(eta, cn, sqrt_fast(1.0f - sin2));
+                            sx = fmaf(eta, ux, -k * rnx); sy = fmaf(eta, uy, -k * rny); sz = fmaf(eta, uz, -k * rnz);
+                        }
+                    }
+                } else {  // DiffuseLight (material.go:296-298): no scatter
+                    scattered = false;
+                }
+                // traceRay(scattered, depth+1) is black at once when depth+1 >= maxDepth or when
+                // recursiveReflections is off (renderer.go:166-168,186-189): no ray needed
+                bool cont = scattered && P.recursive && (int)(depth + 1) < P.max_depth;
+                const float wr = m2.z;
+                tr *= ar * wr; tg *= ag * wr; tb *= ab * wr;
+                // Exact dead-path test.  Everything the remaining bounces can add reaches the pixel as
+                // fixed-point adds of T * c with |c| <= dead_bound.  If T * dead_bound < 2^-31 in every
+                // channel, each add rounds to zero: tracing on cannot change the accumulator.  (Rays trapped
+                // inside a rough-metal sphere otherwise bounce to max_depth with throughput ~0.03^k.)
+                const float db = P.dead_bound;
+                if (db > 0.f && fabsf(tr) * db < 4.6566e-10f && fabsf(tg) * db < 4.6566e-10f && fabsf(tb) * db < 4.6566e-10f) cont = false;
+                if (cont) {
+                    float t2;
+                    survive = query<STATS, SMALL>(P, px, py, pz, sx, sy, sz, 0.001f, FLT_MAX * 2.0f, false, t2, prim2, st);
+                    if (survive) {
+                        px = fmaf(t2, sx, px); py = fmaf(t2, sy, py); pz = fmaf(t2, sz, pz);
+                        sd += 0x10000u;
+                    }
+                }
+                if (STATS && !survive) {
+                    const uint32_t dd = depth + (scattered ? 1u : 0u);
+                    if (dd >= 5) stat_add<STATS>(st, kStatDepth5);
+                    if (dd >= 20) stat_add<STATS>(st, kStatDepth20);
+                    if ((int)dd >= P.max_depth) stat_add<STATS>(st, kStatDepthMax);
+                }
+            }
+            __syncwarp();  // every lane has read its slot before the survivors are compacted over the popped region
+            const unsigned hm = __ballot_sync(FULL_MASK, survive);
+            if (survive) {
+                const int d = base + __popc(hm & lt_mask);
+                PQ[PF_PX][d] = __float_as_uint(px); PQ[PF_PY][d] = __float_as_uint(py); PQ[PF_PZ][d] = __float_as_uint(pz);
+                PQ[PF_DX][d] = __float_as_uint(sx); PQ[PF_DY][d] = __float_as_uint(sy); PQ[PF_DZ][d] = __float_as_uint(sz);
+                PQ[PF_PRIM][d] = (uint32_t)prim2;
+                PQ[PF_TR][d] = __float_as_uint(tr); PQ[PF_TG][d] = __float_as_uint(tg); PQ[PF_TB][d] = __float_as_uint(tb);
+                PQ[PF_PIXG][d] = pixg; PQ[PF_PIXL][d] = pixl2; PQ[PF_SD][d] = sd; PQ[PF_FOG][d] = __float_as_uint(fog);
+            }
+            pqn = base + __popc(hm);
+            sqn += n;
+            urgent = P.urgent_depth > 0 && __any_sync(FULL_MASK, survive && (int)(sd >> 16) >= P.urgent_depth);
+            __syncwarp();
+            continue;
         }
+
+        // ================= SHADE: calculateDirectLighting for the top n <= 32 records of SQ =================
+        const int n = min(32, sqn);
+        const int base = sqn - n;
+        sqn = base;
         const bool act = lane < n;
         const int slot = base + (act ? lane : 0);
         const float inv_n = 1.0f / (float)n;
-
-        // ---- A: hit record + Material.Scatter (lane = path) ----
+        // lane = record: material constants and the running total (starts at the ambient term, renderer.go:236-246)
+        float dr = 0.f, dg = 0.f, db = 0.f;
+        float kar = 0.f, kag = 0.f, kab = 0.f, spec_pow = 0.f, spec_w = 0.f;
         if (act) {
-            stat_add<STATS>(st, kStatShaded);
-            const float dx = qf(Q, QF_DX, slot), dy = qf(Q, QF_DY, slot), dz = qf(Q, QF_DZ, slot);
-            const float t = qf(Q, QF_T, slot);
-            const int prim = (int)Q[QF_PRIM][slot];
-            // hit record (sphere.go:42-50, triangle.go:69-73)
-            const float px = fmaf(t, dx, qf(Q, QF_OX, slot)), py = fmaf(t, dy, qf(Q, QF_OY, slot)), pz = fmaf(t, dz, qf(Q, QF_OZ, slot));
-            float nx, ny, nz;
-            int mat;
-            if (SMALL) {
-                const float4 s = P.small_sph[prim];
-                const float inv_r = rcp_fast(s.w);
-                nx = (px - s.x) * inv_r; ny = (py - s.y) * inv_r; nz = (pz - s.z) * inv_r;
-                mat = P.small_mat[prim];
-            } else if (prim >= 0) {
-                const float4 s = ldg4(S.spheres + prim);
-                const float inv_r = rcp_fast(s.w);
-                nx = (px - s.x) * inv_r; ny = (py - s.y) * inv_r; nz = (pz - s.z) * inv_r;
-                mat = __ldg(&S.sphere_meta[prim]).x;
-            } else {
-                const float4* tp = S.tris + 4 * (size_t)(prim & 0x7fffffff);
-                mat = __float_as_int(ldg4(tp).w);
-                const float4 nn = ldg4(tp + 3);
-                nx = nn.x; ny = nn.y; nz = nn.z;
-            }
-            const float ddn0 = dot3(dx, dy, dz, nx, ny, nz);
-            const bool front = ddn0 < 0.f;
-            if (!front) { nx = -nx; ny = -ny; nz = -nz; }
-            const float ddn = front ? ddn0 : -ddn0;  // ray.Direction . normal (<= 0)
-
-            const float4* mp = S.mats + 4 * (size_t)mat;
-            const float4 m0 = ldg4(mp), m1 = ldg4(mp + 1), m2 = ldg4(mp + 2), m3 = ldg4(mp + 3);
-            const int mtype = __float_as_int(m0.x);
-            const uint32_t depth = Q[QF_DEPTH][slot];
-            const uint32_t pixg = Q[QF_PIXG][slot], sample = Q[QF_SAMPLE][slot];
-            const uint32_t bs = (depth << 8) | kStreamScatter;
-            bool scattered = true;
-            float sx = 0.f, sy = 0.f, sz = 0.f, ar = 0.f, ag = 0.f, ab = 0.f;
-            if (mtype == 0) {  // Lambertian (material.go:26-35)
-                float bx, by, bz;
-                rng_ball<STATS>(P, pixg, sample, bs, 0u, bx, by, bz, st);
-                sx = nx + bx; sy = ny + by; sz = nz + bz;
-                if (fabsf(sx) < 1e-8f && fabsf(sy) < 1e-8f && fabsf(sz) < 1e-8f) { sx = nx; sy = ny; sz = nz; }
-                normalize3(sx, sy, sz);
-                ar = m0.y; ag = m0.z; ab = m0.w;
-            } else if (mtype <= 3) {  // Metal / Shiny / PerfectMirror (material.go:75-113,169-189; advanced_materials.go:125-144)
-                sx = fmaf(-2.0f * ddn, nx, dx); sy = fmaf(-2.0f * ddn, ny, dy); sz = fmaf(-2.0f * ddn, nz, dz);  // Reflect vector.go:77
-                const bool rough = (mtype == 2) ? (m1.x > 0.f) : (m1.x > 0.001f);
-                if (rough) {
-                    float bx, by, bz;
-                    rng_ball<STATS>(P, pixg, sample, bs, 0u, bx, by, bz, st);
-                    sx = fmaf(m1.x, bx, sx); sy = fmaf(m1.x, by, sy); sz = fmaf(m1.x, bz, sz);
-                    normalize3(sx, sy, sz);
-                }
-                const float cosT = fabsf(ddn);  // ray direction is NOT normalised here (material.go:85)
-                const float fres = fmaf(1.0f - m3.y, pow5(1.0f - cosT), m3.y);
-                const float fs = m3.z;
-                ar = fmaf(m0.y, 1.0f - fs, fres * fs); ag = fmaf(m0.z, 1.0f - fs, fres * fs); ab = fmaf(m0.w, 1.0f - fs, fres * fs);
-                if (mtype == 1) {
-                    ar = fmaxf(0.f, fminf(1.f, ar)); ag = fmaxf(0.f, fminf(1.f, ag)); ab = fmaxf(0.f, fminf(1.f, ab));
-                    if (m3.w >= 0.f) {  // metallic > 0.8 (material.go:102-109)
-                        const float mf = m3.w;
-                        ar = fmaf(ar, 1.0f - mf, fres * mf); ag = fmaf(ag, 1.0f - mf, fres * mf); ab = fmaf(ab, 1.0f - mf, fres * mf);
-                    }
-                } else if (mtype == 2) {
-                    ar = fminf(1.f, ar); ag = fminf(1.f, ag); ab = fminf(1.f, ab);
-                }
-            } else if (mtype <= 5) {  // Glass / Dielectric (advanced_materials.go:21-46; material.go:235-260)
-                ar = m0.y; ag = m0.z; ab = m0.w;  // Glass colour; Dielectric packed as (1,1,1)
-                const float ratio = front ? m3.z : m1.w;  // 1/ior precomputed in float64 on the host
-                float ux = dx, uy = dy, uz = dz;
-                normalize3(ux, uy, uz);
-                const float udn = dot3(ux, uy, uz, nx, ny, nz);
-                const float cosT = fminf(-udn, 1.0f);
-                const float sinT = sqrt_fast(1.0f - cosT * cosT);
-                bool reflect = ratio * sinT > 1.0f;  // cannotRefract
-                if (!reflect) {
-                    const float r0 = m3.y;  // ((1-x)/(1+x))^2 is the same for x = ior and x = 1/ior
-                    const float refl = fmaf(1.0f - r0, pow5(1.0f - cosT), r0);  // reflectance material.go:282-286
-                    const uint4 r = philox(P.rk, pixg, sample, bs, 0u);
-                    stat_add<STATS>(st, kStatRngBlocks);
-                    reflect = refl > (float)(r.x >> 8) * (1.0f / 16777216.0f);
-                }
-                if (reflect) {
-                    sx = fmaf(-2.0f * udn, nx, ux); sy = fmaf(-2.0f * udn, ny, uy); sz = fmaf(-2.0f * udn, nz, uz);
-                } else {
-                    // Vec3.Refract (vector.go:81-96) with v = unit direction, normal against the ray
-                    float cn = udn, eta = ratio, rnx = nx, rny = ny, rnz = nz;
-                    if (cn > 0.f) { rnx = -nx; rny = -ny; rnz = -nz; eta = rcp_fast(eta); cn = -cn; }
-                    const float sin2 = eta * eta * (1.0f - cn * cn);
-                    if (sin2 > 1.0f) {
-                        const float d2 = dot3(ux, uy, uz, rnx, rny, rnz);
-                        sx = fmaf(-2.0f * d2, rnx, ux); sy = fmaf(-2.0f * d2, rny, uy); sz = fmaf(-2.0f * d2, rnz, uz);
-                    } else {
-                        const float k = fmaf(eta, cn, sqrt_fast(1.0f - sin2));
-                        sx = fmaf(eta, ux, -k * rnx); sy = fmaf(eta, uy, -k * rny); sz = fmaf(eta, uz, -k * rnz);
-                    }
-                }
-            } else {  // DiffuseLight (material.go:296-298)
-                scattered = false;
-            }
-            // traceRay(scattered, depth+1) returns black at once when depth+1 >= maxDepth or when
-            // recursiveReflections is off (renderer.go:166-168,186-189): no ray needed
-            const bool cont = scattered && P.recursive && (int)(depth + 1) < P.max_depth;
-            const float wr = m2.z;
-            W.n[0][lane] = nx; W.n[1][lane] = ny; W.n[2][lane] = nz;
-            W.att[0][lane] = ar * wr; W.att[1][lane] = ag * wr; W.att[2][lane] = ab * wr;
-            W.direct[0][lane] = m2.x; W.direct[1][lane] = m2.x; W.direct[2][lane] = m2.x;  // ambient (renderer.go:236-246)
-            W.flags[lane] = (scattered ? 1u : 0u) | (cont ? 2u : 0u) | ((uint32_t)mat << 8);
-            // the slot now carries the NEXT segment: origin = hit point, direction = scattered direction
-            Q[QF_OX][slot] = __float_as_uint(px); Q[QF_OY][slot] = __float_as_uint(py); Q[QF_OZ][slot] = __float_as_uint(pz);
-            Q[QF_DX][slot] = __float_as_uint(sx); Q[QF_DY][slot] = __float_as_uint(sy); Q[QF_DZ][slot] = __float_as_uint(sz);
+            const float4* mp = S.mats + 4 * (size_t)SQ[SF_MAT][slot];
+            const float4 m0 = ldg4(mp), m2 = ldg4(mp + 2);
+            const bool is_light = __float_as_int(m0.x) == 6;
+            // GetAlbedo: DiffuseLight -> 0 (material.go:304); Dielectric -> 1 (packed by the host)
+            kar = is_light ? 0.f : m0.y * m2.y; kag = is_light ? 0.f : m0.z * m2.y; kab = is_light ? 0.f : m0.w * m2.y;
+            dr = dg = db = m2.x;
+            spec_pow = __ldg(&mp[3].x);       // 0: metallic <= 0.5, no specular term
+            spec_w = __ldg(&mp[1].y) * 3.0f;  // metallic * 3
         }
-        __syncwarp();
-
-        // ---- B + C per chunk of lights ----
         const int nl = S.n_lights;
-        bool ext_done = false;
-        for (int l0 = 0; l0 < nl || !ext_done; l0 += kLightChunk) {
-            const int lc = max(0, min(kLightChunk, nl - l0));
-            // B: rays [0, n*lc) are the hard shadow rays (light-major), rays [n*lc, n*lc+n) the scattered rays
-            const int n_hard = n * lc;
-            const int n_rays = n_hard + (ext_done ? 0 : n);
+        for (int l0 = 0; l0 < nl; l0 += kLightChunk) {
+            const int lc = min(kLightChunk, nl - l0);
+            // ---- B: the hard shadow ray of every (record, light), light-major, 32 per step ----
+            const int n_rays = n * lc;
             for (int r0 = 0; r0 < n_rays; r0 += 32) {
                 const int r = r0 + lane;
                 const bool valid = r < n_rays;
                 const int li = valid ? (int)(((float)r + 0.5f) * inv_n) : 0;
-                const int j = r - li * n;
-                const int sj = base + (valid ? j : 0);
-                const bool is_ext = li >= lc;
-                float ox = qf(Q, QF_OX, sj), oy = qf(Q, QF_OY, sj), oz = qf(Q, QF_OZ, sj);
-                float dx, dy, dz, tmax;
-                bool go = valid;
-                if (is_ext) {
-                    dx = qf(Q, QF_DX, sj); dy = qf(Q, QF_DY, sj); dz = qf(Q, QF_DZ, sj);
-                    tmax = FLT_MAX * 2.0f;
-                    go = go && (W.flags[valid ? j : 0] & 2u);
-                } else {
-                    const float4 L0 = ldg4(S.lights + 2 * (l0 + li));
-                    dx = L0.x - ox; dy = L0.y - oy; dz = L0.z - oz;
-                    const float dist2 = dot3(dx, dy, dz, dx, dy, dz);
-                    const float inv_d = dist2 > 0.f ? rsqrt_fast(dist2) : 0.f;
-                    tmax = dist2 * inv_d;  // lightDistance
-                    dx *= inv_d; dy *= inv_d; dz *= inv_d;
-                    go = go && !(tmax < 0.001f);  // renderer.go:252-254
-                    if (go) stat_add<STATS>(st, kStatLightEvals);
+                const int j = valid ? r - li * n : 0;
+                const int sj = base + j;
+                const float ox = qf(SQ, SF_PX, sj), oy = qf(SQ, SF_PY, sj), oz = qf(SQ, SF_PZ, sj);
+                const float4 L0 = ldg4(S.lights + 2 * (l0 + li));
+                float dx = L0.x - ox, dy = L0.y - oy, dz = L0.z - oz;
+                const float dist2 = dot3(dx, dy, dz, dx, dy, dz);
+                const float inv_d = dist2 > 0.f ? rsqrt_fast(dist2) : 0.f;
+                const float dist = dist2 * inv_d;  // lightDistance
+                dx *= inv_d; dy *= inv_d; dz *= inv_d;
+                const bool go = valid && !(dist < 0.001f);  // renderer.go:252-254
+                bool lit = false;
+                if (go) {
+                    stat_add<STATS>(st, kStatLightEvals);
+                    float tt;
+                    int pp;
+                    lit = !query<STATS, SMALL>(P, ox, oy, oz, dx, dy, dz, 0.001f, dist, true, tt, pp, st);
                 }
-                float tt = 0.f;
-                int pp = 0;
-                bool h = false;
-                if (go) h = query<STATS, SMALL>(P, ox, oy, oz, dx, dy, dz, 0.001f, tmax, !is_ext, tt, pp, st);
-                if (valid) {
-                    if (is_ext) {
-                        if (h) {
-                            W.t2[j] = tt;
-                            W.prim2[j] = pp;
-                            W.flags[j] |= 4u;
-                        }
+                if (valid) W.lit[li][j] = lit ? 1 : 0;
+                if (SMALL && lit && P.soft) {
+                    // which spheres can the pair's 16 jittered rays reach at all?
+                    uint32_t cm = 0;
+                    if (P.no_cone_cull) {
+                        cm = (1u << P.small_n) - 1u;
                     } else {
-                        W.lit[li][j] = (go && !h) ? 1 : 0;
+#pragma unroll 1
+                        for (int si = 0; si < P.small_n; si++) {
+                            stat_add<STATS>(st, kStatConeTests);
+                            const float4 s = P.small_sph[si];
+                            if (cone_sphere_candidate(s.x - ox, s.y - oy, s.z - oz, fabsf(s.w), dx, dy, dz, dist)) cm |= 1u << si;
+                        }
                     }
+                    W.cmask[li][j] = (uint16_t)cm;
                 }
             }
-            ext_done = true;
             __syncwarp();
-            if (lc == 0) break;
 
-            // C: calculateSmartShadow's 16 jittered rays (renderer.go:311-328) for every lit pair of the chunk
+            // ---- C: calculateSmartShadow's 16 jittered rays (renderer.go:311-328) for every lit pair of the chunk ----
             if (P.soft) {
                 int np = 0;
                 for (int li = 0; li < lc; li++) {
@@ -742,48 +941,112 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
                     np += __popc(m);
                 }
                 __syncwarp();
-                for (int q0 = 0; q0 < np; q0 += 2) {
-                    const int qi = q0 + (lane >> 4);
-                    const bool valid = qi < np;
-                    const int pr = valid ? (int)W.pairs[qi] : 0;
-                    const int li = pr >> 8, j = pr & 31;
-                    const int sj = base + j;
-                    bool unocc = false;
-                    if (valid) {
-                        const float ox = qf(Q, QF_OX, sj), oy = qf(Q, QF_OY, sj), oz = qf(Q, QF_OZ, sj);
-                        const float4 L0 = ldg4(S.lights + 2 * (l0 + li));
-                        float dx = L0.x - ox, dy = L0.y - oy, dz = L0.z - oz;
-                        const float dist2 = dot3(dx, dy, dz, dx, dy, dz);
-                        const float inv_d = rsqrt_fast(dist2);
-                        const float dist = dist2 * inv_d;
-                        float bx, by, bz;
-                        stat_add<STATS>(st, kStatSoftRays);
-                        rng_ball<STATS>(P, Q[QF_PIXG][sj], Q[QF_SAMPLE][sj], (Q[QF_DEPTH][sj] << 8) | kStreamShadow,
-                                        ((uint32_t)(l0 + li) << 12) | ((uint32_t)(lane & 15) << 8), bx, by, bz, st);
-                        dx = fmaf(dx, inv_d, 0.1f * bx); dy = fmaf(dy, inv_d, 0.1f * by); dz = fmaf(dz, inv_d, 0.1f * bz);
-                        normalize3(dx, dy, dz);
-                        float tt;
-                        int pp;
-                        unocc = !query<STATS, SMALL>(P, ox, oy, oz, dx, dy, dz, 0.001f, dist, true, tt, pp, st);
+                for (int p0 = 0; p0 < np; p0 += 32) {
+                    const int pc = min(32, np - p0);
+                    if (!SMALL) {
+                        // lane = pair: one cone walk collects the pair's candidate primitives
+                        if (lane < pc) {
+                            const int pr = (int)W.pairs[p0 + lane];
+                            const int sj = base + (pr & 31);
+                            const float ox = qf(SQ, SF_PX, sj), oy = qf(SQ, SF_PY, sj), oz = qf(SQ, SF_PZ, sj);
+                            const float4 L0 = ldg4(S.lights + 2 * (l0 + (pr >> 8)));
+                            float ax = L0.x - ox, ay = L0.y - oy, az = L0.z - oz;
+                            const float dist2 = dot3(ax, ay, az, ax, ay, az);
+                            const float inv_d = rsqrt_fast(dist2);
+                            ax *= inv_d; ay *= inv_d; az *= inv_d;
+                            W.ncand[lane] = P.no_cone_cull ? (uint8_t)kCandOverflow
+                                                           : (uint8_t)cone_candidates<STATS>(S, ox, oy, oz, ax, ay, az, dist2 * inv_d, W.cand[lane], st);
+                        }
+                        __syncwarp();
                     }
-                    const unsigned ub = __ballot_sync(FULL_MASK, unocc);
-                    if (valid && (lane & 15) == 0) W.cnt[li][j] = (uint8_t)__popc((lane < 16) ? (ub & 0xFFFFu) : (ub >> 16));
+                    // a quarter warp per pair; lane & 7 = k handles shadow samples 2k and 2k+1 (renderer.go:313)
+                    for (int q0 = 0; q0 < pc; q0 += 4) {
+                        const int qi = q0 + (lane >> 3);
+                        const bool valid = qi < pc;
+                        const int pr = valid ? (int)W.pairs[p0 + qi] : 0;
+                        const int li = pr >> 8, j = pr & 31;
+                        const int sj = base + j;
+                        bool unA = false, unB = false;
+                        if (valid) {
+                            const float ox = qf(SQ, SF_PX, sj), oy = qf(SQ, SF_PY, sj), oz = qf(SQ, SF_PZ, sj);
+                            const float4 L0 = ldg4(S.lights + 2 * (l0 + li));
+                            float ax = L0.x - ox, ay = L0.y - oy, az = L0.z - oz;
+                            const float dist2 = dot3(ax, ay, az, ax, ay, az);
+                            const float inv_d = rsqrt_fast(dist2);
+                            const float dist = dist2 * inv_d;
+                            ax *= inv_d; ay *= inv_d; az *= inv_d;
+                            const uint32_t sdw = SQ[SF_SD][sj];
+                            const uint4 rb = philox(P.rk, SQ[SF_PIXG][sj], sdw & 0xffffu, ((sdw >> 16) << 8) | kStreamShadow,
+                                                    ((uint32_t)(l0 + li) << 12) | ((uint32_t)(lane & 7) << 8));
+                            stat_add<STATS>(st, kStatRngBlocks);
+                            stat_add<STATS>(st, kStatSoftRays, 2);
+                            float bx, by, bz;
+                            ball_from_bits(rb.x, rb.y, bx, by, bz);
+                            float dxa = fmaf(0.1f, bx, ax), dya = fmaf(0.1f, by, ay), dza = fmaf(0.1f, bz, az);
+                            normalize3(dxa, dya, dza);
+                            ball_from_bits(rb.z, rb.w, bx, by, bz);
+                            float dxb = fmaf(0.1f, bx, ax), dyb = fmaf(0.1f, by, ay), dzb = fmaf(0.1f, bz, az);
+                            normalize3(dxb, dyb, dzb);
+                            bool occA = false, occB = false;
+                            if (SMALL) {
+                                uint32_t cm = W.cmask[li][j];
+                                stat_add<STATS>(st, kStatShadow, 2);
+                                while (cm) {
+                                    const int si = __ffs(cm) - 1;
+                                    cm &= cm - 1;
+                                    stat_add<STATS>(st, kStatSphereTests, 2);
+                                    const float4 s = P.small_sph[si];
+                                    occA = occA || sphere_occludes_unit(s, ox, oy, oz, dxa, dya, dza, 0.001f, dist);
+                                    occB = occB || sphere_occludes_unit(s, ox, oy, oz, dxb, dyb, dzb, 0.001f, dist);
+                                }
+                            } else {
+                                const uint32_t nc = W.ncand[qi];
+                                if (nc == kCandOverflow) {
+                                    float tt;
+                                    int pp;
+                                    occA = traverse<STATS>(S, ox, oy, oz, dxa, dya, dza, 0.001f, dist, true, tt, pp, st);
+                                    occB = traverse<STATS>(S, ox, oy, oz, dxb, dyb, dzb, 0.001f, dist, true, tt, pp, st);
+                                } else {
+                                    stat_add<STATS>(st, kStatShadow, 2);
+                                    for (uint32_t k = 0; k < nc; k++) {
+                                        const uint32_t ref = W.cand[qi][k];
+                                        if (ref & 0x80000000u) {
+                                            const float4* tp = S.tris + 4 * (size_t)(ref & 0x7fffffffu);
+                                            const bool ha = tri_occludes(tp, ox, oy, oz, dxa, dya, dza, 0.001f, dist);
+                                            const bool hb = tri_occludes(tp, ox, oy, oz, dxb, dyb, dzb, 0.001f, dist);
+                                            if (STATS) {
+                                                stat_add<STATS>(st, kStatTriTests, 2);
+                                                stat_add<STATS>(st, ha ? kStatTriHits : kStatTriRejA);  // rejects counted at the cheapest stage
+                                                stat_add<STATS>(st, hb ? kStatTriHits : kStatTriRejA);
+                                            }
+                                            occA = occA || ha;
+                                            occB = occB || hb;
+                                        } else {
+                                            stat_add<STATS>(st, kStatSphereTests, 2);
+                                            const float4 s = ldg4(S.spheres + ref);
+                                            occA = occA || sphere_occludes_unit(s, ox, oy, oz, dxa, dya, dza, 0.001f, dist);
+                                            occB = occB || sphere_occludes_unit(s, ox, oy, oz, dxb, dyb, dzb, 0.001f, dist);
+                                        }
+                                    }
+                                }
+                            }
+                            unA = !occA;
+                            unB = !occB;
+                        }
+                        const unsigned ua = __ballot_sync(FULL_MASK, unA), ub = __ballot_sync(FULL_MASK, unB);
+                        if (valid && (lane & 7) == 0) {
+                            const int sh = lane & 24;
+                            W.cnt[li][j] = (uint8_t)(__popc((ua >> sh) & 0xFFu) + __popc((ub >> sh) & 0xFFu));
+                        }
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
 
-            // D (lighting part): calculateDirectLighting's arithmetic for the chunk (renderer.go:258-293), lane = path
+            // ---- D: calculateDirectLighting's arithmetic for the chunk (renderer.go:258-293), lane = record ----
             if (act) {
-                const float4* mp = S.mats + 4 * (size_t)(W.flags[lane] >> 8);
-                const float4 m0 = ldg4(mp), m2 = ldg4(mp + 2);
-                const bool is_light = __float_as_int(m0.x) == 6;
-                // GetAlbedo: DiffuseLight -> 0 (material.go:304); Dielectric -> 1 (packed by the host)
-                const float kar = is_light ? 0.f : m0.y * m2.y, kag = is_light ? 0.f : m0.z * m2.y, kab = is_light ? 0.f : m0.w * m2.y;
-                const float spec_pow = __ldg(&mp[3].x);         // 0: metallic <= 0.5, no specular term
-                const float spec_w = __ldg(&mp[1].y) * 3.0f;    // metallic * 3
-                const float px = qf(Q, QF_OX, slot), py = qf(Q, QF_OY, slot), pz = qf(Q, QF_OZ, slot);
-                const float nx = W.n[0][lane], ny = W.n[1][lane], nz = W.n[2][lane];
-                float dr = W.direct[0][lane], dg = W.direct[1][lane], db = W.direct[2][lane];
+                const float px = qf(SQ, SF_PX, slot), py = qf(SQ, SF_PY, slot), pz = qf(SQ, SF_PZ, slot);
+                const float nx = qf(SQ, SF_NX, slot), ny = qf(SQ, SF_NY, slot), nz = qf(SQ, SF_NZ, slot);
                 for (int li = 0; li < lc; li++) {
                     if (!W.lit[li][lane]) continue;
                     const float factor = P.soft ? (float)W.cnt[li][lane] * (1.0f / 16.0f) : 1.0f;
@@ -812,59 +1075,26 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
                         dr = fmaf(L1.x, sw, dr); dg = fmaf(L1.y, sw, dg); db = fmaf(L1.z, sw, db);
                     }
                 }
-                W.direct[0][lane] = dr; W.direct[1][lane] = dg; W.direct[2][lane] = db;
             }
+            __syncwarp();  // lit / cnt / cmask are reused by the next chunk
         }
 
-        // ---- D (combination): traceRay's weighting (renderer.go:177-226), flush or re-queue ----
-        PathState ps;
-        bool survive = false;
+        // ---- traceRay's weighting of this hit (renderer.go:177-226): T * (emitted + w * direct) into the pixel ----
         if (act) {
-            queue_load(Q, slot, ps);  // origin/direction already describe the scattered ray
-            const uint32_t fl = W.flags[lane];
-            const float4* mp = S.mats + 4 * (size_t)(fl >> 8);
+            const float4* mp = S.mats + 4 * (size_t)SQ[SF_MAT][slot];
             const float4 m0 = ldg4(mp), m2 = ldg4(mp + 2);
             const bool is_light = __float_as_int(m0.x) == 6;
+            // DiffuseLight does not scatter: emitted + direct (renderer.go:182-184); everything else: emitted (0) + w_d * direct
+            const float wd = is_light ? 1.0f : m2.w;
             const float er = is_light ? m0.y : 0.f, eg = is_light ? m0.z : 0.f, eb = is_light ? m0.w : 0.f;  // Emitted
-            const float dr = W.direct[0][lane], dg = W.direct[1][lane], db = W.direct[2][lane];
-            if (!(fl & 1u)) {  // no scatter: emitted + direct (renderer.go:182-184)
-                ps.lr = fmaf(ps.tr, er + dr, ps.lr); ps.lg = fmaf(ps.tg, eg + dg, ps.lg); ps.lb = fmaf(ps.tb, eb + db, ps.lb);
-            } else {
-                const float wd = m2.w;
-                ps.lr = fmaf(ps.tr, fmaf(dr, wd, er), ps.lr); ps.lg = fmaf(ps.tg, fmaf(dg, wd, eg), ps.lg); ps.lb = fmaf(ps.tb, fmaf(db, wd, eb), ps.lb);
-                ps.tr *= W.att[0][lane]; ps.tg *= W.att[1][lane]; ps.tb *= W.att[2][lane];
-                ps.depth += 1;
-                if (fl & 4u) {  // the scattered ray hit something: the path goes on
-                    ps.t = W.t2[lane];
-                    ps.prim = W.prim2[lane];
-                    survive = true;
-                    // Exact dead-path test.  Whatever the remaining bounces return, it reaches this
-                    // sample as fma(T, c, L) terms with |T c| <= T * dead_bound.  If that is below
-                    // 2^-25 |L| in every channel, each such term is less than half an ulp of L and
-                    // round-to-nearest leaves L bit-for-bit unchanged: tracing on cannot alter the
-                    // result.  (Rays trapped inside a rough-metal sphere keep bouncing to max_depth
-                    // in the reference with throughput ~0.03^k; 95 such paths were the 30 % tail of
-                    // the C1 frame, profiles/r1_tail.md.)
-                    const float db = P.dead_bound;
-                    if (db > 0.f && fabsf(ps.tr) * db < 2.98023224e-8f * fabsf(ps.lr) && fabsf(ps.tg) * db < 2.98023224e-8f * fabsf(ps.lg) &&
-                        fabsf(ps.tb) * db < 2.98023224e-8f * fabsf(ps.lb))
-                        survive = false;
-                }
+            float r = qf(SQ, SF_TR, slot) * fmaf(dr, wd, er), g = qf(SQ, SF_TG, slot) * fmaf(dg, wd, eg), b = qf(SQ, SF_TB, slot) * fmaf(db, wd, eb);
+            if (P.fog_enabled) {  // extension: final = (1-f) * radiance + f * fog colour, f from the primary hit
+                const float f = qf(SQ, SF_FOG, slot);
+                r *= 1.0f - f; g *= 1.0f - f; b *= 1.0f - f;
+                if ((SQ[SF_SD][slot] >> 16) == 0) { r = fmaf(P.fog_r, f, r); g = fmaf(P.fog_g, f, g); b = fmaf(P.fog_b, f, b); }
             }
-            // miss, depth limit, no scatter: the reflected colour is black and the sample is complete
-            if (!survive) {
-                flush_radiance(P, ps.pixl, ps.fog, ps.lr, ps.lg, ps.lb);
-                if (STATS) {
-                    if (ps.depth >= 5) stat_add<STATS>(st, kStatDepth5);
-                    if (ps.depth >= 20) stat_add<STATS>(st, kStatDepth20);
-                    if ((int)ps.depth >= P.max_depth) stat_add<STATS>(st, kStatDepthMax);
-                }
-            }
+            add_radiance(P, SQ[SF_PIXL][slot], r, g, b);
         }
-        __syncwarp();  // every lane has read its slot before the survivors are compacted over the popped region
-        const unsigned hm = __ballot_sync(FULL_MASK, survive);
-        if (survive) queue_store(Q, base + __popc(hm & lt_mask), ps);
-        qcount = base + __popc(hm);
         __syncwarp();
     }
 

@@ -36,7 +36,8 @@ enum StatIndex {
     kStatDepth5 = 17,      // samples whose path reached depth >= 5 / >= 20 / max_depth
     kStatDepth20 = 18,
     kStatDepthMax = 19,
-    kStatCount = 20
+    kStatConeTests = 20,   // cone-vs-box / cone-vs-primitive tests of the soft-shadow candidate pass
+    kStatCount = 21
 };
 
 struct DevCamera {
@@ -77,9 +78,13 @@ struct TraceParams {
     uint32_t rk[20];             // Philox4x32-10 round keys: rk[2r] = key0 + r*W0, rk[2r+1] = key1 + r*W1
     int fog_enabled;
     float fog_density, fog_r, fog_g, fog_b;
-    // Upper bound on |radiance| any further bounce sequence can return per unit of throughput (host,
-    // float64, deliberately loose): used by the exact dead-path test in trace_kernel.  0 disables it.
+    // Upper bound on |emitted + w * direct| x |throughput growth| of any further bounce per unit of
+    // throughput (host, float64, deliberately loose): used by the exact dead-path test in trace_kernel
+    // (a path is dropped once every add it could still make rounds to zero in the fixed-point accumulator).
+    // 0 disables it.
     float dead_bound;
+    int urgent_depth;  // > 0: a warp whose newest survivors reached this depth extends them before refilling (tail latency)
+    int no_cone_cull;  // test switch (GORT_NO_CONE_CULL): soft-shadow rays test every primitive / walk the BVH themselves
     // tiny sphere-only scene, in the reference's scan order (small_n == 0: use the BVH)
     int small_n;
     int small_mat[kSmallMax];

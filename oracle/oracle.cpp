@@ -183,6 +183,23 @@ struct Rng {
         const double rad = std::cbrt(u3);
         return V3{rad * sxy * std::cos(phi), rad * sxy * std::sin(phi), rad * z};
     }
+    // The soft-shadow samples (renderer.go:313-316) draw TWO ball points from one Philox block in PHILOX
+    // mode (the CUDA path gives a lane two shadow rays per block): half 0 from words (0,1), half 1 from
+    // words (2,3); u1 = 21 bits, u2 = 21 bits, u3 = 22 bits, then the same loop-free map as above.
+    // MT mode: the reference's rejection loop, one call per sample.
+    V3 in_unit_sphere_half(uint32_t stream, uint32_t seq, int half) {
+        if (mode == RNG_MT) return in_unit_sphere(stream, seq);
+        uint32_t r[4];
+        block(stream, seq, r);
+        const uint32_t a = r[2 * half], b = r[2 * half + 1];
+        const double u1 = (double)(a >> 11) * (1.0 / 2097152.0), u2 = (double)(b >> 11) * (1.0 / 2097152.0);
+        const double u3 = (double)(((a & 0x7FFu) << 11) | (b & 0x7FFu)) * (1.0 / 4194304.0);
+        const double z = 1.0 - 2.0 * u1;
+        const double sxy = std::sqrt(std::fmax(0.0, 1.0 - z * z));
+        const double phi = 6.283185307179586476925286766559 * u2;
+        const double rad = std::cbrt(u3);
+        return V3{rad * sxy * std::cos(phi), rad * sxy * std::sin(phi), rad * z};
+    }
 };
 
 // ---------------------------------------------------------------------------
@@ -583,7 +600,7 @@ struct Tracer {
             const int shadowSamples = 16;
             double sum = 0.0;
             for (int i = 0; i < shadowSamples; i++) {
-                V3 off = muls(rng.in_unit_sphere(STREAM_SHADOW, (light_index << 12) | ((uint32_t)i << 8)), 0.1);
+                V3 off = muls(rng.in_unit_sphere_half(STREAM_SHADOW, (light_index << 12) | ((uint32_t)(i >> 1) << 8), i & 1), 0.1);
                 V3 softDir = normalize(add(lightDir, off));
                 Ray softRay{hit.point, softDir};
                 cnt.shadow_rays++;
@@ -1136,6 +1153,14 @@ void orc_in_unit_sphere(unsigned long long seed, unsigned pixel, unsigned sample
     rng.key[0] = (uint32_t)seed; rng.key[1] = (uint32_t)(seed >> 32);
     rng.pixel = pixel; rng.sample = sample; rng.bounce = bounce;
     put(out3, rng.in_unit_sphere(stream, seq_base));
+}
+void orc_in_unit_sphere_half(unsigned long long seed, unsigned pixel, unsigned sample, unsigned bounce, unsigned stream,
+                             unsigned seq_base, int half, double* out3) {
+    Rng rng;
+    rng.mode = RNG_PHILOX;
+    rng.key[0] = (uint32_t)seed; rng.key[1] = (uint32_t)(seed >> 32);
+    rng.pixel = pixel; rng.sample = sample; rng.bounce = bounce;
+    put(out3, rng.in_unit_sphere_half(stream, seq_base, half));
 }
 void orc_get_ray(void* sp, int camera_mode, double u, double v, double* out6) {
     Scene* s = (Scene*)sp;

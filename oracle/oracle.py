@@ -114,6 +114,7 @@ def lib() -> C.CDLL:
         up = C.POINTER(C.c_uint)
         L.orc_philox4x32_10.argtypes = [up, up, up]
         L.orc_in_unit_sphere.argtypes = [C.c_ulonglong, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, dp]
+        L.orc_in_unit_sphere_half.argtypes = [C.c_ulonglong, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_int, dp]
         L.orc_get_ray.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, dp]
         L.orc_hit_world.argtypes = [C.c_void_p, dp, dp, C.c_double, C.c_double, C.c_int, dp]
         _lib = L
@@ -365,6 +366,12 @@ def philox4x32_10(ctr, key):
     out = (C.c_uint * 4)()
     lib().orc_philox4x32_10((C.c_uint * 4)(*ctr), (C.c_uint * 2)(*key), out)
     return tuple(out[:])
+
+
+def in_unit_sphere_half(seed, pixel, sample, bounce, stream, seq_base, half):
+    out = (C.c_double * 3)()
+    lib().orc_in_unit_sphere_half(seed, pixel, sample, bounce, stream, seq_base, half, out)
+    return np.array(out[:])
 
 
 def in_unit_sphere(seed, pixel, sample, bounce, stream, seq_base):

@@ -228,3 +228,29 @@ def test_c1_golden_fixture(gort, renderer):
     rad = renderer.ReadRadiance(200, 150)
     close = sum(np.allclose(rad[s["y"], s["x"]], s["rgb"], rtol=2e-3, atol=1e-5) for s in meta["radiance"])
     assert close >= len(meta["radiance"]) - 2
+
+
+def test_soft_shadow_candidate_culling_is_exact(gort, renderer):
+    """The per-(hit, light) cone culling of soft-shadow candidates (kernels.cu) only skips tests that must
+    fail: with GORT_NO_CONE_CULL=1 every ray tests every primitive (tiny sphere scenes: same arithmetic,
+    the radiance must be bit-identical) or walks the BVH itself (BVH scenes: same booleans up to the
+    rounding of two formulations of the same test)."""
+    import os
+    for d, opts, W, H, exact in ((Cm.c1_view(), 0, 400, 300, True), (Cm.c2_view(), 1, 300, 225, False),
+                                 (Cm.random_sphere_scene(300, 7), 0, 256, 192, False)):
+        sc = gort.SceneFromDict(d, opts)
+        configure(renderer, 8, 12, seed=11)
+        renderer.Render(sc, W, H)
+        a = renderer.ReadRadiance(W, H)
+        os.environ["GORT_NO_CONE_CULL"] = "1"
+        try:
+            renderer.Render(sc, W, H)
+            b = renderer.ReadRadiance(W, H)
+        finally:
+            del os.environ["GORT_NO_CONE_CULL"]
+        assert a.max() > 0
+        if exact:
+            assert np.array_equal(a, b)
+        else:
+            same = float((np.abs(a - b).max(axis=-1) <= 1e-9).mean())
+            assert same >= 0.9995, same

@@ -252,6 +252,28 @@ def test_in_unit_sphere_distribution(oracle):
     assert stats.kstest((pts[:, 2] / r + 1) / 2, "uniform").pvalue > 1e-3
 
 
+def test_in_unit_sphere_half_distribution(oracle):
+    """The paired sampler of the soft-shadow stream (two ball points per Philox block, 21/21/22-bit uniforms)
+    obeys the same uniform-ball law, for both halves, and the halves are uncorrelated."""
+    n = 12000
+    from scipy import stats
+    halves = []
+    for half in (0, 1):
+        pts = np.array([oracle.in_unit_sphere_half(5, i, 1, 2, oracle.STREAM_SHADOW, 0x1300, half) for i in range(n)])
+        r = np.linalg.norm(pts, axis=1)
+        assert (r < 1).all()
+        m = _ball_moments(pts)
+        assert abs(m["r3_mean"] - 0.5) < 0.012 and m["mean"] < 0.015
+        for k in ("x2", "y2", "z2"):
+            assert abs(m[k] - 0.2) < 0.008
+        assert stats.kstest(r ** 3, "uniform").pvalue > 1e-3
+        assert stats.kstest((np.arctan2(pts[:, 1], pts[:, 0]) + np.pi) / (2 * np.pi), "uniform").pvalue > 1e-3
+        assert stats.kstest((pts[:, 2] / r + 1) / 2, "uniform").pvalue > 1e-3
+        halves.append(pts)
+    c = np.corrcoef(halves[0].T, halves[1].T)[:3, 3:]
+    assert np.abs(c).max() < 0.04
+
+
 def test_rejection_and_loop_free_samplers_agree(oracle):
     """Reference-mode (mt19937 + the Go rejection loop) and Philox-mode renders of a rough-metal / lambertian
     scene with soft shadows converge to the same image: the two unit-ball samplers are interchangeable."""
