@@ -103,11 +103,7 @@ __device__ __forceinline__ float lg2_fast(float x) {
 // rejection-samples the cube; a data-dependent loop costs a warp its slowest lane (first profile: 13
 // active lanes per instruction, RNG = 32 % of issued instructions), so the same distribution is drawn
 // loop-free from one Philox block: z = 1-2u1, phi = 2 pi u2, r = cbrt(u3) (oracle.cpp Rng::in_unit_sphere).
-template <bool STATS>
-__device__ __forceinline__ void rng_ball(const TraceParams& P, uint32_t pix, uint32_t samp, uint32_t bounce_stream,
-                                         uint32_t seq, float& bx, float& by, float& bz, Stats& st) {
-    const uint4 r = philox(P.rk, pix, samp, bounce_stream, seq);
-    stat_add<STATS>(st, kStatRngBlocks);
+__device__ __forceinline__ void ball_from_block(const uint4 r, float& bx, float& by, float& bz) {
     const float k = 1.0f / 16777216.0f;
     const float u1 = (float)(r.x >> 8) * k, u2 = (float)(r.y >> 8) * k, u3 = (float)(r.z >> 8) * k;
     const float z = fmaf(-2.0f, u1, 1.0f);
@@ -203,9 +199,12 @@ __device__ __forceinline__ void test_tris(const SceneView& S, RayQuery& q, uint3
 // hitWorld over the BVH.  `any` (per lane, data not code: closest-hit and shadow rays share every
 // instruction of a batch) ends the walk at the first accepted primitive — exactly how the renderer
 // uses hitWorld for shadows (renderer.go:305,320: only `hit` is read).
+// One copy per kernel (__noinline__): inlined at its five call sites the walk was 42 % of an 80 KB kernel,
+// more than the 32 KB instruction cache holds; warps sit in different stages, so they thrashed it
+// (profiles/r1_ncu_trace_c2view_v5.txt: stall_no_instruction 5.2 per issue).
 template <bool STATS>
-__device__ __forceinline__ bool traverse(const SceneView& S, float ox, float oy, float oz, float dx, float dy, float dz,
-                                         float tmin, float tmax, bool any, float& t_out, int& prim_out, Stats& st) {
+__device__ __noinline__ bool traverse(const SceneView& S, float ox, float oy, float oz, float dx, float dy, float dz,
+                                      float tmin, float tmax, bool any, float& t_out, int& prim_out, Stats& st) {
     stat_add<STATS>(st, any ? kStatShadow : kStatClosest);
     if (S.n_nodes == 0) return false;
     RayQuery q;
@@ -289,9 +288,11 @@ __device__ __forceinline__ bool small_query(const TraceParams& P, float ox, floa
     const float inv_a = rcp_fast(a);
     float tbest = tmax;
     int best = -1;
-#pragma unroll
-    for (int i = 0; i < kSmallMax; i++) {
-        if (i < P.small_n) {
+    // rolled on purpose: unrolled 12x at three call sites this loop was 30 % of the kernel's code and the
+    // kernel did not fit the instruction cache (profiles/r1_ncu_trace_c1view_v5.txt)
+#pragma unroll 1
+    for (int i = 0; i < P.small_n; i++) {
+        {
             stat_add<STATS>(st, kStatSphereTests);
             const float4 s = P.small_sph[i];
             const float ocx = ox - s.x, ocy = oy - s.y, ocz = oz - s.z;
@@ -760,19 +761,26 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
                 const uint32_t bs = (depth << 8) | kStreamScatter;
                 bool scattered = true;
                 float ar = 0.f, ag = 0.f, ab = 0.f;
+                // Scatter draws at most one Philox block per hit, counter (pixel, sample, bounce|scatter, 0):
+                // Lambertian and rough Metal/Shiny/Mirror turn it into a ball point, Glass/Dielectric use word 0
+                const bool rough = (mtype == 2) ? (m1.x > 0.f) : (m1.x > 0.001f);
+                uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
+                if (mtype == 0 || (mtype <= 3 && rough) || mtype == 4 || mtype == 5) {
+                    rnd = philox(P.rk, pixg, sample, bs, 0u);
+                    stat_add<STATS>(st, kStatRngBlocks);
+                }
                 if (mtype == 0) {  // Lambertian (material.go:26-35)
                     float bx, by, bz;
-                    rng_ball<STATS>(P, pixg, sample, bs, 0u, bx, by, bz, st);
+                    ball_from_block(rnd, bx, by, bz);
                     sx = nx + bx; sy = ny + by; sz = nz + bz;
                     if (fabsf(sx) < 1e-8f && fabsf(sy) < 1e-8f && fabsf(sz) < 1e-8f) { sx = nx; sy = ny; sz = nz; }
                     normalize3(sx, sy, sz);
                     ar = m0.y; ag = m0.z; ab = m0.w;
                 } else if (mtype <= 3) {  // Metal / Shiny / PerfectMirror (material.go:75-113,169-189; advanced_materials.go:125-144)
                     sx = fmaf(-2.0f * ddn, nx, dx); sy = fmaf(-2.0f * ddn, ny, dy); sz = fmaf(-2.0f * ddn, nz, dz);  // Reflect vector.go:77
-                    const bool rough = (mtype == 2) ? (m1.x > 0.f) : (m1.x > 0.001f);
                     if (rough) {
                         float bx, by, bz;
-                        rng_ball<STATS>(P, pixg, sample, bs, 0u, bx, by, bz, st);
+                        ball_from_block(rnd, bx, by, bz);
                         sx = fmaf(m1.x, bx, sx); sy = fmaf(m1.x, by, sy); sz = fmaf(m1.x, bz, sz);
                         normalize3(sx, sy, sz);
                     }
@@ -801,9 +809,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
                     if (!reflect) {
                         const float r0 = m3.y;  // ((1-x)/(1+x))^2 is the same for x = ior and x = 1/ior
                         const float refl = fmaf(1.0f - r0, pow5(1.0f - cosT), r0);  // reflectance material.go:282-286
-                        const uint4 r = philox(P.rk, pixg, sample, bs, 0u);
-                        stat_add<STATS>(st, kStatRngBlocks);
-                        reflect = refl > (float)(r.x >> 8) * (1.0f / 16777216.0f);
+                        reflect = refl > (float)(rnd.x >> 8) * (1.0f / 16777216.0f);
                     }
                     if (reflect) {
                         sx = fmaf(-2.0f * udn, nx, ux); sy = fmaf(-2.0f * udn, ny, uy); sz = fmaf(-2.0f * udn, nz, uz);
