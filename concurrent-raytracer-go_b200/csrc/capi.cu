@@ -336,7 +336,8 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     tp.inv_w = 1.0f / (float)p->width; tp.inv_h = 1.0f / (float)p->height;
     // tiny sphere-only scenes: the spheres ride in the kernel parameters, in scan order
     tp.small_n = 0;
-    if (ctx->scene.tris.empty() && !ctx->scene.spheres.empty() && (int)ctx->scene.spheres.size() <= kSmallMax) {
+    if (ctx->scene.tris.empty() && !ctx->scene.spheres.empty() && (int)ctx->scene.spheres.size() <= kSmallMax &&
+        (int)ctx->scene.mats.size() <= kSmallMax && (int)ctx->scene.lights.size() <= kSmallLights) {
         std::vector<const HostSphere*> sorted;
         for (const HostSphere& hs : ctx->scene.spheres) sorted.push_back(&hs);
         std::sort(sorted.begin(), sorted.end(), [](const HostSphere* a, const HostSphere* b) { return a->order < b->order; });
@@ -344,6 +345,16 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
         for (int i = 0; i < tp.small_n; i++) {
             tp.small_sph[i] = make_float4((float)sorted[i]->c[0], (float)sorted[i]->c[1], (float)sorted[i]->c[2], (float)sorted[i]->r);
             tp.small_mat[i] = sorted[i]->mat;
+        }
+        for (size_t i = 0; i < ctx->scene.mats.size(); i++) {
+            F4 m[4];
+            pack_material(ctx->scene.mats[i], m);
+            for (int k = 0; k < 4; k++) tp.small_mats[i][k] = make_float4(m[k].x, m[k].y, m[k].z, m[k].w);
+        }
+        for (size_t i = 0; i < ctx->scene.lights.size(); i++) {
+            const HostLight& l = ctx->scene.lights[i];
+            tp.small_lights[i][0] = make_float4((float)l.pos[0], (float)l.pos[1], (float)l.pos[2], (float)l.intensity);
+            tp.small_lights[i][1] = make_float4((float)l.color[0], (float)l.color[1], (float)l.color[2], 0.f);
         }
     }
     tp.jitter = p->anti_aliasing ? 1 : 0; tp.recursive = p->recursive_reflections ? 1 : 0; tp.soft = p->soft_shadows ? 1 : 0;
@@ -490,7 +501,7 @@ int gort_create(const int* device_ids, int n_devices, gort_ctx** out) {
         for (int k = 0; k < 4 && e == cudaSuccess; k++) e = cudaEventCreate(&d.ev[k]);
         if (e == cudaSuccess) e = cudaMalloc(&d.d_counter, 16);
         if (e == cudaSuccess) e = cudaMalloc(&d.d_stats, kStatCount * sizeof(unsigned long long));
-        if (e == cudaSuccess && getenv("GORT_DEBUG_TIMES")) e = cudaMalloc(&d.d_debug, (1 + 4 * 148 * 64) * sizeof(unsigned long long));
+        if (e == cudaSuccess && getenv("GORT_DEBUG_TIMES")) e = cudaMalloc(&d.d_debug, (1 + 8 * 148 * 64) * sizeof(unsigned long long));
         if (e != cudaSuccess) return bail(GORT_ERR_CUDA, std::string("device init: ") + cudaGetErrorString(e));
     }
     if (n_devices > 1) {  // direct NVLink copies for the slab gather

@@ -26,6 +26,12 @@ namespace gort {
 
 #define FULL_MASK 0xffffffffu
 
+#ifdef GORT_DEBUG
+constexpr bool kDbg = true;
+#else
+constexpr bool kDbg = false;
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------------
@@ -324,6 +330,19 @@ __device__ __forceinline__ bool query(const TraceParams& P, float ox, float oy, 
     return traverse<STATS>(P.scene, ox, oy, oz, dx, dy, dz, tmin, tmax, any, t_out, prim_out, st);
 }
 
+// material / light records: tiny scenes read them from the kernel parameter bank (no memory latency on
+// the dependent chain of a deep path), BVH scenes from global memory through L1
+template <bool SMALL>
+__device__ __forceinline__ float4 mat4(const TraceParams& P, int mat, int k) {
+    if (SMALL) return P.small_mats[mat][k];
+    return ldg4(P.scene.mats + 4 * (size_t)mat + k);
+}
+template <bool SMALL>
+__device__ __forceinline__ float4 light4(const TraceParams& P, int light, int k) {
+    if (SMALL) return P.small_lights[light][k];
+    return ldg4(P.scene.lights + 2 * (size_t)light + k);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Soft-shadow candidate culling.
 //
@@ -582,8 +601,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
     const uint32_t n_batches = (uint32_t)((P.samples + spu - 1) / spu);
     const uint32_t n_units = n_active * n_batches, deep_units = n_deep * n_batches;
 
-    unsigned long long t_units_done = 0, dbg_rounds = 0, dbg_paths = 0;
-    if (P.debug_times && lane == 0) {
+    // per-warp timeline, compiled in only with -DGORT_DEBUG (lib/libgort_dbg.so; tools/debug_times.py)
+    unsigned long long t_units_done = 0, dbg_rounds = 0, dbg_paths = 0, dbg_shades = 0, dbg_t_ext = 0, dbg_t_shade = 0, dbg_t0 = 0;
+    if (kDbg && P.debug_times && lane == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         atomicMin(P.debug_times, t);
@@ -617,7 +637,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
                 u = __shfl_sync(FULL_MASK, u, 0);
                 if (u >= n_units) {
                     more_units = false;
-                    if (P.debug_times) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_units_done));
+                    if (kDbg && P.debug_times) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_units_done));
                     continue;
                 }
                 // unit = (sample batch, active 8x4 block), batch-major; all units of the blocks that can see
@@ -704,9 +724,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
             const int base = pqn - n;
             const bool act = lane < n;
             const int slot = base + (act ? lane : 0);
-            if (P.debug_times && !more_units) {
+            if (kDbg && P.debug_times && !more_units) {
                 dbg_rounds++;
                 dbg_paths += n;
+                dbg_t0 = clock64();
             }
             bool survive = false;
             float px = 0.f, py = 0.f, pz = 0.f, sx = 0.f, sy = 0.f, sz = 0.f, tr = 0.f, tg = 0.f, tb = 0.f, fog = 0.f;
@@ -754,8 +775,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
                     SQ[SF_FOG][ss] = __float_as_uint(fog);
                 }
 
-                const float4* mp = S.mats + 4 * (size_t)mat;
-                const float4 m0 = ldg4(mp), m1 = ldg4(mp + 1), m2 = ldg4(mp + 2), m3 = ldg4(mp + 3);
+                const float4 m0 = mat4<SMALL>(P, mat, 0), m1 = mat4<SMALL>(P, mat, 1), m2 = mat4<SMALL>(P, mat, 2), m3 = mat4<SMALL>(P, mat, 3);
                 const int mtype = __float_as_int(m0.x);
                 const uint32_t depth = sd >> 16, sample = sd & 0xffffu;
                 const uint32_t bs = (depth << 8) | kStreamScatter;
@@ -869,6 +889,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
             sqn += n;
             urgent = P.urgent_depth > 0 && __any_sync(FULL_MASK, survive && (int)(sd >> 16) >= P.urgent_depth);
             __syncwarp();
+            if (kDbg && P.debug_times && !more_units) dbg_t_ext += clock64() - dbg_t0;
             continue;
         }
 
@@ -879,18 +900,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
         const bool act = lane < n;
         const int slot = base + (act ? lane : 0);
         const float inv_n = 1.0f / (float)n;
+        if (kDbg && P.debug_times && !more_units) {
+            dbg_shades++;
+            dbg_t0 = clock64();
+        }
         // lane = record: material constants and the running total (starts at the ambient term, renderer.go:236-246)
         float dr = 0.f, dg = 0.f, db = 0.f;
         float kar = 0.f, kag = 0.f, kab = 0.f, spec_pow = 0.f, spec_w = 0.f;
         if (act) {
-            const float4* mp = S.mats + 4 * (size_t)SQ[SF_MAT][slot];
-            const float4 m0 = ldg4(mp), m2 = ldg4(mp + 2);
+            const int mat = (int)SQ[SF_MAT][slot];
+            const float4 m0 = mat4<SMALL>(P, mat, 0), m2 = mat4<SMALL>(P, mat, 2);
             const bool is_light = __float_as_int(m0.x) == 6;
             // GetAlbedo: DiffuseLight -> 0 (material.go:304); Dielectric -> 1 (packed by the host)
             kar = is_light ? 0.f : m0.y * m2.y; kag = is_light ? 0.f : m0.z * m2.y; kab = is_light ? 0.f : m0.w * m2.y;
             dr = dg = db = m2.x;
-            spec_pow = __ldg(&mp[3].x);       // 0: metallic <= 0.5, no specular term
-            spec_w = __ldg(&mp[1].y) * 3.0f;  // metallic * 3
+            spec_pow = mat4<SMALL>(P, mat, 3).x;       // 0: metallic <= 0.5, no specular term
+            spec_w = mat4<SMALL>(P, mat, 1).y * 3.0f;  // metallic * 3
         }
         const int nl = S.n_lights;
         for (int l0 = 0; l0 < nl; l0 += kLightChunk) {
@@ -904,7 +929,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
                 const int j = valid ? r - li * n : 0;
                 const int sj = base + j;
                 const float ox = qf(SQ, SF_PX, sj), oy = qf(SQ, SF_PY, sj), oz = qf(SQ, SF_PZ, sj);
-                const float4 L0 = ldg4(S.lights + 2 * (l0 + li));
+                const float4 L0 = light4<SMALL>(P, l0 + li, 0);
                 float dx = L0.x - ox, dy = L0.y - oy, dz = L0.z - oz;
                 const float dist2 = dot3(dx, dy, dz, dx, dy, dz);
                 const float inv_d = dist2 > 0.f ? rsqrt_fast(dist2) : 0.f;
@@ -955,7 +980,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
                             const int pr = (int)W.pairs[p0 + lane];
                             const int sj = base + (pr & 31);
                             const float ox = qf(SQ, SF_PX, sj), oy = qf(SQ, SF_PY, sj), oz = qf(SQ, SF_PZ, sj);
-                            const float4 L0 = ldg4(S.lights + 2 * (l0 + (pr >> 8)));
+                            const float4 L0 = light4<SMALL>(P, l0 + (pr >> 8), 0);
                             float ax = L0.x - ox, ay = L0.y - oy, az = L0.z - oz;
                             const float dist2 = dot3(ax, ay, az, ax, ay, az);
                             const float inv_d = rsqrt_fast(dist2);
@@ -975,7 +1000,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
                         bool unA = false, unB = false;
                         if (valid) {
                             const float ox = qf(SQ, SF_PX, sj), oy = qf(SQ, SF_PY, sj), oz = qf(SQ, SF_PZ, sj);
-                            const float4 L0 = ldg4(S.lights + 2 * (l0 + li));
+                            const float4 L0 = light4<SMALL>(P, l0 + li, 0);
                             float ax = L0.x - ox, ay = L0.y - oy, az = L0.z - oz;
                             const float dist2 = dot3(ax, ay, az, ax, ay, az);
                             const float inv_d = rsqrt_fast(dist2);
@@ -1058,7 +1083,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
                     const float factor = P.soft ? (float)W.cnt[li][lane] * (1.0f / 16.0f) : 1.0f;
                     if (!(factor > 0.0f)) continue;
                     stat_add<STATS>(st, kStatDiffuse);
-                    const float4 L0 = ldg4(S.lights + 2 * (l0 + li));
+                    const float4 L0 = light4<SMALL>(P, l0 + li, 0);
                     float ldx = L0.x - px, ldy = L0.y - py, ldz = L0.z - pz;
                     const float dist2 = dot3(ldx, ldy, ldz, ldx, ldy, ldz);
                     const float inv_d = rsqrt_fast(dist2);
@@ -1069,7 +1094,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
                     dr = fmaf(kar, kdw, dr); dg = fmaf(kag, kdw, dg); db = fmaf(kab, kdw, db);
                     if (spec_pow > 0.f) {  // metallic > 0.5, resolved in float64 on the host
                         stat_add<STATS>(st, kStatSpec);
-                        const float4 L1 = ldg4(S.lights + 2 * (l0 + li) + 1);
+                        const float4 L1 = light4<SMALL>(P, l0 + li, 1);
                         float vx = -px, vy = -py, vz = -pz;  // viewDir toward the world origin (renderer.go:279)
                         normalize3(vx, vy, vz);
                         float hx = ldx + vx, hy = ldy + vy, hz = ldz + vz;
@@ -1087,8 +1112,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
 
         // ---- traceRay's weighting of this hit (renderer.go:177-226): T * (emitted + w * direct) into the pixel ----
         if (act) {
-            const float4* mp = S.mats + 4 * (size_t)SQ[SF_MAT][slot];
-            const float4 m0 = ldg4(mp), m2 = ldg4(mp + 2);
+            const int mat = (int)SQ[SF_MAT][slot];
+            const float4 m0 = mat4<SMALL>(P, mat, 0), m2 = mat4<SMALL>(P, mat, 2);
             const bool is_light = __float_as_int(m0.x) == 6;
             // DiffuseLight does not scatter: emitted + direct (renderer.go:182-184); everything else: emitted (0) + w_d * direct
             const float wd = is_light ? 1.0f : m2.w;
@@ -1102,16 +1127,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
             add_radiance(P, SQ[SF_PIXL][slot], r, g, b);
         }
         __syncwarp();
+        if (kDbg && P.debug_times && !more_units) dbg_t_shade += clock64() - dbg_t0;
     }
 
-    if (P.debug_times && lane == 0) {
+    if (kDbg && P.debug_times && lane == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         const unsigned int w = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-        P.debug_times[1 + 4 * w] = t_units_done;
-        P.debug_times[2 + 4 * w] = t;
-        P.debug_times[3 + 4 * w] = dbg_rounds;
-        P.debug_times[4 + 4 * w] = dbg_paths;
+        unsigned long long* o = P.debug_times + 1 + 8 * (size_t)w;
+        o[0] = t_units_done; o[1] = t; o[2] = dbg_rounds; o[3] = dbg_paths; o[4] = dbg_shades; o[5] = dbg_t_ext; o[6] = dbg_t_shade;
     }
     if (STATS && P.stats) {
 #pragma unroll
@@ -1285,28 +1309,29 @@ static cudaError_t launch_trace_variant(const TraceParams& p, int sm_count, cuda
         if (e != cudaSuccess) return e;
         ctas_per_sm = n > 0 ? n : 1;
     }
-    if (p.debug_times) {  // GORT_DEBUG_TIMES: per-warp finish times of this launch on stderr
+    if (kDbg && p.debug_times) {  // -DGORT_DEBUG build + GORT_DEBUG_TIMES=1: per-warp timeline of this launch on stderr
         const int nw = sm_count * ctas_per_sm * kWarpsPerCta;
         cudaMemsetAsync(p.debug_times, 0xff, 8, stream);
-        cudaMemsetAsync(p.debug_times + 1, 0, (size_t)nw * 32, stream);
+        cudaMemsetAsync(p.debug_times + 1, 0, (size_t)nw * 64, stream);
         trace_kernel<STATS, SMALL><<<sm_count * ctas_per_sm, kWarpsPerCta * 32, 0, stream>>>(p);
-        std::vector<unsigned long long> h(1 + 4 * (size_t)nw);
+        std::vector<unsigned long long> h(1 + 8 * (size_t)nw);
         cudaMemcpyAsync(h.data(), p.debug_times, h.size() * 8, cudaMemcpyDeviceToHost, stream);
         cudaStreamSynchronize(stream);
-        struct Rec { double units, end; unsigned long long rounds, paths; };
+        struct Rec { double units, end; unsigned long long rounds, paths, shades; double ext_us, shade_us; };
         std::vector<Rec> recs;
         for (int w = 0; w < nw; w++) {
-            if (!h[2 + 4 * w]) continue;
-            recs.push_back(Rec{(double)(h[1 + 4 * w] - h[0]) * 1e-3, (double)(h[2 + 4 * w] - h[0]) * 1e-3, h[3 + 4 * w], h[4 + 4 * w]});
+            const unsigned long long* o = &h[1 + 8 * (size_t)w];
+            if (!o[1]) continue;
+            recs.push_back(Rec{(double)(o[0] - h[0]) * 1e-3, (double)(o[1] - h[0]) * 1e-3, o[2], o[3], o[4], (double)o[5] / 1965.0, (double)o[6] / 1965.0});
         }
         std::sort(recs.begin(), recs.end(), [](const Rec& a, const Rec& b) { return a.end < b.end; });
         auto at = [&](double q) -> const Rec& { return recs[(size_t)(q * (recs.size() - 1))]; };
         if (!recs.empty()) {
             fprintf(stderr, "[gort debug] warps %zu finish us p0 %.1f p10 %.1f p50 %.1f p90 %.1f p99 %.1f p100 %.1f\n", recs.size(), at(0).end, at(0.1).end,
                     at(0.5).end, at(0.9).end, at(0.99).end, at(1).end);
-            for (size_t i = recs.size() > 8 ? recs.size() - 8 : 0; i < recs.size(); i++)
-                fprintf(stderr, "[gort debug]   slow warp: units exhausted %.1f us, end %.1f us, rounds after %llu, paths after %llu\n", recs[i].units, recs[i].end,
-                        recs[i].rounds, recs[i].paths);
+            for (size_t i = recs.size() > 6 ? recs.size() - 6 : 0; i < recs.size(); i++)
+                fprintf(stderr, "[gort debug]   slow warp: units exhausted %.1f us, end %.1f us; after that %llu EXTEND rounds (%llu paths) %.1f us, %llu SHADE rounds %.1f us\n",
+                        recs[i].units, recs[i].end, recs[i].rounds, recs[i].paths, recs[i].ext_us, recs[i].shades, recs[i].shade_us);
         }
         return cudaGetLastError();
     }

@@ -8,7 +8,8 @@ namespace gort {
 
 constexpr int kTile = 32;                 // createRenderTasks tileSize (renderer.go:401)
 constexpr int kTilePixels = kTile * kTile;
-constexpr int kSmallMax = 12;             // sphere-only scenes up to this size use the unrolled linear scan
+constexpr int kSmallMax = 12;             // sphere-only scenes up to this size use the linear scan from the parameter bank
+constexpr int kSmallLights = 4;           // ... if they also have at most this many lights
 constexpr int kAccumFracBits = 30;        // fixed-point radiance accumulators: value * 2^30 in int64
 constexpr float kSampleClamp = 65536.0f;  // |per-sample radiance| clamp before fixed-point conversion
 
@@ -89,6 +90,8 @@ struct TraceParams {
     int small_n;
     int small_mat[kSmallMax];
     float4 small_sph[kSmallMax];
+    float4 small_mats[kSmallMax][4];      // the scene's materials (same packing as SceneView::mats)
+    float4 small_lights[kSmallLights][2];  // the scene's lights (same packing as SceneView::lights)
 };
 
 struct ResolveParams {
