@@ -361,7 +361,7 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     tp.tiles_x = tiles_x; tp.tiles_y = tiles_y;
     tp.shard_rank = eff_rank; tp.shard_count = eff_count; tp.n_local_tiles = n_local;
     // work units = (sample batch, active 8x4 block), sized on the device: aim for >= 8 per resident warp
-    tp.target_units = 8u * (uint32_t)d.sm_count * 24u;  // ~8 units per resident warp
+    tp.target_units = 8u * (uint32_t)d.sm_count * 32u;  // ~8 units per resident warp
     tp.active_list = d.d_active; tp.active_count = d.d_counter + 1;
 
     tp.debug_times = d.d_debug;

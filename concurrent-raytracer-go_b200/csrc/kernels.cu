@@ -501,14 +501,19 @@ __device__ __forceinline__ uint32_t cone_candidates(const SceneView& S, float ox
 // and the scratch of the shade round.
 // ---------------------------------------------------------------------------------------------
 constexpr int kWarpsPerCta = 4;
-constexpr int kQueueCap = 64;   // neither queue exceeds 63: an action that pushes <= 32 only runs below 32
-constexpr int kLightChunk = 8;  // lights handled per pass of a shade round
+// Queue capacity.  Shared memory is what limits the resident warps (64 registers per thread would allow 32
+// warps per SM): 48 entries instead of 64 brings the tiny-scene kernel from 6 to 8 CTAs per SM.  Invariants:
+// FILL (pushes <= 32 paths) only runs with pqn <= kQueueCap - 32; EXTEND pops n <= 32 paths and pushes n
+// records, and only runs with sqn + n <= kQueueCap (SHADE makes room first).
+constexpr int kQueueCap = 48;
+constexpr int kLightChunkMax = 8;  // lights handled per pass of a shade round (tiny scenes: kSmallLights)
 enum PField { PF_PX, PF_PY, PF_PZ, PF_DX, PF_DY, PF_DZ, PF_PRIM, PF_TR, PF_TG, PF_TB, PF_PIXG, PF_PIXL, PF_SD, PF_FOG, PF_COUNT };
 enum SField { SF_PX, SF_PY, SF_PZ, SF_NX, SF_NY, SF_NZ, SF_TR, SF_TG, SF_TB, SF_MAT, SF_PIXG, SF_PIXL, SF_SD, SF_FOG, SF_COUNT };
 // *_SD = sample | depth << 16;  *_FOG = fog factor of the path's primary hit (extension)
 
 template <bool SMALL>
 struct WarpShared {
+    static constexpr int kLightChunk = SMALL ? kSmallLights : kLightChunkMax;
     uint32_t pq[PF_COUNT][kQueueCap];
     uint32_t sq[SF_COUNT][kQueueCap];
     uint8_t lit[kLightChunk][32];        // hard shadow ray unoccluded
@@ -570,12 +575,10 @@ __device__ __forceinline__ void ball_from_bits(uint32_t a, uint32_t b, float& bx
 //           pre-culled with the pair's cone), then calculateDirectLighting's arithmetic and ONE
 //           fixed-point add of T_k * (...) to the pixel.
 // ---------------------------------------------------------------------------------------------
-#ifndef GORT_MIN_CTAS
-#define GORT_MIN_CTAS 6
-#endif
-
+// resident CTAs per SM the register allocation must allow: 8 (64 registers) for the tiny-scene kernel, whose
+// shared memory fits 8; 6 for the BVH kernel (its walk needs ~80 registers)
 template <bool STATS, bool SMALL>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel(const __grid_constant__ TraceParams P) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 6) trace_kernel(const __grid_constant__ TraceParams P) {
     __shared__ WarpShared<SMALL> wsh[kWarpsPerCta];
     const int lane = threadIdx.x & 31;
     WarpShared<SMALL>& W = wsh[threadIdx.x >> 5];
@@ -618,14 +621,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GORT_MIN_CTAS) trace_kernel
     bool lane_valid = false, jit_valid = false;
     uint32_t jit_z = 0, jit_w = 0;
     const unsigned lt_mask = (1u << lane) - 1u;
+    constexpr int kLightChunk = WarpShared<SMALL>::kLightChunk;
 
     for (;;) {
         const bool can_fill = (s_cur < s_end) || more_units;
         int action;  // 0 FILL, 1 EXTEND, 2 SHADE
         if (sqn >= 32) action = 2;
-        else if (pqn >= 32 || (pqn > 0 && urgent)) action = 1;
+        else if (pqn > kQueueCap - 32 || (pqn > 0 && (urgent || !can_fill)))
+            action = (sqn + min(32, pqn) > kQueueCap) ? 2 : 1;  // EXTEND, after SHADE has made room for its records
         else if (can_fill) action = 0;
-        else if (pqn > 0) action = 1;
         else if (sqn > 0) action = 2;
         else break;
 
