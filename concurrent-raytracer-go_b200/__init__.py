@@ -93,6 +93,7 @@ class Stats(C.Structure):
         ("diffuse_evals", C.c_uint64), ("specular_evals", C.c_uint64),
         ("paths_depth_ge5", C.c_uint64), ("paths_depth_ge20", C.c_uint64), ("paths_depth_max", C.c_uint64),
         ("cone_tests", C.c_uint64),
+        ("walk_lane_visits", C.c_uint64 * 4), ("walk_warp_visits", C.c_uint64 * 4),
         ("algorithmic_flops", C.c_double),
     ]
 

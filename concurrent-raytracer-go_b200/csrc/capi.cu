@@ -444,6 +444,7 @@ int collect_stats(gort_ctx* ctx, const gort_render_params* p, gort_stats* s, dou
         s->soft_shadow_rays = tot[kStatSoftRays]; s->diffuse_evals = tot[kStatDiffuse]; s->specular_evals = tot[kStatSpec];
         s->paths_depth_ge5 = tot[kStatDepth5]; s->paths_depth_ge20 = tot[kStatDepth20]; s->paths_depth_max = tot[kStatDepthMax];
         s->cone_tests = tot[kStatConeTests];
+        for (int k = 0; k < 4; k++) { s->walk_lane_visits[k] = tot[kStatWalkLane0 + k]; s->walk_warp_visits[k] = tot[kStatWalkWarp0 + k]; }
         // SURVEY §8d operation costs (FMA = 2 flops): ray generation 12, AABB slab 24 (two per node),
         // sphere 23 miss / 47 hit, triangle 20/30/46/52 staged rejects / 92 accept, 30 per (hit, light)
         // set-up, 36 per soft-shadow direction, 50 per diffuse term, 45 per specular term, ~70 per

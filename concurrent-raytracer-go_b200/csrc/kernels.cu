@@ -323,6 +323,18 @@ __device__ __forceinline__ bool small_query(const TraceParams& P, float ox, floa
     return best >= 0;
 }
 
+// STATS only: account the node visits a lane made since `before` to call site `site` (see kStatWalkLane0)
+template <bool STATS>
+__device__ __forceinline__ void walk_account(Stats& st, unsigned int before, int site) {
+    if (STATS) {
+        const unsigned int d = st.v[kStatNodes] - before;
+        const unsigned int m = __activemask();
+        const unsigned int mx = __reduce_max_sync(m, d);
+        st.v[kStatWalkLane0 + site] += d;
+        if ((int)(threadIdx.x & 31) == __ffs(m) - 1) st.v[kStatWalkWarp0 + site] += 32u * mx;
+    }
+}
+
 template <bool STATS, bool SMALL>
 __device__ __forceinline__ bool query(const TraceParams& P, float ox, float oy, float oz, float dx, float dy, float dz, float tmin,
                                       float tmax, bool any, float& t_out, int& prim_out, Stats& st) {
@@ -697,7 +709,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 6) trace_kernel
                 dz = fmaf(v, P.cam.vz, fmaf(u, P.cam.hz, P.cam.llz));
                 // traceRay depth 0 (renderer.go:166-173); max_depth <= 0 returns black before any hit test
                 if (P.max_depth > 0)
-                    hit = query<STATS, SMALL>(P, P.cam.ox, P.cam.oy, P.cam.oz, dx, dy, dz, 0.001f, FLT_MAX * 2.0f, false, t, prim, st);
+                    {
+                        const unsigned int nv0 = STATS ? st.v[kStatNodes] : 0u;
+                        hit = query<STATS, SMALL>(P, P.cam.ox, P.cam.oy, P.cam.oz, dx, dy, dz, 0.001f, FLT_MAX * 2.0f, false, t, prim, st);
+                        walk_account<STATS>(st, nv0, 0);
+                    }
             }
             const unsigned hm = __ballot_sync(FULL_MASK, hit);
             if (hit) {
@@ -866,7 +882,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 6) trace_kernel
                 if (db > 0.f && fabsf(tr) * db < 4.6566e-10f && fabsf(tg) * db < 4.6566e-10f && fabsf(tb) * db < 4.6566e-10f) cont = false;
                 if (cont) {
                     float t2;
-                    survive = query<STATS, SMALL>(P, px, py, pz, sx, sy, sz, 0.001f, FLT_MAX * 2.0f, false, t2, prim2, st);
+                    {
+                        const unsigned int nv0 = STATS ? st.v[kStatNodes] : 0u;
+                        survive = query<STATS, SMALL>(P, px, py, pz, sx, sy, sz, 0.001f, FLT_MAX * 2.0f, false, t2, prim2, st);
+                        walk_account<STATS>(st, nv0, 1);
+                    }
                     if (survive) {
                         px = fmaf(t2, sx, px); py = fmaf(t2, sy, py); pz = fmaf(t2, sz, pz);
                         sd += 0x10000u;
@@ -945,7 +965,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 6) trace_kernel
                     stat_add<STATS>(st, kStatLightEvals);
                     float tt;
                     int pp;
-                    lit = !query<STATS, SMALL>(P, ox, oy, oz, dx, dy, dz, 0.001f, dist, true, tt, pp, st);
+                    {
+                        const unsigned int nv0 = STATS ? st.v[kStatNodes] : 0u;
+                        lit = !query<STATS, SMALL>(P, ox, oy, oz, dx, dy, dz, 0.001f, dist, true, tt, pp, st);
+                        walk_account<STATS>(st, nv0, 2);
+                    }
                 }
                 if (valid) W.lit[li][j] = lit ? 1 : 0;
                 if (SMALL && lit && P.soft) {
@@ -1039,8 +1063,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 6) trace_kernel
                                 if (nc == kCandOverflow) {
                                     float tt;
                                     int pp;
+                                    const unsigned int nv0 = STATS ? st.v[kStatNodes] : 0u;
                                     occA = traverse<STATS>(S, ox, oy, oz, dxa, dya, dza, 0.001f, dist, true, tt, pp, st);
                                     occB = traverse<STATS>(S, ox, oy, oz, dxb, dyb, dzb, 0.001f, dist, true, tt, pp, st);
+                                    walk_account<STATS>(st, nv0, 3);
                                 } else {
                                     stat_add<STATS>(st, kStatShadow, 2);
                                     for (uint32_t k = 0; k < nc; k++) {

@@ -38,7 +38,10 @@ enum StatIndex {
     kStatDepth20 = 18,
     kStatDepthMax = 19,
     kStatConeTests = 20,   // cone-vs-box / cone-vs-primitive tests of the soft-shadow candidate pass
-    kStatCount = 21
+    // SIMT use of the BVH walk per call site (FILL, EXTEND, SHADE-B, SHADE-C overflow): node visits summed over
+    // lanes, and 32 x the longest lane of each warp-level call; their ratio is the lane utilisation
+    kStatWalkLane0 = 21, kStatWalkWarp0 = 25,
+    kStatCount = 29
 };
 
 struct DevCamera {

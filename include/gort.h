@@ -161,6 +161,9 @@ typedef struct gort_stats {
     uint64_t specular_evals;  /* ... of which metallic > 0.5 (Blinn-Phong term) */
     uint64_t paths_depth_ge5, paths_depth_ge20, paths_depth_max; /* samples whose path reached that depth */
     uint64_t cone_tests;      /* cone-vs-box / cone-vs-primitive tests of the soft-shadow candidate pass */
+    /* SIMT use of the BVH walk per call site {FILL, EXTEND, SHADE hard shadows, SHADE soft shadows without
+     * candidates}: node visits summed over lanes / 32 x the longest lane of every warp-level call */
+    uint64_t walk_lane_visits[4], walk_warp_visits[4];
     double algorithmic_flops; /* SURVEY §8d per-operation costs applied to the counters above */
 } gort_stats;
 
