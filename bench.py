@@ -236,13 +236,13 @@ def main():
         """one frame, everything resident in HBM; returns number of kernels launched"""
         if world == 1:
             r.RenderDevice(W, H, frame.data_ptr())
-            return 2  # trace + resolve
+            return 3  # cull + trace + resolve (libgort kernels; memsets and the L2 flush are not counted)
         r.RenderShardDevice(W, H, slab.data_ptr())
         dist.all_gather_into_tensor(gathered, slab)
         if rank == 0:
             r.UnswizzleDevice(gathered.data_ptr(), world, W, H, frame.data_ptr())
-            return 3
-        return 2
+            return 4  # + unswizzle (the all-gather is NCCL's)
+        return 3
 
     def step_e2e():
         """public API with host buffers: scene upload (host flatten + BVH + H2D) and frame D2H inside the step"""
