@@ -45,6 +45,9 @@ WORKLOADS = {
     "c3": ("c3", 800, 600, 1, 8, 0, "two_red_cubes 800x600 1spp depth8 no-jitter hard-shadows (deterministic correctness config)"),
     "c4": ("c4", 1920, 1080, 64, 16, 0, "synthetic 100k random spheres 1920x1080 64spp depth16 3 lights"),
     "c5": ("c5", 3840, 2160, 256, 32, 2, "synthetic 1M-primitive sphere/box scene 3840x2160 256spp depth32 fog on"),
+    # the same 4K frame at 32 spp: 8x cheaper stand-in for scaling runs on a GPU-minute budget (less work per GPU,
+    # so its parallel efficiency is a lower bound for the 256-spp frame)
+    "c5_spp32": ("c5", 3840, 2160, 32, 32, 2, "synthetic 1M-primitive sphere/box scene 3840x2160 32spp depth32 fog on"),
 }
 
 
