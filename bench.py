@@ -191,6 +191,7 @@ def main():
     ap.add_argument("--impl", default="gort", choices=["gort", "reference"])
     ap.add_argument("--workload", default="c1_view", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="link", choices=["link", "nccl"], help="N > 1: how the frame is assembled on rank 0")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "gort" else args.warmup
     wl = WORKLOADS[args.workload]
@@ -228,6 +229,30 @@ def main():
     r.set_stream(stream.cuda_stream)
     r.UploadScene(flat)
 
+    # N > 1: assemble the frame over NVLink peer memory (frame link: every rank's resolve kernel stores its tiles
+    # straight into rank 0's frame, flag handshake, no collective); --gather nccl keeps the slab all-gather
+    link = None
+    if world > 1 and args.gather == "link":
+        try:
+            ht = torch.zeros(64, dtype=torch.uint8, device=dev)
+            ok = torch.ones(1, dtype=torch.int32, device=dev)
+            if rank == 0:
+                link, handle = r.LinkCreate(W, H, world)
+                ht.copy_(torch.frombuffer(bytearray(handle), dtype=torch.uint8))
+            dist.broadcast(ht, 0)
+            if rank != 0:
+                try:
+                    link = r.LinkOpen(bytes(ht.cpu().numpy().tobytes()), W, H, world, rank)
+                except G.GortError as e:
+                    sys.stderr.write("rank %d: frame link unavailable (%s): falling back to the NCCL gather\n" % (rank, e))
+                    ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                if link is not None:
+                    r.LinkClose(link)
+                link = None
+        except G.GortError as e:
+            raise SystemExit("frame link: %s" % e)
     slab_bytes = G.shard_slab_bytes(W, H, world)
     slab = torch.zeros(slab_bytes, dtype=torch.uint8, device=dev)
     gathered = torch.zeros(slab_bytes * world, dtype=torch.uint8, device=dev) if world > 1 else None
@@ -240,6 +265,9 @@ def main():
         if world == 1:
             r.RenderDevice(W, H, frame.data_ptr())
             return 3  # cull + trace + resolve (libgort kernels; memsets and the L2 flush are not counted)
+        if link is not None:
+            r.RenderLinked(W, H, link)
+            return 5  # (release | -) + cull + trace + (- | wait) + resolve + (wait | signal)
         r.RenderShardDevice(W, H, slab.data_ptr())
         dist.all_gather_into_tensor(gathered, slab)
         if rank == 0:
@@ -253,6 +281,13 @@ def main():
         if world == 1:
             img = r.Render(flat, W, H, out=host_frame.numpy().reshape(H, W, 4))
             return img
+        if link is not None:
+            r.RenderLinked(W, H, link)
+            if rank == 0:
+                r.LinkRead(link, W, H, out=host_frame.numpy().reshape(H, W, 4))
+            else:
+                torch.cuda.synchronize()
+            return host_frame
         r.RenderShardDevice(W, H, slab.data_ptr())
         dist.all_gather_into_tensor(gathered, slab)
         if rank == 0:
@@ -315,6 +350,20 @@ def main():
     e2e_s = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- N > 1: the link-assembled frame must be the frame the NCCL slab gather produces, bit for bit ----
+    frame_check = None
+    if link is not None:
+        r.RenderLinked(W, H, link)
+        if rank == 0:
+            r.LinkRead(link, W, H, out=host_frame.numpy().reshape(H, W, 4))
+        r.RenderShardDevice(W, H, slab.data_ptr())
+        dist.all_gather_into_tensor(gathered, slab)
+        if rank == 0:
+            r.UnswizzleDevice(gathered.data_ptr(), world, W, H, frame.data_ptr())
+            torch.cuda.synchronize()
+            frame_check = "identical" if bool((frame.cpu() == host_frame).all()) else "MISMATCH"
+        barrier()
+
     # ---- algorithmic FLOPs of one frame (device counters, separate untimed launch) -----------------
     r.SetCollectStats(True)
     st = r.RenderShardDevice(W, H, slab.data_ptr(), want_stats=True) if world > 1 else r.RenderDevice(W, H, frame.data_ptr(), want_stats=True)
@@ -346,7 +395,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "width": W, "height": H, "samples": spp, "max_depth": depth,
                        "camera_mode": "reference", "l2": "flushed between timed steps (256 MiB fill outside the events)",
-                       "sharding": "tile_id %% %d == rank, NCCL all-gather of RGBA8 slabs" % world if world > 1 else "single GPU",
+                       "sharding": ("tile_id %% %d == rank, " % world + ("tiles stored into rank 0's frame over NVLink peer memory (frame link)" if link is not None else "NCCL all-gather of RGBA8 slabs")) if world > 1 else "single GPU",
                        "rng": "philox4x32-10 seed 20240601"},
             "pixels_per_second": value * 1e6 / spp,
             "ray_segments_per_second": segs / (ms_per_step * 1e-3),
@@ -360,11 +409,16 @@ def main():
                          "peak_source": "measured live: dependent-FFMA microbenchmark (MEASURED_PEAKS.json has no fp32 entry; nominal %.1f)" % NOMINAL_FP32_TFLOPS,
                          "note": "divergent traversal + shading: bounded by FP32/INT issue, not HBM (scene fits L1/L2)"},
         }
+        if frame_check is not None:
+            line["config"]["frame_link_vs_nccl_gather"] = frame_check
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(wl, work)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
+        if link is not None:
+            torch.cuda.synchronize()
+            r.LinkClose(link)
         dist.destroy_process_group()
     return 0
 

@@ -41,6 +41,8 @@ EXPORTED_SYMBOLS = [
     "gort_host_scene_parse", "gort_host_scene_free", "gort_host_scene_counts", "gort_host_scene_get_sphere",
     "gort_host_scene_get_triangle", "gort_host_scene_get_material", "gort_host_scene_get_light", "gort_host_scene_get_camera",
     "gort_host_scene_bvh_validate",
+    "gort_link_create", "gort_link_open", "gort_link_close", "gort_link_frame", "gort_render_linked",
+    "gort_link_read", "gort_link_open_local",
 ]
 
 
@@ -150,6 +152,15 @@ def load_library() -> C.CDLL:
     L.gort_host_scene_get_light.argtypes = [vp, C.c_int32, dp]
     L.gort_host_scene_get_camera.argtypes = [vp, dp]
     L.gort_host_scene_bvh_validate.argtypes = [vp, C.POINTER(C.c_int64), C.c_char_p, C.c_size_t]
+    L.gort_link_create.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_char_p, C.POINTER(vp)]
+    L.gort_link_open.argtypes = [vp, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.gort_link_close.argtypes = [vp, vp]
+    L.gort_link_close.restype = None
+    L.gort_link_frame.argtypes = [vp]
+    L.gort_link_frame.restype = vp
+    L.gort_render_linked.argtypes = [vp, C.POINTER(RenderParams), vp, C.POINTER(Stats)]
+    L.gort_link_read.argtypes = [vp, vp, vp, C.c_size_t]
+    L.gort_link_open_local.argtypes = [vp, vp, C.c_int32, C.POINTER(vp)]
     _lib = L
     return L
 
@@ -451,6 +462,43 @@ class ParallelRenderer:
         st = Stats() if want_stats else None
         self._check(self._L.gort_render_shard_device(self._ctx, C.byref(p), C.c_void_p(d_slab_ptr), nbytes,
                                                      C.byref(st) if st is not None else None))
+        if st is not None:
+            self.lastStats = st
+        return st
+
+    # ---- frame link: one process per GPU, tiles stored straight into the owner's frame over NVLink peer memory ----
+    def LinkCreate(self, width: int, height: int, n_ranks: int):
+        """owner rank: -> (link, 64-byte handle to send to the peers)"""
+        buf = C.create_string_buffer(64)
+        link = C.c_void_p()
+        self._check(self._L.gort_link_create(self._ctx, width, height, n_ranks, buf, C.byref(link)))
+        return link, bytes(buf.raw)
+
+    def LinkOpen(self, handle: bytes, width: int, height: int, n_ranks: int, rank: int):
+        link = C.c_void_p()
+        self._check(self._L.gort_link_open(self._ctx, handle, width, height, n_ranks, rank, C.byref(link)))
+        return link
+
+    def LinkOpenLocal(self, owner_link, rank: int):
+        link = C.c_void_p()
+        self._check(self._L.gort_link_open_local(self._ctx, owner_link, rank, C.byref(link)))
+        return link
+
+    def LinkRead(self, link, width: int, height: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        img = out if out is not None else np.zeros((height, width, 4), dtype=np.uint8)
+        self._check(self._L.gort_link_read(self._ctx, link, img.ctypes.data_as(C.c_void_p), img.size))
+        return img
+
+    def LinkClose(self, link) -> None:
+        self._L.gort_link_close(self._ctx, link)
+
+    def LinkFrame(self, link) -> int:
+        return int(self._L.gort_link_frame(link))
+
+    def RenderLinked(self, width: int, height: int, link, want_stats: bool = False) -> Optional[Stats]:
+        p = self._params(width, height)
+        st = Stats() if want_stats else None
+        self._check(self._L.gort_render_linked(self._ctx, C.byref(p), link, C.byref(st) if st is not None else None))
         if st is not None:
             self.lastStats = st
         return st

@@ -72,6 +72,16 @@ struct gort_ctx {
     std::vector<int> last_local_tiles;  // per device
 };
 
+struct gort_link {
+    bool owner = false;
+    int32_t width = 0, height = 0, n_ranks = 1, rank = 0;
+    size_t frame_bytes = 0;
+    uint8_t* base = nullptr;       // owner: cudaMalloc; peer: cudaIpcOpenMemHandle mapping of the owner's allocation
+    unsigned int* ctrl = nullptr;  // {arrived, consumed} behind the frame
+    unsigned int frame_no = 0;
+    bool local_alias = false;      // test hook: peer link sharing the owner's pointer inside one process
+};
+
 namespace {
 
 int fail(gort_ctx* ctx, int code, const std::string& msg) {
@@ -295,8 +305,15 @@ int validate(gort_ctx* ctx, const gort_render_params* p) {
 // Enqueue one device's share of the frame: zero accumulators, trace, resolve into d.d_out.
 // eff_rank/eff_count: the tiles this device owns.  slab_mode: tile-major slab vs row-major frame.
 // out_override: write the resolved pixels there instead of d.d_out (device pointer on this device).
+// Optional stream-ordered hooks around the resolve of one device's share (frame link)
+struct ResolveHooks {
+    const unsigned int* wait_flag = nullptr;  // before resolve: wait until *wait_flag >= wait_target
+    unsigned int wait_target = 0;
+    unsigned int* signal_flag = nullptr;      // after resolve: fence.sys + atomicAdd(*signal_flag, 1)
+};
+
 int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_rank, int eff_count, int slab_mode, uint8_t* out_override,
-                   size_t slab_bytes) {
+                   size_t slab_bytes, const ResolveHooks* hooks = nullptr) {
     DeviceState& d = ctx->devs[di];
     CUDA_TRY(ctx, cudaSetDevice(d.dev));
     cudaStream_t st = stream_of(ctx, di);
@@ -388,7 +405,9 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     rp.accum = d.d_accum; rp.n_local_tiles = n_local; rp.shard_rank = eff_rank; rp.shard_count = eff_count;
     rp.tiles_x = tiles_x; rp.width = p->width; rp.height = p->height; rp.samples = p->samples;
     rp.out = out; rp.slab_mode = slab_mode;
+    if (hooks && hooks->wait_flag) CUDA_TRY(ctx, launch_link_wait(hooks->wait_flag, hooks->wait_target, st));
     CUDA_TRY(ctx, launch_resolve(rp, st));
+    if (hooks && hooks->signal_flag) CUDA_TRY(ctx, launch_link_signal(hooks->signal_flag, st));
     CUDA_TRY(ctx, cudaEventRecord(d.ev[2], st));
     return GORT_OK;
 }
@@ -756,6 +775,118 @@ int gort_render(gort_ctx* ctx, const gort_render_params* p, uint8_t* rgba_out, s
             stats_out->resolve_ms = g - stats_out->trace_ms;
         }
         stats_out->total_ms = now_ms() - t0;
+    }
+    return GORT_OK;
+}
+
+int gort_link_create(gort_ctx* ctx, int32_t width, int32_t height, int32_t n_ranks, uint8_t* handle_out, gort_link** out) {
+    if (!ctx || !out || !handle_out) return GORT_ERR_INVALID;
+    *out = nullptr;
+    if (width <= 0 || height <= 0 || n_ranks < 1 || n_ranks > 64) return fail(ctx, GORT_ERR_INVALID, "gort_link_create: bad arguments");
+    if (ctx->devs.size() != 1) return fail(ctx, GORT_ERR_INVALID, "a frame link joins single-device contexts (one process per GPU)");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->devs[0].dev));
+    gort_link* l = new gort_link();
+    l->owner = true; l->width = width; l->height = height; l->n_ranks = n_ranks; l->rank = 0;
+    l->frame_bytes = (size_t)width * height * 4;
+    const size_t total = ((l->frame_bytes + 255) / 256) * 256 + 256;  // frame + control block {arrived, consumed}
+    cudaError_t e = cudaMalloc(&l->base, total);
+    if (e == cudaSuccess) e = cudaMemset(l->base, 0, total);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, l->base);
+    if (e != cudaSuccess) {
+        if (l->base) cudaFree(l->base);
+        delete l;
+        cudaGetLastError();
+        return fail(ctx, GORT_ERR_CUDA, std::string("gort_link_create: ") + cudaGetErrorString(e));
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == GORT_LINK_HANDLE_BYTES, "IPC handle size");
+    memcpy(handle_out, &h, sizeof(h));
+    l->ctrl = reinterpret_cast<unsigned int*>(l->base + ((l->frame_bytes + 255) / 256) * 256);
+    *out = l;
+    return GORT_OK;
+}
+
+int gort_link_open(gort_ctx* ctx, const uint8_t* handle, int32_t width, int32_t height, int32_t n_ranks, int32_t rank, gort_link** out) {
+    if (!ctx || !out || !handle) return GORT_ERR_INVALID;
+    *out = nullptr;
+    if (width <= 0 || height <= 0 || n_ranks < 2 || rank < 1 || rank >= n_ranks) return fail(ctx, GORT_ERR_INVALID, "gort_link_open: bad arguments");
+    if (ctx->devs.size() != 1) return fail(ctx, GORT_ERR_INVALID, "a frame link joins single-device contexts (one process per GPU)");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->devs[0].dev));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* base = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, GORT_ERR_CUDA, std::string("gort_link_open: ") + cudaGetErrorString(e));
+    }
+    gort_link* l = new gort_link();
+    l->owner = false; l->width = width; l->height = height; l->n_ranks = n_ranks; l->rank = rank;
+    l->frame_bytes = (size_t)width * height * 4;
+    l->base = (uint8_t*)base;
+    l->ctrl = reinterpret_cast<unsigned int*>(l->base + ((l->frame_bytes + 255) / 256) * 256);
+    *out = l;
+    return GORT_OK;
+}
+
+int gort_link_open_local(gort_ctx* ctx, const gort_link* owner, int32_t rank, gort_link** out) {
+    if (!ctx || !owner || !out || !owner->owner || rank < 1 || rank >= owner->n_ranks) return GORT_ERR_INVALID;
+    gort_link* l = new gort_link(*owner);
+    l->owner = false; l->local_alias = true; l->rank = rank; l->frame_no = 0;
+    *out = l;
+    return GORT_OK;
+}
+
+int gort_link_read(gort_ctx* ctx, gort_link* l, uint8_t* rgba_out, size_t rgba_bytes) {
+    if (!ctx || !l || !rgba_out) return GORT_ERR_INVALID;
+    if (!l->owner || rgba_bytes != l->frame_bytes) return fail(ctx, GORT_ERR_INVALID, "gort_link_read: owner link and width*height*4 bytes expected");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->devs[0].dev));
+    cudaStream_t st = stream_of(ctx, 0);
+    CUDA_TRY(ctx, cudaMemcpyAsync(rgba_out, l->base, rgba_bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return GORT_OK;
+}
+
+void gort_link_close(gort_ctx* ctx, gort_link* l) {
+    if (!l) return;
+    if (ctx && !ctx->devs.empty()) {
+        cudaSetDevice(ctx->devs[0].dev);
+        cudaStreamSynchronize(stream_of(ctx, 0));
+    }
+    if (l->base && !l->local_alias) {
+        if (l->owner) cudaFree(l->base);
+        else cudaIpcCloseMemHandle(l->base);
+    }
+    cudaGetLastError();
+    delete l;
+}
+
+void* gort_link_frame(const gort_link* l) { return l ? (void*)l->base : nullptr; }
+
+int gort_render_linked(gort_ctx* ctx, const gort_render_params* p, gort_link* l, gort_stats* stats_out) {
+    const double t0 = now_ms();
+    if (int rc = validate(ctx, p)) return rc;
+    if (!l) return fail(ctx, GORT_ERR_INVALID, "link is NULL");
+    if (p->width != l->width || p->height != l->height) return fail(ctx, GORT_ERR_INVALID, "gort_render_linked: size differs from the link's frame");
+    if (ctx->devs.size() != 1) return fail(ctx, GORT_ERR_INVALID, "a frame link joins single-device contexts (one process per GPU)");
+    const unsigned int k = ++l->frame_no;  // 1, 2, ...
+    ctx->last_w = p->width; ctx->last_h = p->height; ctx->last_samples = p->samples; ctx->last_rank = l->rank; ctx->last_count = l->n_ranks;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->devs[0].dev));
+    cudaStream_t st = stream_of(ctx, 0);
+    ResolveHooks hk;
+    if (l->owner) {
+        // everything this stream did with frame k-1 is done when this runs: the peers may overwrite it
+        CUDA_TRY(ctx, launch_link_store(l->ctrl + 1, k - 1, st));
+        if (int rc = enqueue_device(ctx, 0, p, 0, l->n_ranks, 0, l->base, 0, nullptr)) return rc;
+        if (l->n_ranks > 1) CUDA_TRY(ctx, launch_link_wait(l->ctrl + 0, k * (unsigned int)(l->n_ranks - 1), st));
+    } else {
+        hk.wait_flag = l->ctrl + 1; hk.wait_target = k - 1;
+        hk.signal_flag = l->ctrl + 0;
+        if (int rc = enqueue_device(ctx, 0, p, l->rank, l->n_ranks, 0, l->base, 0, &hk)) return rc;
+    }
+    if (stats_out) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        return collect_stats(ctx, p, stats_out, t0, 1);
     }
     return GORT_OK;
 }

@@ -1447,6 +1447,49 @@ cudaError_t launch_unswizzle(const uint8_t* slabs, int shard_count, int width, i
 }
 
 // ---------------------------------------------------------------------------------------------
+// frame link: every rank's resolve_kernel stores its tiles straight into the owner's row-major frame through
+// a peer mapping (NVLink), so the frame is assembled without a collective and without an un-swizzle pass.
+// Completion and reuse are ordered by two counters in the owner's memory:
+//   arrived  += 1 by every peer after its tiles of frame k are written (fence.sys first);
+//              the owner waits for k * (ranks - 1) before anything that reads the frame
+//   consumed  = k - 1 stored by the owner when it starts frame k (its stream has consumed frame k - 1 by then);
+//              a peer waits for it before it overwrites the frame with its tiles of frame k
+// Each kernel is one thread; a waiting kernel spins on a flag written from ANOTHER GPU (never on a kernel of
+// its own GPU), with back-off.
+// ---------------------------------------------------------------------------------------------
+__global__ void link_signal_kernel(unsigned int* flag) {
+    __threadfence_system();
+    atomicAdd_system(flag, 1u);
+}
+__global__ void link_store_kernel(unsigned int* flag, unsigned int value) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+    __threadfence_system();
+}
+__global__ void link_wait_kernel(const unsigned int* flag, unsigned int target) {
+    unsigned int ns = 100;
+    for (;;) {
+        unsigned int v;
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int)(v - target) >= 0) break;
+        __nanosleep(ns);
+        if (ns < 2000) ns *= 2;
+    }
+    __threadfence_system();
+}
+cudaError_t launch_link_signal(unsigned int* flag, cudaStream_t stream) {
+    link_signal_kernel<<<1, 1, 0, stream>>>(flag);
+    return cudaGetLastError();
+}
+cudaError_t launch_link_store(unsigned int* flag, unsigned int value, cudaStream_t stream) {
+    link_store_kernel<<<1, 1, 0, stream>>>(flag, value);
+    return cudaGetLastError();
+}
+cudaError_t launch_link_wait(const unsigned int* flag, unsigned int target, cudaStream_t stream) {
+    link_wait_kernel<<<1, 1, 0, stream>>>(flag, target);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // test hook: hitWorld for explicit rays
 // ---------------------------------------------------------------------------------------------
 __global__ void trace_rays_kernel(const SceneView S, int n, const float* __restrict__ o, const float* __restrict__ d, float tmin,

@@ -216,6 +216,29 @@ int gort_render_shard_device(gort_ctx* ctx, const gort_render_params* params, vo
                              gort_stats* stats_out);
 int gort_unswizzle_device(gort_ctx* ctx, const void* d_slabs, int32_t shard_count, int32_t width, int32_t height,
                           void* d_rgba, size_t rgba_bytes);
+/* ---- frame link: one process per GPU, frame assembled over NVLink peer memory (no collective) ----
+ * The reference's distributed stub ships pixel rectangles as JSON over HTTP (internal/distributed/
+ * distributed_renderer.go:29-61); here the owner rank allocates the row-major RGBA8 frame, every other rank maps
+ * it (CUDA IPC) and its resolve kernel stores its tiles straight into it; two counters in the owner's memory
+ * order completion and reuse.  Every rank calls gort_render_linked once per frame, with the same params.
+ *   owner:  gort_link_create -> send `handle` to the peers -> per frame gort_render_linked; when it returns,
+ *           the work that waits for all ranks' tiles is enqueued on the ctx stream, and gort_link_frame() may be
+ *           read by anything enqueued after it.  The next gort_render_linked releases the frame for reuse.
+ *   peer:   gort_link_open(handle) -> per frame gort_render_linked. */
+#define GORT_LINK_HANDLE_BYTES 64
+typedef struct gort_link gort_link;
+int gort_link_create(gort_ctx* ctx, int32_t width, int32_t height, int32_t n_ranks, uint8_t* handle_out /* [64] */, gort_link** out);
+int gort_link_open(gort_ctx* ctx, const uint8_t* handle /* [64] */, int32_t width, int32_t height, int32_t n_ranks, int32_t rank,
+                   gort_link** out);
+void gort_link_close(gort_ctx* ctx, gort_link* link);
+void* gort_link_frame(const gort_link* link); /* device pointer of the frame in this process (owner: its own memory) */
+int gort_render_linked(gort_ctx* ctx, const gort_render_params* params, gort_link* link, gort_stats* stats_out);
+/* owner: copy the assembled frame to host memory (stream-ordered after gort_render_linked, then synchronised) */
+int gort_link_read(gort_ctx* ctx, gort_link* link, uint8_t* rgba_out, size_t rgba_bytes);
+/* test hook: a peer link onto an owner link of the SAME process (CUDA IPC cannot open a handle in the process that
+ * made it); lets a single-GPU box exercise the protocol with the ranks run one after the other, peers first. */
+int gort_link_open_local(gort_ctx* ctx, const gort_link* owner, int32_t rank, gort_link** out);
+
 /* Sample-averaged linear radiance (before tone-map) of the last render on this ctx, float64 RGB
  * [height][width][3] on the host; tiles not owned by the shard are left untouched.  Test hook. */
 int gort_read_radiance(gort_ctx* ctx, double* radiance_out, size_t bytes);

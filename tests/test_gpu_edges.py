@@ -142,3 +142,28 @@ def test_error_codes(gort, renderer):
     r2.close()
     with pytest.raises(gort.GortError):
         gort.LoadFromFile("/nonexistent/scene.json")
+
+
+def test_frame_link_assembles_the_frame_in_the_owners_memory(gort, renderer):
+    """Frame link (include/gort.h): every rank's resolve kernel stores its tiles straight into the owner's row-major
+    frame.  On this single-GPU box the three ranks are three contexts of one process (gort_link_open_local stands in
+    for the CUDA-IPC mapping) run one after the other, peers first, so no kernel ever waits for another."""
+    W, H, n = 200, 150, 3
+    sc = gort.SceneFromDict(Cm.c2_view(), 1)
+    renderer.SetSamples(4); renderer.SetMaxDepth(10); renderer.SetSeed(17); renderer.SetShard(0, 1)
+    full = renderer.Render(sc, W, H).copy()
+    ranks = [gort.NewParallelRenderer(1) for _ in range(n)]
+    for r in ranks:
+        r.SetSamples(4); r.SetMaxDepth(10); r.SetSeed(17)
+        r.UploadScene(sc)
+    link0, handle = ranks[0].LinkCreate(W, H, n)
+    assert len(handle) == 64
+    links = [link0] + [ranks[k].LinkOpenLocal(link0, k) for k in range(1, n)]
+    for k in (2, 1, 0):  # peers first: their tiles and arrival counts are in place when the owner waits for them
+        st = ranks[k].RenderLinked(W, H, links[k], want_stats=True)
+        assert st.n_tiles == len(gort.tiles_of_shard(W, H, k, n))
+    img = ranks[0].LinkRead(link0, W, H)
+    assert np.array_equal(img, full)
+    for k in (2, 1, 0):
+        ranks[k].LinkClose(links[k])
+        ranks[k].close()
