@@ -65,6 +65,7 @@ struct gort_ctx {
     HostScene scene;
     FlatBvh bvh;
     bool has_scene = false;
+    bool peer_direct = false;  // multi-device ctx: all devices can store into the lead device's memory
     std::string err;
     double upload_ms = 0, bvh_ms = 0;
     // last render (for gort_read_radiance)
@@ -524,18 +525,25 @@ int gort_create(const int* device_ids, int n_devices, gort_ctx** out) {
         if (e == cudaSuccess && getenv("GORT_DEBUG_TIMES")) e = cudaMalloc(&d.d_debug, (1 + 8 * 148 * 64) * sizeof(unsigned long long));
         if (e != cudaSuccess) return bail(GORT_ERR_CUDA, std::string("device init: ") + cudaGetErrorString(e));
     }
-    if (n_devices > 1) {  // direct NVLink copies for the slab gather
+    if (n_devices > 1) {  // NVLink peer access: the other devices store their tiles straight into the lead's frame
+        ctx->peer_direct = true;
         for (int i = 1; i < n_devices; i++) {
-            int can = 0;
+            int can = 0, can_back = 0;
             cudaDeviceCanAccessPeer(&can, ctx->devs[0].dev, ctx->devs[i].dev);
+            cudaDeviceCanAccessPeer(&can_back, ctx->devs[i].dev, ctx->devs[0].dev);
             if (can) {
                 cudaSetDevice(ctx->devs[0].dev);
                 cudaDeviceEnablePeerAccess(ctx->devs[i].dev, 0);
-                cudaSetDevice(ctx->devs[i].dev);
-                cudaDeviceEnablePeerAccess(ctx->devs[0].dev, 0);
-                cudaGetLastError();
             }
+            if (can_back) {
+                cudaSetDevice(ctx->devs[i].dev);
+                cudaError_t e = cudaDeviceEnablePeerAccess(ctx->devs[0].dev, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can_back = 0;
+            }
+            cudaGetLastError();
+            if (!can_back) ctx->peer_direct = false;  // fall back to slabs + peer copies + un-swizzle
         }
+        if (getenv("GORT_NO_PEER_DIRECT")) ctx->peer_direct = false;
     }
     *out = ctx;
     return GORT_OK;
@@ -666,6 +674,15 @@ static int render_frame_device(gort_ctx* ctx, const gort_render_params* p, uint8
         if (sc != 1) return fail(ctx, GORT_ERR_INVALID, "a multi-device ctx renders whole frames (shard_count must be 1)");
         const size_t slab = gort_shard_slab_bytes(p->width, p->height, nd);
         DeviceState& lead = ctx->devs[0];
+        if (ctx->peer_direct) {
+            // every device resolves its interleaved tiles into the lead's row-major frame (peer stores over NVLink)
+            for (int i = 0; i < nd; i++)
+                if (int rc = enqueue_device(ctx, i, p, i, nd, 0, d_rgba, 0)) return rc;
+            CUDA_TRY(ctx, cudaSetDevice(lead.dev));
+            cudaStream_t st0 = stream_of(ctx, 0);
+            for (int i = 1; i < nd; i++) CUDA_TRY(ctx, cudaStreamWaitEvent(st0, ctx->devs[i].ev[2], 0));
+            CUDA_TRY(ctx, cudaEventRecord(lead.ev[3], st0));
+        } else {
         CUDA_TRY(ctx, cudaSetDevice(lead.dev));
         if (int rc = ensure(ctx, lead.d_gather, lead.gather_bytes, slab * nd)) return rc;
         for (int i = 0; i < nd; i++) {
@@ -680,6 +697,7 @@ static int render_frame_device(gort_ctx* ctx, const gort_render_params* p, uint8
         }
         CUDA_TRY(ctx, launch_unswizzle(lead.d_gather, nd, p->width, p->height, d_rgba, st0));
         CUDA_TRY(ctx, cudaEventRecord(lead.ev[3], st0));
+        }
     }
     if (stats_out || sync) {
         CUDA_TRY(ctx, cudaSetDevice(ctx->devs[0].dev));

@@ -167,3 +167,30 @@ def test_frame_link_assembles_the_frame_in_the_owners_memory(gort, renderer):
     for k in (2, 1, 0):
         ranks[k].LinkClose(links[k])
         ranks[k].close()
+
+
+def test_multi_device_context_matches_single_device(gort, renderer):
+    """gort_create with several devices (single process): tiles interleaved over the GPUs, every device resolving
+    straight into the lead device's frame over NVLink peer access (or slabs + peer copies + un-swizzle when
+    GORT_NO_PEER_DIRECT is set) — bit-identical to one GPU.  Needs >= 2 GPUs."""
+    import os
+    n = gort.load_library().gort_device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    W, H = 330, 250
+    sc = gort.SceneFromDict(Cm.c1_view())
+    renderer.SetSamples(8); renderer.SetMaxDepth(50); renderer.SetSeed(23); renderer.SetShard(0, 1)
+    full = renderer.Render(sc, W, H).copy()
+    for nd in sorted({2, min(n, 8)}):
+        for no_direct in (False, True):
+            if no_direct:
+                os.environ["GORT_NO_PEER_DIRECT"] = "1"
+            try:
+                r = gort.NewParallelRenderer(nd, devices=list(range(nd)))
+            finally:
+                os.environ.pop("GORT_NO_PEER_DIRECT", None)
+            r.SetSamples(8); r.SetMaxDepth(50); r.SetSeed(23)
+            img = r.Render(sc, W, H)
+            assert r.lastStats.n_devices == nd
+            assert np.array_equal(img, full), (nd, no_direct)
+            r.close()
