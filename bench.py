@@ -389,6 +389,16 @@ def main():
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
         except (OSError, ValueError):
             pass
+        # the HBM side of the roofline, to show it is not the bound: measured DRAM traffic of the kernel over its time
+        hbm = None
+        try:
+            peak_gbs = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+            peak_src = "MEASURED_PEAKS.json"
+        except (OSError, ValueError, KeyError):
+            peak_gbs, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        if traffic:
+            gbs = traffic / (tr * 1e-3) / 1e9
+            hbm = {"achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs, "peak_source": peak_src}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -407,7 +417,8 @@ def main():
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
                          "traffic": traffic, "kernel": "trace_kernel", "kernel_ms": tr, "algorithmic_flops_per_launch": st.algorithmic_flops,
                          "peak_source": "measured live: dependent-FFMA microbenchmark (MEASURED_PEAKS.json has no fp32 entry; nominal %.1f)" % NOMINAL_FP32_TFLOPS,
-                         "note": "divergent traversal + shading: bounded by FP32/INT issue, not HBM (scene fits L1/L2)"},
+                         "note": "divergent traversal + shading: bounded by FP32/INT issue, not HBM (scene fits L1/L2)",
+                         "hbm": hbm},
         }
         if frame_check is not None:
             line["config"]["frame_link_vs_nccl_gather"] = frame_check
