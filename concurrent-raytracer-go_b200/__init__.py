@@ -42,7 +42,7 @@ EXPORTED_SYMBOLS = [
     "gort_host_scene_get_triangle", "gort_host_scene_get_material", "gort_host_scene_get_light", "gort_host_scene_get_camera",
     "gort_host_scene_bvh_validate",
     "gort_link_create", "gort_link_open", "gort_link_close", "gort_link_frame", "gort_render_linked",
-    "gort_link_read", "gort_link_open_local",
+    "gort_link_read", "gort_link_open_local", "gort_scene_render_hints",
 ]
 
 
@@ -160,6 +160,7 @@ def load_library() -> C.CDLL:
     L.gort_link_frame.restype = vp
     L.gort_render_linked.argtypes = [vp, C.POINTER(RenderParams), vp, C.POINTER(Stats)]
     L.gort_link_read.argtypes = [vp, vp, vp, C.c_size_t]
+    L.gort_scene_render_hints.argtypes = [vp, ip]
     L.gort_link_open_local.argtypes = [vp, vp, C.c_int32, C.POINTER(vp)]
     _lib = L
     return L
@@ -511,6 +512,13 @@ class ParallelRenderer:
         out = np.zeros((height, width, 3), dtype=np.float64)
         self._check(self._L.gort_read_radiance(self._ctx, out.ctypes.data_as(C.POINTER(C.c_double)), out.nbytes))
         return out
+
+    def SceneRenderHints(self) -> dict:
+        """The uploaded scene's own "renderer" block (extension; None where absent)."""
+        h = (C.c_int32 * 5)()
+        self._check(self._L.gort_scene_render_hints(self._ctx, h))
+        keys = ("samples", "maxDepth", "antiAliasing", "recursiveReflections", "softShadows")
+        return {k: (None if v < 0 else (int(v) if i < 2 else bool(v))) for i, (k, v) in enumerate(zip(keys, h))}
 
     def SceneCounts(self) -> dict:
         v = [C.c_int32() for _ in range(5)]

@@ -5,7 +5,8 @@
 //
 //   raytracer <scene_file> <output_file> <width> <height>
 // Additive flags (before the positionals, like Go's flag package): -gpus N, -samples N, -max-depth N, -seed N,
-// -camera-mode reference|lookat, -prisms, -fog, -readme-json FILE (README.md:50-71 schema).
+// -camera-mode reference|lookat, -prisms, -fog, -scene-settings (use the scene's own "renderer" block),
+// -readme-json FILE (README.md:50-71 schema).
 #include <sys/stat.h>
 
 #include <chrono>
@@ -26,6 +27,8 @@ int main(int argc, char** argv) {
     int gpus = 0, samples = 100, max_depth = 50, camera_mode = GORT_CAMERA_REFERENCE;
     unsigned long long seed = (unsigned long long)std::chrono::system_clock::now().time_since_epoch().count();  // time-seeded like random.go:8-10
     uint32_t options = 0;
+    bool scene_settings = false, samples_given = false, depth_given = false;
+    int aa = 1, rr = 1, ss = 1;  // NewParallelRenderer defaults, renderer.go:54-65
     std::string readme_json;
     std::vector<std::string> args;
     for (int i = 1; i < argc; i++) {
@@ -35,8 +38,9 @@ int main(int argc, char** argv) {
             return argv[++i];
         };
         if (a == "-gpus" || a == "--gpus") gpus = atoi(val("-gpus"));
-        else if (a == "-samples" || a == "--samples") samples = atoi(val("-samples"));
-        else if (a == "-max-depth" || a == "--max-depth") max_depth = atoi(val("-max-depth"));
+        else if (a == "-samples" || a == "--samples") { samples = atoi(val("-samples")); samples_given = true; }
+        else if (a == "-max-depth" || a == "--max-depth") { max_depth = atoi(val("-max-depth")); depth_given = true; }
+        else if (a == "-scene-settings" || a == "--scene-settings") scene_settings = true;
         else if (a == "-seed" || a == "--seed") seed = strtoull(val("-seed"), nullptr, 10);
         else if (a == "-camera-mode" || a == "--camera-mode") camera_mode = std::string(val("-camera-mode")) == "lookat" ? GORT_CAMERA_LOOKAT : GORT_CAMERA_REFERENCE;
         else if (a == "-prisms" || a == "--prisms") options |= 1u;
@@ -76,13 +80,23 @@ int main(int argc, char** argv) {
     gort_scene_counts(ctx, &n_sph, &n_tri, &n_mat, &n_light, &n_hit);
     printf("Created %d hittables total\n", n_hit);  // scene.go:88
 
+    if (scene_settings) {  // extension: the scene's "renderer" block (README.md:285-291); explicit flags win
+        int32_t h[5];
+        if (gort_scene_render_hints(ctx, h) == GORT_OK) {
+            if (h[0] > 0 && !samples_given) samples = h[0];
+            if (h[1] >= 0 && !depth_given) max_depth = h[1];
+            if (h[2] >= 0) aa = h[2];
+            if (h[3] >= 0) rr = h[3];
+            if (h[4] >= 0) ss = h[4];
+        }
+    }
     printf("Rendering at %ldx%ld resolution...\n", width, height);
     gort_render_params p;
     memset(&p, 0, sizeof(p));
     p.abi_version = GORT_ABI_VERSION;
     p.width = (int32_t)width; p.height = (int32_t)height;
     p.samples = samples; p.max_depth = max_depth;
-    p.anti_aliasing = 1; p.recursive_reflections = 1; p.soft_shadows = 1;  // NewParallelRenderer defaults, renderer.go:54-65
+    p.anti_aliasing = aa; p.recursive_reflections = rr; p.soft_shadows = ss;
     p.camera_mode = camera_mode; p.shard_rank = 0; p.shard_count = 1; p.seed = seed;
     std::vector<uint8_t> pix((size_t)width * height * 4);
     gort_stats st;

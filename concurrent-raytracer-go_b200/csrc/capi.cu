@@ -634,6 +634,13 @@ int gort_scene_get_material(const gort_ctx* ctx, int32_t i, int32_t* type, doubl
     return GORT_OK;
 }
 
+int gort_scene_render_hints(const gort_ctx* ctx, int32_t* hints5) {
+    if (!ctx || !ctx->has_scene) return GORT_ERR_NO_SCENE;
+    if (!hints5) return GORT_ERR_INVALID;
+    memcpy(hints5, ctx->scene.render_hints, 5 * sizeof(int32_t));
+    return GORT_OK;
+}
+
 size_t gort_shard_slab_bytes(int32_t width, int32_t height, int32_t shard_count) {
     if (width <= 0 || height <= 0) return 0;
     if (shard_count <= 0) shard_count = 1;

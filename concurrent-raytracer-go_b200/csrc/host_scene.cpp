@@ -250,6 +250,17 @@ std::string scene_from_json(const char* text, size_t len, uint32_t options, Host
         }
     }
 
+    {   // always parsed, never applied by the library: hosts that want the scene's own settings ask for them
+        const json::Value* rb = field(root.get(), "renderer");
+        if (rb) {
+            const json::Value* v;
+            if ((v = field(rb, "samples")) && v->kind == json::Value::Number) out.render_hints[0] = (int32_t)v->num;
+            if ((v = field(rb, "maxDepth")) && v->kind == json::Value::Number) out.render_hints[1] = (int32_t)v->num;
+            const char* flags[3] = {"antiAliasing", "recursiveReflections", "softShadows"};
+            for (int k = 0; k < 3; k++)
+                if ((v = field(rb, flags[k])) && v->kind == json::Value::Bool) out.render_hints[2 + k] = v->b ? 1 : 0;
+        }
+    }
     if (options & 2u) {
         const json::Value* fog = field(root.get(), "fog");
         const json::Value* en = field(fog, "enabled");

@@ -44,6 +44,9 @@ struct HostScene {
     int32_t n_hittables = 0;  // len(scene.GetHittables()): spheres + meshes
     int32_t fog_enabled = 0;
     double fog_density = 0, fog_color[3] = {0, 0, 0};
+    // the scene's own "renderer" block (README.md:285-291; ignored by the reference loader):
+    // {samples, maxDepth, antiAliasing, recursiveReflections, softShadows}, -1 = key absent
+    int32_t render_hints[5] = {-1, -1, -1, -1, -1};
 
     int32_t next_order() const { return (int32_t)(spheres.size() + tris.size()); }
 };

@@ -195,6 +195,10 @@ int gort_scene_counts(const gort_ctx* ctx, int32_t* n_spheres, int32_t* n_triang
                       int32_t* n_lights, int32_t* n_hittables);
 int gort_scene_get_triangle(const gort_ctx* ctx, int32_t order_index_among_triangles, double* v9, int32_t* material);
 int gort_scene_get_material(const gort_ctx* ctx, int32_t index, int32_t* type, double* color3_rough_metal_spec_ior7);
+/* Extension: the loaded scene's own "renderer" block (README.md:285-291; the reference's loader drops it, scene.go:12-16):
+ * hints5 = {samples, maxDepth, antiAliasing, recursiveReflections, softShadows}, -1 where the key is absent (and for
+ * scenes uploaded as gort_scene_desc).  The library never applies them; a host may copy them into gort_render_params. */
+int gort_scene_render_hints(const gort_ctx* ctx, int32_t* hints5);
 
 /* ---- render (replaces the body of ParallelRenderer.Render, renderer.go:67-126) ------------ */
 /* rgba_out: caller-owned host buffer of width*height*4 bytes, row-major, row y=0 first ==

@@ -75,3 +75,17 @@ def test_benchmark_cli_sweeps_and_reports(tmp_path):
         assert res["rays_per_second"] == pytest.approx(res["pixels_per_second"] * res["samples"], rel=1e-3)
         assert res["duration"] > 0 and res["frames"] >= 1
     assert rep["summary"]["total_benchmarks"] == 2
+
+
+@pytest.mark.gpu
+def test_raytracer_scene_settings_extension(gort, tmp_path):
+    """-scene-settings uses the scene's own "renderer" block (samples 200, maxDepth 20 in the shipped cube scene)."""
+    scene = os.path.join(Cm.SCENES, "final_silver_prism_purple_cube_.json")
+    out = tmp_path / "o.png"
+    r = run([os.path.join(BIN, "raytracer"), "-scene-settings", "-seed", "1", scene, str(out), "64", "48"])
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Samples per pixel: 200" in r.stdout and "Max depth: 20" in r.stdout
+    rr = gort.NewParallelRenderer(1)
+    rr.UploadScene(gort.LoadFromFile(scene))
+    assert rr.SceneRenderHints() == {"samples": 200, "maxDepth": 20, "antiAliasing": True, "recursiveReflections": True, "softShadows": True}
+    rr.close()

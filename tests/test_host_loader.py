@@ -103,3 +103,15 @@ def test_flat_scene_round_trip_types(gort):
     flat = hs.to_flat()
     assert flat.desc.n_triangles == 40 and flat.desc.n_materials == 4 and flat.desc.n_lights == 3
     assert flat.desc.abi_version == gort.ABI_VERSION
+
+
+def test_renderer_block_is_parsed_but_never_applied(gort):
+    """README.md:285-291 advertises a per-scene "renderer" block that the reference loader drops (scene.go:12-16).
+    The loader keeps it as hints for hosts that opt in (raytracer -scene-settings); nothing else changes."""
+    import json
+    d = Cm.load_scene_dict("final_silver_prism_purple_cube_.json")
+    assert d["renderer"]["samples"] == 200 and d["renderer"]["maxDepth"] == 20
+    a = gort.HostScene(json.dumps(d))
+    del d["renderer"]
+    b = gort.HostScene(json.dumps(d))
+    assert a.counts() == b.counts()
