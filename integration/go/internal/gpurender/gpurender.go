@@ -71,6 +71,15 @@ type Context struct{ ctx *C.gort_ctx }
 
 func lastErr(ctx *C.gort_ctx) string { return C.GoString(C.gort_last_error(ctx)) }
 
+// DeviceCount is the number of usable CUDA devices (0 when there is none).
+func DeviceCount() int {
+	n := int(C.gort_device_count())
+	if n < 0 {
+		return 0
+	}
+	return n
+}
+
 // New opens nGPUs devices (0..n-1).  There is no CPU fallback: without a CUDA device this fails.
 func New(nGPUs int) (*Context, error) {
 	var c *C.gort_ctx
