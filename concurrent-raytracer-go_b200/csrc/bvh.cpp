@@ -7,7 +7,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <atomic>
 #include <queue>
+#include <thread>
 
 namespace gort {
 namespace {
@@ -51,12 +53,22 @@ struct Box {
 constexpr int kBins = 16;
 static double kNodeCost = 1.0;  // GORT_BVH_NODE_COST (in primitive tests)
 
+// A subtree whose construction was deferred to a worker thread: the slot of the parent that will point to it
+struct Deferred {
+    int parent, which;  // nodes[parent].left (0) / .right (1) receives the subtree's root
+    int first, count, depth;
+};
+
 struct Builder {
-    std::vector<BPrim> prims;
+    std::vector<BPrim>* prims_ptr = nullptr;  // shared permutation array; builders work on disjoint ranges
     std::vector<BNode> nodes;
     int max_depth = 0;
+    // top-level builder only: subtrees with <= defer_below primitives are not built but recorded here
+    int defer_below = 0;
+    std::vector<Deferred> deferred;
 
     int make_leaf(int first, int count, int depth, const Box& b) {
+        std::vector<BPrim>& prims = *prims_ptr;
         BNode n;
         memcpy(n.lo, b.lo, sizeof(n.lo));
         memcpy(n.hi, b.hi, sizeof(n.hi));
@@ -70,6 +82,7 @@ struct Builder {
     }
 
     int build(int first, int count, int depth) {
+        std::vector<BPrim>& prims = *prims_ptr;
         Box b, cb;
         b.reset();
         cb.reset();
@@ -173,8 +186,12 @@ struct Builder {
         n.count = count;
         nodes.push_back(n);
         int self = (int)nodes.size() - 1;
-        int l = build(first, split - first, depth + 1);
-        int r = build(split, first + count - split, depth + 1);
+        const int lc = split - first, rc = first + count - split;
+        int l = -2, r = -2;
+        if (defer_below > 0 && lc <= defer_below && lc > kMaxLeafPrims) deferred.push_back(Deferred{self, 0, first, lc, depth + 1});
+        else l = build(first, lc, depth + 1);
+        if (defer_below > 0 && rc <= defer_below && rc > kMaxLeafPrims) deferred.push_back(Deferred{self, 1, split, rc, depth + 1});
+        else r = build(split, rc, depth + 1);
         nodes[self].left = l;
         nodes[self].right = r;
         return self;
@@ -208,7 +225,8 @@ void build_bvh(const HostScene& scene, FlatBvh& out) {
     out = FlatBvh();
     Builder B;
     const int nS = (int)scene.spheres.size(), nT = (int)scene.tris.size();
-    B.prims.reserve((size_t)nS + nT);
+    std::vector<BPrim> prims_storage;
+    prims_storage.reserve((size_t)nS + nT);
     Box world;
     world.reset();
     for (int i = 0; i < nS; i++) {
@@ -222,7 +240,7 @@ void build_bvh(const HostScene& scene, FlatBvh& out) {
         }
         p.type = 0;
         p.idx = i;
-        B.prims.push_back(p);
+        prims_storage.push_back(p);
         world.grow(p.lo, p.hi);
     }
     for (int i = 0; i < nT; i++) {
@@ -235,14 +253,53 @@ void build_bvh(const HostScene& scene, FlatBvh& out) {
         }
         p.type = 1;
         p.idx = i;
-        B.prims.push_back(p);
+        prims_storage.push_back(p);
         world.grow(p.lo, p.hi);
     }
     const int n = nS + nT;
     if (n == 0) return;
 
+    // Large scenes: the top of the tree is built here, subtrees below ~n/64 primitives by worker threads (each on
+    // its own disjoint range of the permutation array, into its own node vector), then spliced in.  The tree is
+    // the same as the sequential one: every split depends only on the primitives of its own range.
+    B.prims_ptr = &prims_storage;
     B.nodes.reserve((size_t)n);
+    unsigned hw = std::thread::hardware_concurrency();
+    if (const char* e = getenv("GORT_BVH_THREADS")) hw = (unsigned)std::max(1, atoi(e));
+    const bool parallel = n >= 20000 && hw > 1;
+    if (parallel) B.defer_below = std::max(1024, n / 64);
     int root = B.build(0, n, 0);
+    if (parallel && !B.deferred.empty()) {
+        const size_t nj = B.deferred.size();
+        std::vector<Builder> subs(nj);
+        std::vector<int> sub_root(nj, -1);
+        std::atomic<size_t> next{0};
+        auto work = [&]() {
+            for (;;) {
+                const size_t j = next.fetch_add(1);
+                if (j >= nj) break;
+                subs[j].prims_ptr = &prims_storage;
+                subs[j].nodes.reserve((size_t)B.deferred[j].count);
+                sub_root[j] = subs[j].build(B.deferred[j].first, B.deferred[j].count, B.deferred[j].depth);
+            }
+        };
+        std::vector<std::thread> pool;
+        const unsigned nt = (unsigned)std::min<size_t>(hw, nj);
+        for (unsigned t = 1; t < nt; t++) pool.emplace_back(work);
+        work();
+        for (auto& th : pool) th.join();
+        for (size_t j = 0; j < nj; j++) {
+            const int off = (int)B.nodes.size();
+            for (BNode nd : subs[j].nodes) {
+                if (nd.left >= 0) nd.left += off;
+                if (nd.right >= 0) nd.right += off;
+                B.nodes.push_back(nd);
+            }
+            const Deferred& d = B.deferred[j];
+            (d.which ? B.nodes[d.parent].right : B.nodes[d.parent].left) = sub_root[j] + off;
+            B.max_depth = std::max(B.max_depth, subs[j].max_depth);
+        }
+    }
     // Nodes store the children's boxes in the parent, so a leaf root (single-primitive scene) needs
     // a wrapper; both slots reference the same leaf (the second test ties and changes nothing).
     if (B.nodes[root].left < 0) {
@@ -288,14 +345,14 @@ void build_bvh(const HostScene& scene, FlatBvh& out) {
         if (leaf.type == 0) {
             start = (uint32_t)out.spheres.size();
             for (int i = leaf.first; i < leaf.first + leaf.count; i++) {
-                const HostSphere& s = scene.spheres[B.prims[i].idx];
+                const HostSphere& s = scene.spheres[prims_storage[i].idx];
                 out.spheres.push_back(F4{(float)s.c[0], (float)s.c[1], (float)s.c[2], (float)s.r});
                 out.sphere_meta.push_back(I2{s.mat, s.order});
             }
         } else {
             start = (uint32_t)(out.tris.size() / 4);
             for (int i = leaf.first; i < leaf.first + leaf.count; i++) {
-                const HostTriangle& t = scene.tris[B.prims[i].idx];
+                const HostTriangle& t = scene.tris[prims_storage[i].idx];
                 double e1[3], e2[3], nrm[3];
                 for (int a = 0; a < 3; a++) {
                     e1[a] = t.v[1][a] - t.v[0][a];

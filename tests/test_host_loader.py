@@ -115,3 +115,20 @@ def test_renderer_block_is_parsed_but_never_applied(gort):
     del d["renderer"]
     b = gort.HostScene(json.dumps(d))
     assert a.counts() == b.counts()
+
+
+def test_parallel_bvh_build_equals_sequential(gort):
+    """Scenes of >= 20 000 primitives build the lower subtrees on worker threads; every split depends only on its own
+    primitive range, so the tree (inner nodes, depth, leaves, bytes) is the sequential one and passes the invariant check."""
+    import json
+    import os
+    d = Cm.random_sphere_scene(30000, 11, extent=40.0)
+    hs = gort.HostScene(json.dumps(d))
+    infos = []
+    for th in ("1", "7"):
+        os.environ["GORT_BVH_THREADS"] = th
+        try:
+            infos.append(hs.bvh_validate())
+        finally:
+            del os.environ["GORT_BVH_THREADS"]
+    assert infos[0] == infos[1] and infos[0]["leaves"] == infos[0]["nodes"] + 1
