@@ -336,9 +336,10 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     }
 
     CUDA_TRY(ctx, cudaEventRecord(d.ev[0], st));
-    if (accum_want) CUDA_TRY(ctx, cudaMemsetAsync(d.d_accum, 0, accum_want, st));
+    // the accumulators are cleared block by block in the cull pass (kept blocks only), not wholesale
     CUDA_TRY(ctx, cudaMemsetAsync(d.d_counter, 0, 4 * sizeof(unsigned int), st));
-    if (int rc = ensure(ctx, d.d_active, d.active_bytes, (size_t)n_local * 32 * sizeof(uint32_t))) return rc;
+    // active-block list (uint32 per block) followed by the kept/culled byte of every block
+    if (int rc = ensure(ctx, d.d_active, d.active_bytes, (size_t)n_local * 32 * (sizeof(uint32_t) + 1))) return rc;
     if (p->collect_stats) CUDA_TRY(ctx, cudaMemsetAsync(d.d_stats, 0, kStatCount * sizeof(unsigned long long), st));
     if (slab_mode && slab_bytes > (size_t)n_local * kTilePixels * 4)
         CUDA_TRY(ctx, cudaMemsetAsync(out + (size_t)n_local * kTilePixels * 4, 0, slab_bytes - (size_t)n_local * kTilePixels * 4, st));
@@ -381,6 +382,7 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     // work units = (sample batch, active 8x4 block), sized on the device: aim for >= 8 per resident warp
     tp.target_units = 8u * (uint32_t)d.sm_count * 32u;  // ~8 units per resident warp
     tp.active_list = d.d_active; tp.active_count = d.d_counter + 1;
+    tp.block_active = reinterpret_cast<uint8_t*>(d.d_active + (size_t)n_local * 32);
 
     tp.debug_times = d.d_debug;
     tp.accum = d.d_accum; tp.work_counter = d.d_counter; tp.stats = p->collect_stats ? d.d_stats : nullptr;
@@ -403,6 +405,7 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     CUDA_TRY(ctx, cudaEventRecord(d.ev[1], st));
 
     ResolveParams rp;
+    rp.block_active = tp.block_active;
     rp.accum = d.d_accum; rp.n_local_tiles = n_local; rp.shard_rank = eff_rank; rp.shard_count = eff_count;
     rp.tiles_x = tiles_x; rp.width = p->width; rp.height = p->height; rp.samples = p->samples;
     rp.out = out; rp.slab_mode = slab_mode;
@@ -932,6 +935,8 @@ int gort_read_radiance(gort_ctx* ctx, double* out, size_t bytes) {
         CUDA_TRY(ctx, cudaStreamSynchronize(stream_of(ctx, i)));
         std::vector<long long> h((size_t)n_local * kTilePixels * 3);
         CUDA_TRY(ctx, cudaMemcpy(h.data(), d.d_accum, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        std::vector<uint8_t> kept((size_t)n_local * 32);  // culled blocks never had their accumulators cleared: they are black
+        CUDA_TRY(ctx, cudaMemcpy(kept.data(), reinterpret_cast<uint8_t*>(d.d_active + (size_t)n_local * 32), kept.size(), cudaMemcpyDeviceToHost));
         const int eff_count = ctx->last_count * nd, eff_rank = ctx->last_rank + i * ctx->last_count;
         for (int lt = 0; lt < n_local; lt++) {
             const int gt = eff_rank + lt * eff_count;
@@ -939,7 +944,8 @@ int gort_read_radiance(gort_ctx* ctx, double* out, size_t bytes) {
             for (int p = 0; p < kTilePixels; p++) {
                 const int x = tx * kTile + (p & (kTile - 1)), y = ty * kTile + p / kTile;
                 if (x >= W || y >= H) continue;
-                for (int c = 0; c < 3; c++) out[((size_t)y * W + x) * 3 + c] = (double)h[((size_t)lt * kTilePixels + p) * 3 + c] * inv;
+                const bool k = kept[(size_t)lt * 32 + ((p / kTile) >> 2) * 4 + ((p & (kTile - 1)) >> 3)] != 0;
+                for (int c = 0; c < 3; c++) out[((size_t)y * W + x) * 3 + c] = k ? (double)h[((size_t)lt * kTilePixels + p) * 3 + c] * inv : 0.0;
             }
         }
     }

@@ -1212,8 +1212,11 @@ __global__ void __launch_bounds__(128) cull_kernel(const __grid_constant__ Trace
     const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= (uint32_t)P.n_local_tiles * 32u) return;
     const SceneView& S = P.scene;
-    if (S.n_nodes == 0 || P.max_depth <= 0) return;
     const uint32_t ltile = id >> 5, block = id & 31u;
+    // The frame's accumulators are not cleared wholesale (12 MB for 800x600): a kept block clears its own 32 pixels
+    // here, a culled block is marked and resolve_kernel writes black for it without reading them.
+    P.block_active[id] = 0;
+    if (S.n_nodes == 0 || P.max_depth <= 0) return;
     const uint32_t gtile = (uint32_t)P.shard_rank + ltile * (uint32_t)P.shard_count;
     const uint32_t tx = gtile % (uint32_t)P.tiles_x, ty = gtile / (uint32_t)P.tiles_x;
     const uint32_t x0 = tx * kTile + ((block & 3u) << 3), y0 = ty * kTile + ((block >> 2) << 2);
@@ -1316,6 +1319,17 @@ __global__ void __launch_bounds__(128) cull_kernel(const __grid_constant__ Trace
             node = stack[--sp];
         }
     }
+    if (active || deep) {
+        P.block_active[id] = 1;
+        // 4 rows x 8 pixels x 3 channels of int64: 192 contiguous bytes per row
+        const uint32_t lx0 = (block & 3u) << 3, ly0 = (block >> 2) << 2;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            ulonglong2* row = reinterpret_cast<ulonglong2*>(P.accum + 3 * ((size_t)ltile * kTilePixels + (ly0 + r) * kTile + lx0));
+#pragma unroll
+            for (int k = 0; k < 12; k++) row[k] = make_ulonglong2(0ull, 0ull);
+        }
+    }
     // one array, two cursors: deep blocks fill it from the front, the others from the back
     if (deep || degenerate) active_list[atomicAdd(active_count, 1u)] = id;
     else if (active) active_list[(uint32_t)P.n_local_tiles * 32u - 1u - atomicAdd(active_count + 1, 1u)] = id;
@@ -1403,7 +1417,9 @@ __global__ void __launch_bounds__(256) resolve_kernel(const ResolveParams R) {
     const int x = (gt % R.tiles_x) * kTile + lx, y = (gt / R.tiles_x) * kTile + ly;
     const bool inside = x < R.width && y < R.height;
     uchar4 px = make_uchar4(0, 0, 0, 0);
-    if (inside) {
+    const bool kept = R.block_active[lt * 32 + (ly >> 2) * 4 + (lx >> 3)] != 0;
+    if (inside && !kept) px = make_uchar4(0, 0, 0, 255);  // culled block: every sample missed (renderer.go:171-173), toneMap(0) = 0
+    if (inside && kept) {
         const double inv = 1.0 / ((double)(1u << kAccumFracBits) * (double)R.samples);
         const unsigned long long* a = R.accum + 3 * (size_t)i;
         px.x = tone_map_u8((long long)a[0], inv);

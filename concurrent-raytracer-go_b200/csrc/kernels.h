@@ -75,6 +75,8 @@ struct TraceParams {
     const uint32_t* active_list;     // pixel blocks kept by the cull pass: (local tile << 5) | block;
                                      // [0, n_deep) from the front, n_norm more from the back of [0, 32*n_local_tiles)
     const unsigned int* active_count;  // {n_deep, n_norm}
+    uint8_t* block_active;       // [32 * n_local_tiles] written by the cull pass for EVERY block: 1 = kept (its accumulators are
+                                 // zeroed there), 0 = culled (accumulators stale: resolve writes black without reading them)
     unsigned long long* accum;   // [n_local_tiles][1024][3] int64 fixed point
     unsigned int* work_counter;  // zeroed before launch
     unsigned long long* stats;   // [kStatCount] or nullptr
@@ -98,6 +100,7 @@ struct TraceParams {
 };
 
 struct ResolveParams {
+    const uint8_t* block_active;  // see TraceParams
     const unsigned long long* accum;
     int n_local_tiles, shard_rank, shard_count;
     int tiles_x, width, height, samples;
