@@ -78,7 +78,7 @@ struct gort_link {
     int32_t width = 0, height = 0, n_ranks = 1, rank = 0;
     size_t frame_bytes = 0;
     uint8_t* base = nullptr;       // owner: cudaMalloc; peer: cudaIpcOpenMemHandle mapping of the owner's allocation
-    unsigned int* ctrl = nullptr;  // {arrived, consumed} behind the frame
+    unsigned int* ctrl = nullptr;  // {arrived, consumed, timed_out} behind the frame
     unsigned int frame_no = 0;
     bool local_alias = false;      // test hook: peer link sharing the owner's pointer inside one process
 };
@@ -310,6 +310,7 @@ int validate(gort_ctx* ctx, const gort_render_params* p) {
 struct ResolveHooks {
     const unsigned int* wait_flag = nullptr;  // before resolve: wait until *wait_flag >= wait_target
     unsigned int wait_target = 0;
+    unsigned int* timed_out = nullptr;        // set by a wait that gave up
     unsigned int* signal_flag = nullptr;      // after resolve: fence.sys + atomicAdd(*signal_flag, 1)
 };
 
@@ -409,7 +410,7 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     rp.accum = d.d_accum; rp.n_local_tiles = n_local; rp.shard_rank = eff_rank; rp.shard_count = eff_count;
     rp.tiles_x = tiles_x; rp.width = p->width; rp.height = p->height; rp.samples = p->samples;
     rp.out = out; rp.slab_mode = slab_mode;
-    if (hooks && hooks->wait_flag) CUDA_TRY(ctx, launch_link_wait(hooks->wait_flag, hooks->wait_target, st));
+    if (hooks && hooks->wait_flag) CUDA_TRY(ctx, launch_link_wait(hooks->wait_flag, hooks->wait_target, hooks->timed_out, st));
     CUDA_TRY(ctx, launch_resolve(rp, st));
     if (hooks && hooks->signal_flag) CUDA_TRY(ctx, launch_link_signal(hooks->signal_flag, st));
     CUDA_TRY(ctx, cudaEventRecord(d.ev[2], st));
@@ -872,6 +873,9 @@ int gort_link_read(gort_ctx* ctx, gort_link* l, uint8_t* rgba_out, size_t rgba_b
     cudaStream_t st = stream_of(ctx, 0);
     CUDA_TRY(ctx, cudaMemcpyAsync(rgba_out, l->base, rgba_bytes, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    unsigned int timed_out = 0;
+    CUDA_TRY(ctx, cudaMemcpy(&timed_out, l->ctrl + 2, sizeof(timed_out), cudaMemcpyDeviceToHost));
+    if (timed_out) return fail(ctx, GORT_ERR_CUDA, "frame link: a rank did not deliver its tiles within 20 s (frame incomplete)");
     return GORT_OK;
 }
 
@@ -906,9 +910,9 @@ int gort_render_linked(gort_ctx* ctx, const gort_render_params* p, gort_link* l,
         // everything this stream did with frame k-1 is done when this runs: the peers may overwrite it
         CUDA_TRY(ctx, launch_link_store(l->ctrl + 1, k - 1, st));
         if (int rc = enqueue_device(ctx, 0, p, 0, l->n_ranks, 0, l->base, 0, nullptr)) return rc;
-        if (l->n_ranks > 1) CUDA_TRY(ctx, launch_link_wait(l->ctrl + 0, k * (unsigned int)(l->n_ranks - 1), st));
+        if (l->n_ranks > 1) CUDA_TRY(ctx, launch_link_wait(l->ctrl + 0, k * (unsigned int)(l->n_ranks - 1), l->ctrl + 2, st));
     } else {
-        hk.wait_flag = l->ctrl + 1; hk.wait_target = k - 1;
+        hk.wait_flag = l->ctrl + 1; hk.wait_target = k - 1; hk.timed_out = l->ctrl + 2;
         hk.signal_flag = l->ctrl + 0;
         if (int rc = enqueue_device(ctx, 0, p, l->rank, l->n_ranks, 0, l->base, 0, &hk)) return rc;
     }

@@ -1481,14 +1481,22 @@ __global__ void link_store_kernel(unsigned int* flag, unsigned int value) {
     asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
     __threadfence_system();
 }
-__global__ void link_wait_kernel(const unsigned int* flag, unsigned int target) {
+__global__ void link_wait_kernel(const unsigned int* flag, unsigned int target, unsigned int* timed_out) {
     unsigned int ns = 100;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     for (;;) {
         unsigned int v;
         asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
         if ((int)(v - target) >= 0) break;
         __nanosleep(ns);
         if (ns < 2000) ns *= 2;
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > 20000000000ull) {  // 20 s: a rank died; never hang the GPU — flag it and let the host report
+            atomicExch_system(timed_out, 1u);
+            break;
+        }
     }
     __threadfence_system();
 }
@@ -1500,8 +1508,8 @@ cudaError_t launch_link_store(unsigned int* flag, unsigned int value, cudaStream
     link_store_kernel<<<1, 1, 0, stream>>>(flag, value);
     return cudaGetLastError();
 }
-cudaError_t launch_link_wait(const unsigned int* flag, unsigned int target, cudaStream_t stream) {
-    link_wait_kernel<<<1, 1, 0, stream>>>(flag, target);
+cudaError_t launch_link_wait(const unsigned int* flag, unsigned int target, unsigned int* timed_out, cudaStream_t stream) {
+    link_wait_kernel<<<1, 1, 0, stream>>>(flag, target, timed_out);
     return cudaGetLastError();
 }
 

@@ -113,10 +113,11 @@ cudaError_t launch_cull(const TraceParams& p, uint32_t* active_list, unsigned in
 cudaError_t launch_trace(const TraceParams& p, bool stats, int sm_count, cudaStream_t stream);
 cudaError_t launch_resolve(const ResolveParams& p, cudaStream_t stream);
 // Frame link (one process per GPU, the owner's frame mapped into every peer): system-scope flag handshake in
-// the owner's memory.  signal: fence + atomicAdd(flag, 1); store: flag = value; wait: spin until flag >= target.
+// the owner's memory.  signal: fence + atomicAdd(flag, 1); store: flag = value; wait: spin until flag >= target
+// (gives up after 20 s and sets *timed_out instead of hanging the GPU when a rank has died).
 cudaError_t launch_link_signal(unsigned int* flag, cudaStream_t stream);
 cudaError_t launch_link_store(unsigned int* flag, unsigned int value, cudaStream_t stream);
-cudaError_t launch_link_wait(const unsigned int* flag, unsigned int target, cudaStream_t stream);
+cudaError_t launch_link_wait(const unsigned int* flag, unsigned int target, unsigned int* timed_out, cudaStream_t stream);
 cudaError_t launch_unswizzle(const uint8_t* slabs, int shard_count, int width, int height, uint8_t* rgba, cudaStream_t stream);
 cudaError_t launch_trace_rays(const SceneView& scene, int n, const float* origins, const float* dirs, float tmin, float tmax,
                               int any_hit, float* out_t, int* out_order, cudaStream_t stream);
