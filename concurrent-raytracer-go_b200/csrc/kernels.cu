@@ -420,7 +420,7 @@ __device__ __forceinline__ bool tri_occludes(const float4* __restrict__ tp, floa
     return !(t < tmin || t > tmax);
 }
 
-constexpr int kMaxCand = 8;           // candidate primitives kept per (hit, light) pair on BVH scenes
+constexpr int kMaxCand = 6;           // candidate primitives kept per (hit, light) pair on BVH scenes
 constexpr uint32_t kCandOverflow = 0xFFu;  // more than kMaxCand: the pair's rays walk the BVH themselves
 
 // Walk the BVH with the cone (apex o, unit axis a, range tmax); boxes are tested through their bounding
@@ -518,7 +518,7 @@ constexpr int kWarpsPerCta = 4;
 // FILL (pushes <= 32 paths) only runs with pqn <= kQueueCap - 32; EXTEND pops n <= 32 paths and pushes n
 // records, and only runs with sqn + n <= kQueueCap (SHADE makes room first).
 constexpr int kQueueCap = 48;
-constexpr int kLightChunkMax = 8;  // lights handled per pass of a shade round (tiny scenes: kSmallLights)
+constexpr int kLightChunkMax = 4;  // lights handled per pass of a shade round
 enum PField { PF_PX, PF_PY, PF_PZ, PF_DX, PF_DY, PF_DZ, PF_PRIM, PF_TR, PF_TG, PF_TB, PF_PIXG, PF_PIXL, PF_SD, PF_FOG, PF_COUNT };
 enum SField { SF_PX, SF_PY, SF_PZ, SF_NX, SF_NY, SF_NZ, SF_TR, SF_TG, SF_TB, SF_MAT, SF_PIXG, SF_PIXL, SF_SD, SF_FOG, SF_COUNT };
 // *_SD = sample | depth << 16;  *_FOG = fog factor of the path's primary hit (extension)
@@ -587,10 +587,13 @@ __device__ __forceinline__ void ball_from_bits(uint32_t a, uint32_t b, float& bx
 //           pre-culled with the pair's cone), then calculateDirectLighting's arithmetic and ONE
 //           fixed-point add of T_k * (...) to the pixel.
 // ---------------------------------------------------------------------------------------------
-// resident CTAs per SM the register allocation must allow: 8 (64 registers) for the tiny-scene kernel, whose
-// shared memory fits 8; 6 for the BVH kernel (its walk needs ~80 registers)
+// resident CTAs per SM the register allocation must allow: 8 (64 registers) for the tiny-scene kernel; 7 (72) for
+// the BVH kernel.  Its walk is bound by per-warp latency (node fetch + dependent slab arithmetic): measured on the
+// 100 k / 1 M primitive scenes and the 40-triangle scene, 7 CTAs beat 6 by 5 / 8 / 4 % although the walk then spills
+// ~70 bytes, and 8 is no better than 7.  Shared memory (27 KB per CTA: 6 candidates per pair, 4 lights per pass)
+// is sized so that 7-8 CTAs fit.
 template <bool STATS, bool SMALL>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 6) trace_kernel(const __grid_constant__ TraceParams P) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel(const __grid_constant__ TraceParams P) {
     __shared__ WarpShared<SMALL> wsh[kWarpsPerCta];
     const int lane = threadIdx.x & 31;
     WarpShared<SMALL>& W = wsh[threadIdx.x >> 5];
