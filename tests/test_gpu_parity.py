@@ -173,6 +173,26 @@ def test_stochastic_psnr_1024spp(gort, oracle, renderer):
     assert p >= 40.0, "PSNR %.2f dB" % p
 
 
+def test_stochastic_psnr_1024spp_c2_view(gort, oracle, renderer):
+    """The same bar on the README's second benchmark scene (cubes + prisms, 3 lights, BVH kernel, cone-culled soft
+    shadows): 1024 spp both sides, independent streams, crop over the geometry."""
+    d = Cm.c2_view()
+    W, H = 600, 450
+    configure(renderer, 1024, 50, seed=77)
+    img = renderer.Render(gort.SceneFromDict(d, 1), W, H)
+    lit = img[..., :3].sum(-1) > 0
+    ys, xs = np.nonzero(lit)
+    x0, x1, y0, y1 = max(0, int(xs.min()) - 4), min(W, int(xs.max()) + 5), max(0, int(ys.min()) - 4), min(H, int(ys.max()) + 5)
+    # keep the oracle's share to a few seconds: at most 160 x 60 pixels around the centre of the lit region
+    cx, cy = (x0 + x1) // 2, (y0 + y1) // 2
+    crop = (max(x0, cx - 80), max(y0, cy - 30), min(x1, cx + 80), min(y1, cy + 30))
+    ref, _, _ = oracle.Scene(d, prisms=True).render(W, H, samples=1024, max_depth=50, rng_mode=oracle.RNG_MT, seed=5, crop=crop, threads=8)
+    a, b = img[crop[1]:crop[3], crop[0]:crop[2]], ref[crop[1]:crop[3], crop[0]:crop[2]]
+    assert (b[..., :3].sum(-1) > 0).mean() > 0.2
+    p = Cm.psnr(a, b)
+    assert p >= 40.0, "PSNR %.2f dB" % p
+
+
 def test_random_spheres_bvh_scene_same_stream(gort, oracle, renderer):
     """C4-style synthetic scene (metal/glass/dielectric spheres, 3 lights) small enough for the
     linear-scan oracle: exercises deep BVH traversal inside the full path loop."""
