@@ -35,6 +35,12 @@ struct DeviceState {
     float4* d_mats = nullptr;
     float4* d_lights = nullptr;
     size_t cap_nodes = 0, cap_spheres = 0, cap_meta = 0, cap_tris = 0, cap_mats = 0, cap_lights = 0;
+    // small scenes (<= kBlobMax bytes in all): one pinned staging buffer, one device blob, ONE async copy per upload
+    uint8_t* h_stage = nullptr;
+    uint8_t* d_blob = nullptr;
+    size_t stage_bytes = 0, blob_bytes = 0;
+    cudaEvent_t ev_upload = nullptr;
+    bool blob_in_use = false;  // the scene pointers currently point into d_blob
     // per-frame buffers
     unsigned long long* d_accum = nullptr;
     size_t accum_tiles = 0;
@@ -116,6 +122,17 @@ int ensure(gort_ctx* ctx, T*& ptr, size_t& have, size_t want_bytes) {
 
 void free_scene(DeviceState& d) {
     cudaSetDevice(d.dev);
+    if (d.blob_in_use) {
+        d.d_nodes = d.d_spheres = d.d_tris = d.d_mats = d.d_lights = nullptr;
+        d.d_meta = nullptr;
+        d.blob_in_use = false;
+    }
+    cudaFree(d.d_blob);
+    d.d_blob = nullptr; d.blob_bytes = 0;
+    if (d.h_stage) cudaFreeHost(d.h_stage);
+    d.h_stage = nullptr; d.stage_bytes = 0;
+    if (d.ev_upload) cudaEventDestroy(d.ev_upload);
+    d.ev_upload = nullptr;
     cudaFree(d.d_nodes); cudaFree(d.d_spheres); cudaFree(d.d_meta); cudaFree(d.d_tris); cudaFree(d.d_mats); cudaFree(d.d_lights);
     d.d_nodes = d.d_spheres = d.d_tris = d.d_mats = d.d_lights = nullptr;
     d.d_meta = nullptr;
@@ -193,10 +210,55 @@ int upload_scene(gort_ctx* ctx) {
         lights[2 * i + 1] = F4{(float)l.color[0], (float)l.color[1], (float)l.color[2], 0.f};
     }
     const FlatBvh& b = ctx->bvh;
+    const void* src[6] = {b.nodes.data(), b.spheres.data(), b.sphere_meta.data(), b.tris.data(), mats.data(), lights.data()};
+    const size_t len[6] = {b.nodes.size() * sizeof(F4), b.spheres.size() * sizeof(F4), b.sphere_meta.size() * sizeof(I2),
+                           b.tris.size() * sizeof(F4), mats.size() * sizeof(F4), lights.size() * sizeof(F4)};
+    size_t off[6], total = 0;
+    for (int k = 0; k < 6; k++) {
+        off[k] = total;
+        total += (std::max<size_t>(len[k], 16) + 255) / 256 * 256;
+    }
+    constexpr size_t kBlobMax = 1u << 20;
     for (size_t i = 0; i < ctx->devs.size(); i++) {
         DeviceState& d = ctx->devs[i];
         CUDA_TRY(ctx, cudaSetDevice(d.dev));
         cudaStream_t st = stream_of(ctx, (int)i);
+        if (total <= kBlobMax) {
+            // A frame of the README scenes is sub-millisecond, so the upload must not cost several API round trips:
+            // the arrays are packed into pinned staging memory and go down in one cudaMemcpyAsync, with no host
+            // synchronisation (the staging buffer is reused only after the previous copy's event has completed).
+            if (!d.ev_upload) CUDA_TRY(ctx, cudaEventCreateWithFlags(&d.ev_upload, cudaEventDisableTiming));
+            if (d.stage_bytes < total) {
+                if (d.h_stage) { CUDA_TRY(ctx, cudaEventSynchronize(d.ev_upload)); CUDA_TRY(ctx, cudaFreeHost(d.h_stage)); }
+                d.h_stage = nullptr; d.stage_bytes = 0;
+                CUDA_TRY(ctx, cudaMallocHost(&d.h_stage, kBlobMax));
+                d.stage_bytes = kBlobMax;
+            }
+            if (int rc = ensure(ctx, d.d_blob, d.blob_bytes, kBlobMax)) return rc;
+            if (!d.blob_in_use) {  // switching from separately allocated arrays
+                cudaFree(d.d_nodes); cudaFree(d.d_spheres); cudaFree(d.d_meta); cudaFree(d.d_tris); cudaFree(d.d_mats); cudaFree(d.d_lights);
+                d.cap_nodes = d.cap_spheres = d.cap_meta = d.cap_tris = d.cap_mats = d.cap_lights = 0;
+                d.blob_in_use = true;
+            }
+            CUDA_TRY(ctx, cudaEventSynchronize(d.ev_upload));
+            for (int k = 0; k < 6; k++)
+                if (len[k]) memcpy(d.h_stage + off[k], src[k], len[k]);
+            CUDA_TRY(ctx, cudaMemcpyAsync(d.d_blob, d.h_stage, total, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(ctx, cudaEventRecord(d.ev_upload, st));
+            d.d_nodes = reinterpret_cast<float4*>(d.d_blob + off[0]);
+            d.d_spheres = reinterpret_cast<float4*>(d.d_blob + off[1]);
+            d.d_meta = reinterpret_cast<int2*>(d.d_blob + off[2]);
+            d.d_tris = reinterpret_cast<float4*>(d.d_blob + off[3]);
+            d.d_mats = reinterpret_cast<float4*>(d.d_blob + off[4]);
+            d.d_lights = reinterpret_cast<float4*>(d.d_blob + off[5]);
+            continue;
+        }
+        if (d.blob_in_use) {  // back to separately allocated arrays: the pointers into the blob are not ours to free
+            d.d_nodes = d.d_spheres = d.d_tris = d.d_mats = d.d_lights = nullptr;
+            d.d_meta = nullptr;
+            d.cap_nodes = d.cap_spheres = d.cap_meta = d.cap_tris = d.cap_mats = d.cap_lights = 0;
+            d.blob_in_use = false;
+        }
         // device buffers are kept across uploads and only grow (a re-upload per frame costs no cudaMalloc)
         auto up = [&](auto*& dst, size_t& cap, const void* src, size_t bytes) -> int {
             if (int rc = ensure(ctx, dst, cap, bytes)) return rc;
@@ -573,6 +635,11 @@ const char* gort_last_error(const gort_ctx* ctx) { return ctx ? ctx->err.c_str()
 
 int gort_set_stream(gort_ctx* ctx, void* cuda_stream) {
     if (!ctx) return GORT_ERR_INVALID;
+    for (DeviceState& d : ctx->devs)  // an asynchronous scene upload on the old stream must land before the new stream reads it
+        if (d.ev_upload) {
+            cudaSetDevice(d.dev);
+            cudaEventSynchronize(d.ev_upload);
+        }
     ctx->user_stream = (cudaStream_t)cuda_stream;
     ctx->use_user_stream = cuda_stream != nullptr;
     return GORT_OK;
