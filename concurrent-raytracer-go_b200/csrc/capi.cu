@@ -56,6 +56,10 @@ struct DeviceState {
     uint8_t* h_pinned = nullptr;
     size_t pinned_bytes = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // zero-copy host frames: the culled (black) blocks are written by a small kernel on aux_stream right after the
+    // cull pass, under the trace kernel; only the kept blocks wait for the end
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_cull = nullptr, ev_aux = nullptr;
 };
 
 double now_ms() {
@@ -370,6 +374,7 @@ int validate(gort_ctx* ctx, const gort_render_params* p) {
 // out_override: write the resolved pixels there instead of d.d_out (device pointer on this device).
 // Optional stream-ordered hooks around the resolve of one device's share (frame link)
 struct ResolveHooks {
+    bool early_black = false;                 // resolve the culled blocks on the aux stream while the trace kernel runs
     const unsigned int* wait_flag = nullptr;  // before resolve: wait until *wait_flag >= wait_target
     unsigned int wait_target = 0;
     unsigned int* timed_out = nullptr;        // set by a wait that gave up
@@ -464,17 +469,32 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     tp.fog_density = (float)ctx->scene.fog_density;
     tp.fog_r = (float)ctx->scene.fog_color[0]; tp.fog_g = (float)ctx->scene.fog_color[1]; tp.fog_b = (float)ctx->scene.fog_color[2];
     CUDA_TRY(ctx, launch_cull(tp, d.d_active, d.d_counter + 1, st));
-    CUDA_TRY(ctx, launch_trace(tp, p->collect_stats != 0, d.sm_count, st));
-    CUDA_TRY(ctx, cudaEventRecord(d.ev[1], st));
-
     ResolveParams rp;
     rp.block_active = tp.block_active;
     rp.accum = d.d_accum; rp.n_local_tiles = n_local; rp.shard_rank = eff_rank; rp.shard_count = eff_count;
     rp.tiles_x = tiles_x; rp.width = p->width; rp.height = p->height; rp.samples = p->samples;
-    rp.out = out; rp.slab_mode = slab_mode;
+    rp.out = out; rp.slab_mode = slab_mode; rp.part = 0;
+    const bool early = hooks && hooks->early_black && n_local > 0;
+    if (early) {
+        if (!d.aux_stream) {
+            CUDA_TRY(ctx, cudaStreamCreateWithFlags(&d.aux_stream, cudaStreamNonBlocking));
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&d.ev_cull, cudaEventDisableTiming));
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&d.ev_aux, cudaEventDisableTiming));
+        }
+        CUDA_TRY(ctx, cudaEventRecord(d.ev_cull, st));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(d.aux_stream, d.ev_cull, 0));
+        rp.part = 1;
+        CUDA_TRY(ctx, launch_resolve(rp, d.aux_stream, d.sm_count));  // 128-thread blocks: they fit beside the resident trace CTAs
+        CUDA_TRY(ctx, cudaEventRecord(d.ev_aux, d.aux_stream));
+        rp.part = 2;
+    }
+    CUDA_TRY(ctx, launch_trace(tp, p->collect_stats != 0, d.sm_count, st));
+    CUDA_TRY(ctx, cudaEventRecord(d.ev[1], st));
+
     if (hooks && hooks->wait_flag) CUDA_TRY(ctx, launch_link_wait(hooks->wait_flag, hooks->wait_target, hooks->timed_out, st));
     CUDA_TRY(ctx, launch_resolve(rp, st));
     if (hooks && hooks->signal_flag) CUDA_TRY(ctx, launch_link_signal(hooks->signal_flag, st));
+    if (early) CUDA_TRY(ctx, cudaStreamWaitEvent(st, d.ev_aux, 0));
     CUDA_TRY(ctx, cudaEventRecord(d.ev[2], st));
     return GORT_OK;
 }
@@ -626,6 +646,9 @@ void gort_destroy(gort_ctx* ctx) {
         if (d.h_pinned) cudaFreeHost(d.h_pinned);
         for (auto& e : d.ev)
             if (e) cudaEventDestroy(e);
+        if (d.aux_stream) { cudaStreamSynchronize(d.aux_stream); cudaStreamDestroy(d.aux_stream); }
+        if (d.ev_cull) cudaEventDestroy(d.ev_cull);
+        if (d.ev_aux) cudaEventDestroy(d.ev_aux);
         if (d.own_stream) cudaStreamDestroy(d.own_stream);
     }
     delete ctx;
@@ -742,12 +765,13 @@ int gort_unswizzle_device(gort_ctx* ctx, const void* d_slabs, int32_t shard_coun
 
 // Frame into device memory of the lead device (row-major).  n_devices > 1: every device renders its
 // interleaved tiles into a slab, slabs are gathered to the lead device over NVLink and unswizzled.
-static int render_frame_device(gort_ctx* ctx, const gort_render_params* p, uint8_t* d_rgba, double t0, gort_stats* stats_out, bool sync) {
+static int render_frame_device(gort_ctx* ctx, const gort_render_params* p, uint8_t* d_rgba, double t0, gort_stats* stats_out, bool sync,
+                               const ResolveHooks* hooks = nullptr) {
     const int nd = (int)ctx->devs.size();
     const int sc = p->shard_count <= 0 ? 1 : p->shard_count;
     ctx->last_w = p->width; ctx->last_h = p->height; ctx->last_samples = p->samples; ctx->last_rank = p->shard_rank; ctx->last_count = sc;
     if (nd == 1) {
-        if (int rc = enqueue_device(ctx, 0, p, p->shard_rank, sc, 0, d_rgba, 0)) return rc;
+        if (int rc = enqueue_device(ctx, 0, p, p->shard_rank, sc, 0, d_rgba, 0, hooks)) return rc;
     } else {
         if (sc != 1) return fail(ctx, GORT_ERR_INVALID, "a multi-device ctx renders whole frames (shard_count must be 1)");
         const size_t slab = gort_shard_slab_bytes(p->width, p->height, nd);
@@ -810,6 +834,24 @@ int gort_render(gort_ctx* ctx, const gort_render_params* p, uint8_t* rgba_out, s
     CUDA_TRY(ctx, cudaSetDevice(lead.dev));
     const int sc = p->shard_count <= 0 ? 1 : p->shard_count;
     cudaStream_t st0 = stream_of(ctx, 0);
+    if (sc == 1 && ctx->devs.size() == 1 && !getenv("GORT_NO_ZERO_COPY")) {
+        // Page-locked caller memory is mapped into the device's address space (UVA): resolve_kernel then stores the RGBA8
+        // pixels straight into the caller's buffer over PCIe — 128 contiguous bytes per warp — instead of into HBM followed
+        // by a device-to-host copy: one launch and one DMA set-up less, and the transfer overlaps the tone mapping.
+        cudaPointerAttributes pa0;
+        if (cudaPointerGetAttributes(&pa0, rgba_out) == cudaSuccess && pa0.type == cudaMemoryTypeHost && pa0.devicePointer) {
+            ResolveHooks hk;
+            hk.early_black = !getenv("GORT_NO_EARLY_BLACK");
+            if (int rc = render_frame_device(ctx, p, (uint8_t*)pa0.devicePointer, t0, nullptr, false, &hk)) return rc;
+            CUDA_TRY(ctx, cudaStreamSynchronize(st0));
+            if (stats_out) {
+                if (int rc = collect_stats(ctx, p, stats_out, t0, 1)) return rc;
+                stats_out->total_ms = now_ms() - t0;
+            }
+            return GORT_OK;
+        }
+        cudaGetLastError();
+    }
     if (sc == 1) {
         if (lead.pinned_bytes < frame_bytes) {
             if (lead.h_pinned) CUDA_TRY(ctx, cudaFreeHost(lead.h_pinned));

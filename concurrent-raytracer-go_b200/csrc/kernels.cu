@@ -1412,33 +1412,36 @@ __device__ __forceinline__ uint8_t tone_map_u8(long long fixed, double inv_scale
 }
 
 __global__ void __launch_bounds__(256) resolve_kernel(const ResolveParams R) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= R.n_local_tiles * kTilePixels) return;
-    const int lt = i / kTilePixels, p = i % kTilePixels;
-    const int lx = p & (kTile - 1), ly = p / kTile;
-    const int gt = R.shard_rank + lt * R.shard_count;
-    const int x = (gt % R.tiles_x) * kTile + lx, y = (gt / R.tiles_x) * kTile + ly;
-    const bool inside = x < R.width && y < R.height;
-    uchar4 px = make_uchar4(0, 0, 0, 0);
-    const bool kept = R.block_active[lt * 32 + (ly >> 2) * 4 + (lx >> 3)] != 0;
-    if (inside && !kept) px = make_uchar4(0, 0, 0, 255);  // culled block: every sample missed (renderer.go:171-173), toneMap(0) = 0
-    if (inside && kept) {
-        const double inv = 1.0 / ((double)(1u << kAccumFracBits) * (double)R.samples);
-        const unsigned long long* a = R.accum + 3 * (size_t)i;
-        px.x = tone_map_u8((long long)a[0], inv);
-        px.y = tone_map_u8((long long)a[1], inv);
-        px.z = tone_map_u8((long long)a[2], inv);
-        px.w = 255;
+    const int n = R.n_local_tiles * kTilePixels;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int lt = i / kTilePixels, p = i % kTilePixels;
+        const int lx = p & (kTile - 1), ly = p / kTile;
+        const int gt = R.shard_rank + lt * R.shard_count;
+        const int x = (gt % R.tiles_x) * kTile + lx, y = (gt / R.tiles_x) * kTile + ly;
+        const bool inside = x < R.width && y < R.height;
+        uchar4 px = make_uchar4(0, 0, 0, 0);
+        const bool kept = R.block_active[lt * 32 + (ly >> 2) * 4 + (lx >> 3)] != 0;
+        if ((R.part == 1 && kept) || (R.part == 2 && !kept)) continue;
+        if (inside && !kept) px = make_uchar4(0, 0, 0, 255);  // culled block: every sample missed (renderer.go:171-173), toneMap(0) = 0
+        if (inside && kept) {
+            const double inv = 1.0 / ((double)(1u << kAccumFracBits) * (double)R.samples);
+            const unsigned long long* a = R.accum + 3 * (size_t)i;
+            px.x = tone_map_u8((long long)a[0], inv);
+            px.y = tone_map_u8((long long)a[1], inv);
+            px.z = tone_map_u8((long long)a[2], inv);
+            px.w = 255;
+        }
+        uchar4* out = reinterpret_cast<uchar4*>(R.out);
+        if (R.slab_mode) out[i] = px;
+        else if (inside) out[(size_t)y * R.width + x] = px;
     }
-    uchar4* out = reinterpret_cast<uchar4*>(R.out);
-    if (R.slab_mode) out[i] = px;
-    else if (inside) out[(size_t)y * R.width + x] = px;
 }
 
-cudaError_t launch_resolve(const ResolveParams& p, cudaStream_t stream) {
+cudaError_t launch_resolve(const ResolveParams& p, cudaStream_t stream, int max_blocks) {
     const int n = p.n_local_tiles * kTilePixels;
     if (n == 0) return cudaSuccess;
-    resolve_kernel<<<(n + 255) / 256, 256, 0, stream>>>(p);
+    if (max_blocks > 0) resolve_kernel<<<std::min(max_blocks, (n + 127) / 128), 128, 0, stream>>>(p);
+    else resolve_kernel<<<(n + 255) / 256, 256, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -106,12 +106,14 @@ struct ResolveParams {
     int tiles_x, width, height, samples;
     uint8_t* out;      // row-major frame (slab_mode 0) or tile-major slab (slab_mode 1)
     int slab_mode;
+    int part;          // 0 every pixel; 1 only the culled blocks (black; needs nothing but the cull pass); 2 only the kept blocks
 };
 
 // All launchers enqueue on `stream` and return the launch error (no synchronisation).
 cudaError_t launch_cull(const TraceParams& p, uint32_t* active_list, unsigned int* active_count, cudaStream_t stream);
 cudaError_t launch_trace(const TraceParams& p, bool stats, int sm_count, cudaStream_t stream);
-cudaError_t launch_resolve(const ResolveParams& p, cudaStream_t stream);
+// max_blocks > 0: a small grid-stride launch (co-resident with the persistent trace grid)
+cudaError_t launch_resolve(const ResolveParams& p, cudaStream_t stream, int max_blocks = 0);
 // Frame link (one process per GPU, the owner's frame mapped into every peer): system-scope flag handshake in
 // the owner's memory.  signal: fence + atomicAdd(flag, 1); store: flag = value; wait: spin until flag >= target
 // (gives up after 20 s and sets *timed_out instead of hanging the GPU when a rank has died).
