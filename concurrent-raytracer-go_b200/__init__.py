@@ -42,7 +42,7 @@ EXPORTED_SYMBOLS = [
     "gort_host_scene_get_triangle", "gort_host_scene_get_material", "gort_host_scene_get_light", "gort_host_scene_get_camera",
     "gort_host_scene_bvh_validate",
     "gort_link_create", "gort_link_open", "gort_link_close", "gort_link_frame", "gort_render_linked",
-    "gort_link_read", "gort_link_open_local", "gort_scene_render_hints",
+    "gort_link_read", "gort_link_open_local", "gort_scene_render_hints", "gort_host_alloc", "gort_host_free",
 ]
 
 
@@ -161,6 +161,9 @@ def load_library() -> C.CDLL:
     L.gort_render_linked.argtypes = [vp, C.POINTER(RenderParams), vp, C.POINTER(Stats)]
     L.gort_link_read.argtypes = [vp, vp, vp, C.c_size_t]
     L.gort_scene_render_hints.argtypes = [vp, ip]
+    L.gort_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.gort_host_free.argtypes = [vp]
+    L.gort_host_free.restype = None
     L.gort_link_open_local.argtypes = [vp, vp, C.c_int32, C.POINTER(vp)]
     _lib = L
     return L
@@ -572,6 +575,31 @@ class ParallelRenderer:
 def NewParallelRenderer(numWorkers: int = 1, devices: Optional[Sequence[int]] = None) -> ParallelRenderer:
     """renderer.NewParallelRenderer (renderer.go:54-65)."""
     return ParallelRenderer(numWorkers, devices)
+
+
+class HostFrame:
+    """Page-locked [H, W, 4] uint8 frame (gort_host_alloc): Render(..., out=frame.array) needs no staging copy."""
+
+    def __init__(self, width: int, height: int):
+        self._L = load_library()
+        p = C.c_void_p()
+        rc = self._L.gort_host_alloc(width * height * 4, C.byref(p))
+        if rc != 0:
+            raise GortError(rc, (self._L.gort_last_error(None) or b"").decode())
+        self._p = p
+        self.array = np.ctypeslib.as_array((C.c_uint8 * (width * height * 4)).from_address(p.value)).reshape(height, width, 4)
+
+    def close(self):
+        if self._p:
+            self.array = None
+            self._L.gort_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def shard_slab_bytes(width: int, height: int, shard_count: int) -> int:

@@ -838,12 +838,28 @@ int gort_render(gort_ctx* ctx, const gort_render_params* p, uint8_t* rgba_out, s
         // Page-locked caller memory is mapped into the device's address space (UVA): resolve_kernel then stores the RGBA8
         // pixels straight into the caller's buffer over PCIe — 128 contiguous bytes per warp — instead of into HBM followed
         // by a device-to-host copy: one launch and one DMA set-up less, and the transfer overlaps the tone mapping.
+        // Pageable caller memory (a Go slice, a numpy array) cannot be mapped: the same stores then go to the ctx's own
+        // page-locked frame and one host memcpy moves it into the caller's buffer.
         cudaPointerAttributes pa0;
-        if (cudaPointerGetAttributes(&pa0, rgba_out) == cudaSuccess && pa0.type == cudaMemoryTypeHost && pa0.devicePointer) {
+        uint8_t* target = rgba_out;
+        bool staged = false;
+        if (!(cudaPointerGetAttributes(&pa0, rgba_out) == cudaSuccess && pa0.type == cudaMemoryTypeHost && pa0.devicePointer)) {
+            cudaGetLastError();
+            if (lead.pinned_bytes < frame_bytes) {
+                if (lead.h_pinned) CUDA_TRY(ctx, cudaFreeHost(lead.h_pinned));
+                lead.h_pinned = nullptr; lead.pinned_bytes = 0;
+                CUDA_TRY(ctx, cudaMallocHost(&lead.h_pinned, frame_bytes));
+                lead.pinned_bytes = frame_bytes;
+            }
+            target = lead.h_pinned;
+            staged = true;
+        }
+        if (cudaPointerGetAttributes(&pa0, target) == cudaSuccess && pa0.type == cudaMemoryTypeHost && pa0.devicePointer) {
             ResolveHooks hk;
             hk.early_black = !getenv("GORT_NO_EARLY_BLACK");
             if (int rc = render_frame_device(ctx, p, (uint8_t*)pa0.devicePointer, t0, nullptr, false, &hk)) return rc;
             CUDA_TRY(ctx, cudaStreamSynchronize(st0));
+            if (staged) memcpy(rgba_out, lead.h_pinned, frame_bytes);
             if (stats_out) {
                 if (int rc = collect_stats(ctx, p, stats_out, t0, 1)) return rc;
                 stats_out->total_ms = now_ms() - t0;
@@ -915,6 +931,23 @@ int gort_render(gort_ctx* ctx, const gort_render_params* p, uint8_t* rgba_out, s
         stats_out->total_ms = now_ms() - t0;
     }
     return GORT_OK;
+}
+
+int gort_host_alloc(size_t bytes, void** out) {
+    if (!out || bytes == 0) return GORT_ERR_INVALID;
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable | cudaHostAllocMapped);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("gort_host_alloc: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? GORT_ERR_NO_DEVICE : GORT_ERR_CUDA;
+    }
+    return GORT_OK;
+}
+
+void gort_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+    cudaGetLastError();
 }
 
 int gort_link_create(gort_ctx* ctx, int32_t width, int32_t height, int32_t n_ranks, uint8_t* handle_out, gort_link** out) {

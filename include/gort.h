@@ -206,6 +206,12 @@ int gort_scene_render_hints(const gort_ctx* ctx, int32_t* hints5);
  * shard's tiles are written; other bytes are left untouched. */
 int gort_render(gort_ctx* ctx, const gort_render_params* params, uint8_t* rgba_out, size_t rgba_bytes,
                 gort_stats* stats_out);
+/* Page-locked host memory for frames.  gort_render into such a buffer needs no staging copy: the resolve kernel stores
+ * the pixels straight into it over PCIe, the culled (black) regions already while the frame is still being traced.
+ * (A Go host wraps it as img.Pix: unsafe.Slice((*byte)(p), n) — see INTEGRATION.md.)  Any other host pointer works
+ * too and costs one extra memcpy of the frame. */
+int gort_host_alloc(size_t bytes, void** out);
+void gort_host_free(void* p);
 /* Same frame, but the row-major RGBA8 image stays in device memory (device_ids[0]); d_rgba is a
  * device pointer with width*height*4 bytes.  Asynchronous on the ctx stream unless stats_out != NULL. */
 int gort_render_device(gort_ctx* ctx, const gort_render_params* params, void* d_rgba, size_t rgba_bytes,

@@ -19,6 +19,7 @@ import "C"
 import (
 	"fmt"
 	"image"
+	"sync"
 	"unsafe"
 )
 
@@ -141,10 +142,36 @@ func b2i(b bool) C.int32_t {
 	return 0
 }
 
-// Frame renders one image; img.Pix is written directly (Stride must be 4*width, which
-// image.NewRGBA guarantees — renderer.go:70).
+// pinned remembers which frames live in page-locked C memory (gort_host_alloc) rather than on the Go heap.
+var pinned sync.Map // *uint8 -> struct{}
+
+// newFrame backs an *image.RGBA with page-locked memory: the GPU then stores the pixels straight into img.Pix (no
+// staging copy; the black regions arrive while the frame is still being traced).  That memory is not garbage
+// collected: release it with FreeFrame, or keep reusing the image.  Falls back to the Go heap if pinning fails.
+func newFrame(width, height int) *image.RGBA {
+	var p unsafe.Pointer
+	n := width * height * 4
+	if C.gort_host_alloc(C.size_t(n), &p) != 0 {
+		return image.NewRGBA(image.Rect(0, 0, width, height))
+	}
+	pinned.Store((*uint8)(p), struct{}{})
+	return &image.RGBA{Pix: unsafe.Slice((*uint8)(p), n), Stride: 4 * width, Rect: image.Rect(0, 0, width, height)}
+}
+
+// FreeFrame releases the pixel memory of an image returned by Frame (safe for Go-heap images too).
+func FreeFrame(img *image.RGBA) {
+	if img == nil || len(img.Pix) == 0 {
+		return
+	}
+	if _, ok := pinned.LoadAndDelete(&img.Pix[0]); ok {
+		C.gort_host_free(unsafe.Pointer(&img.Pix[0]))
+		img.Pix = nil
+	}
+}
+
+// Frame renders one image; img.Pix is written directly (Stride must be 4*width — renderer.go:70).
 func (c *Context) Frame(p Params, width, height int) (*image.RGBA, Stats, error) {
-	img := image.NewRGBA(image.Rect(0, 0, width, height))
+	img := newFrame(width, height)
 	var rp C.gort_render_params
 	rp.abi_version = C.GORT_ABI_VERSION
 	rp.width, rp.height = C.int32_t(width), C.int32_t(height)

@@ -194,3 +194,25 @@ def test_multi_device_context_matches_single_device(gort, renderer):
             assert r.lastStats.n_devices == nd
             assert np.array_equal(img, full), (nd, no_direct)
             r.close()
+
+
+def test_host_frame_kinds_agree(gort, renderer):
+    """gort_render into (a) ordinary pageable memory (staged through the ctx's page-locked frame), (b) a page-locked
+    HostFrame (resolve stores straight into it, culled blocks early on a second stream), (c) the zero-copy path
+    switched off (device frame + D2H copy): the same bytes."""
+    import os
+    sc = gort.SceneFromDict(Cm.c1_view())
+    renderer.SetSamples(6); renderer.SetMaxDepth(50); renderer.SetSeed(31); renderer.SetShard(0, 1)
+    W, H = 333, 257
+    a = renderer.Render(sc, W, H).copy()
+    hf = gort.HostFrame(W, H)
+    hf.array[:] = 7
+    b = renderer.Render(sc, W, H, out=hf.array).copy()
+    os.environ["GORT_NO_ZERO_COPY"] = "1"
+    try:
+        c = renderer.Render(sc, W, H).copy()
+    finally:
+        del os.environ["GORT_NO_ZERO_COPY"]
+    hf.close()
+    assert (a[..., 3] == 255).all() and a[..., :3].max() > 0
+    assert np.array_equal(a, b) and np.array_equal(a, c)
