@@ -143,10 +143,10 @@ struct RayQuery {
 
 // ---- Sphere.Hit (geometry/sphere.go:22-59) for spheres [start, start+cnt) ----
 template <bool STATS>
-__device__ __forceinline__ void test_spheres(const SceneView& S, RayQuery& q, uint32_t start, int cnt, Stats& st) {
+__device__ __forceinline__ void test_spheres(const SceneView& S, const float4* __restrict__ spheres, RayQuery& q, uint32_t start, int cnt, Stats& st) {
     for (int i = 0; i < cnt; i++) {
         stat_add<STATS>(st, kStatSphereTests);
-        const float4 s = ldg4(S.spheres + start + i);
+        const float4 s = ldg4(spheres + start + i);
         const float ocx = q.ox - s.x, ocy = q.oy - s.y, ocz = q.oz - s.z;
         const float hb = dot3(ocx, ocy, ocz, q.dx, q.dy, q.dz);
         // discriminant/a from the component of oc perpendicular to the ray: the same quantity as
@@ -174,10 +174,10 @@ __device__ __forceinline__ void test_spheres(const SceneView& S, RayQuery& q, ui
 
 // ---- Triangle.Hit (geometry/triangle.go:36-88), Moller-Trumbore, for triangles [start, start+cnt) ----
 template <bool STATS>
-__device__ __forceinline__ void test_tris(const SceneView& S, RayQuery& q, uint32_t start, int cnt, Stats& st) {
+__device__ __forceinline__ void test_tris(const SceneView& S, const float4* __restrict__ tris, RayQuery& q, uint32_t start, int cnt, Stats& st) {
     for (int i = 0; i < cnt; i++) {
         stat_add<STATS>(st, kStatTriTests);
-        const float4* tp = S.tris + 4 * (size_t)(start + i);
+        const float4* tp = tris + 4 * (size_t)(start + i);
         const float4 v0 = ldg4(tp), e1 = ldg4(tp + 1), e2 = ldg4(tp + 2);
         const float hx = q.dy * e2.z - q.dz * e2.y, hy = q.dz * e2.x - q.dx * e2.z, hz = q.dx * e2.y - q.dy * e2.x;
         const float aa = dot3(e1.x, e1.y, e1.z, hx, hy, hz);
@@ -224,6 +224,11 @@ __device__ __noinline__ bool traverse(const SceneView& S, float ox, float oy, fl
     const float idz = rcp_fast(fabsf(dz) > ooeps ? dz : copysignf(ooeps, dz));
     const float oodx = ox * idx, oody = oy * idy, oodz = oz * idz;
 
+    // S sits in the kernel's parameter bank behind a reference (this function is not inlined): read the array
+    // pointers once, not once per visit — a dependent load ahead of every node fetch otherwise
+    const float4* __restrict__ nodes = S.nodes;
+    const float4* __restrict__ spheres = S.spheres;
+    const float4* __restrict__ tris = S.tris;
     int stack[64];
     int sp = 0;
     int node = 0;
@@ -231,7 +236,7 @@ __device__ __noinline__ bool traverse(const SceneView& S, float ox, float oy, fl
     for (;;) {
         if (node >= 0) {
             stat_add<STATS>(st, kStatNodes);
-            const float4* np = S.nodes + 4 * (size_t)node;
+            const float4* np = nodes + 4 * (size_t)node;
             const float4 n0 = ldg4(np), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3);
             const float c0lox = fmaf(n0.x, idx, -oodx), c0hix = fmaf(n0.y, idx, -oodx);
             const float c0loy = fmaf(n0.z, idy, -oody), c0hiy = fmaf(n0.w, idy, -oody);
@@ -267,8 +272,8 @@ __device__ __noinline__ bool traverse(const SceneView& S, float ox, float oy, fl
             const uint32_t v = ~(uint32_t)node;
             const uint32_t start = v & 0x3FFFFFFu;
             const int cnt = (int)((v >> 26) & 15u) + 1;
-            if (((v >> 30) & 1u) == 0) test_spheres<STATS>(S, q, start, cnt, st);
-            else test_tris<STATS>(S, q, start, cnt, st);
+            if (((v >> 30) & 1u) == 0) test_spheres<STATS>(S, spheres, q, start, cnt, st);
+            else test_tris<STATS>(S, tris, q, start, cnt, st);
             if ((q.found && any) || sp == 0) break;
             node = stack[--sp];
         }
