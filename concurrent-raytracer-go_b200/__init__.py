@@ -97,6 +97,8 @@ class Stats(C.Structure):
         ("cone_tests", C.c_uint64),
         ("walk_lane_visits", C.c_uint64 * 4), ("walk_warp_visits", C.c_uint64 * 4),
         ("algorithmic_flops", C.c_double),
+        ("soft_pairs_skipped", C.c_uint64),
+        ("pairs_backfacing", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:

@@ -547,6 +547,7 @@ int collect_stats(gort_ctx* ctx, const gort_render_params* p, gort_stats* s, dou
         s->tri_tests = tot[kStatTriTests]; s->tri_hits = tot[kStatTriHits];
         s->tri_rejects[0] = tot[kStatTriRejA]; s->tri_rejects[1] = tot[kStatTriRejU]; s->tri_rejects[2] = tot[kStatTriRejV]; s->tri_rejects[3] = tot[kStatTriRejT];
         s->shaded_hits = tot[kStatShaded]; s->rng_blocks = tot[kStatRngBlocks]; s->light_evals = tot[kStatLightEvals];
+        s->soft_pairs_skipped = tot[kStatSoftSkipped]; s->pairs_backfacing = tot[kStatBackfacing];
         s->soft_shadow_rays = tot[kStatSoftRays]; s->diffuse_evals = tot[kStatDiffuse]; s->specular_evals = tot[kStatSpec];
         s->paths_depth_ge5 = tot[kStatDepth5]; s->paths_depth_ge20 = tot[kStatDepth20]; s->paths_depth_max = tot[kStatDepthMax];
         s->cone_tests = tot[kStatConeTests];
@@ -559,7 +560,7 @@ int collect_stats(gort_ctx* ctx, const gort_render_params* p, gort_stats* s, dou
         s->algorithmic_flops = 12.0 * (double)s->primary_rays + 48.0 * (double)s->nodes_visited +
                                23.0 * (double)(s->sphere_tests - s->sphere_hits) + 47.0 * (double)s->sphere_hits +
                                20.0 * (double)s->tri_rejects[0] + 30.0 * (double)s->tri_rejects[1] + 46.0 * (double)s->tri_rejects[2] +
-                               52.0 * (double)s->tri_rejects[3] + 92.0 * (double)s->tri_hits + 30.0 * (double)s->light_evals +
+                               52.0 * (double)s->tri_rejects[3] + 92.0 * (double)s->tri_hits + 30.0 * (double)tot[kStatPairSetups] +
                                36.0 * (double)s->soft_shadow_rays + 50.0 * (double)s->diffuse_evals + 45.0 * (double)s->specular_evals +
                                70.0 * (double)s->shaded_hits + 20.0 * (double)pixels + 30.0 * (double)s->cone_tests;
     }

@@ -291,8 +291,10 @@ __device__ __noinline__ bool traverse(const SceneView& S, float ox, float oy, fl
 // the reference's last-wins tie rule.  A shadow query is the same code: "some root lies in
 // [tMin, tMax]" is exactly `found`.
 // ---------------------------------------------------------------------------------------------
-template <bool STATS>
-__device__ __forceinline__ bool small_query(const TraceParams& P, float ox, float oy, float oz, float dx, float dy, float dz, float tmin,
+// MASKED: only the spheres whose bit is set in `mask` are tested (the shadow-cone candidates of a (hit, light) pair), in
+// scan order and with the same arithmetic, so the answer equals the full scan's whenever the spheres left out cannot be hit.
+template <bool STATS, bool MASKED>
+__device__ __forceinline__ bool small_query(const TraceParams& P, uint32_t mask, float ox, float oy, float oz, float dx, float dy, float dz, float tmin,
                                             float tmax, bool any, float& t_out, int& prim_out, Stats& st) {
     stat_add<STATS>(st, any ? kStatShadow : kStatClosest);
     const float a = dot3(dx, dy, dz, dx, dy, dz);
@@ -302,14 +304,19 @@ __device__ __forceinline__ bool small_query(const TraceParams& P, float ox, floa
     // rolled on purpose: unrolled 12x at three call sites this loop was 30 % of the kernel's code and the
     // kernel did not fit the instruction cache (profiles/r1_ncu_trace_c1view_v5.txt)
 #pragma unroll 1
-    for (int i = 0; i < P.small_n; i++) {
+    for (int k = 0; MASKED ? (mask != 0u) : (k < P.small_n); k++) {
+        int i = k;
+        if (MASKED) {
+            i = __ffs(mask) - 1;
+            mask &= mask - 1u;
+        }
         {
             stat_add<STATS>(st, kStatSphereTests);
             const float4 s = P.small_sph[i];
             const float ocx = ox - s.x, ocy = oy - s.y, ocz = oz - s.z;
             const float hb = dot3(ocx, ocy, ocz, dx, dy, dz);
-            const float k = hb * inv_a;
-            const float lx = fmaf(-k, dx, ocx), ly = fmaf(-k, dy, ocy), lz = fmaf(-k, dz, ocz);
+            const float k2 = hb * inv_a;
+            const float lx = fmaf(-k2, dx, ocx), ly = fmaf(-k2, dy, ocy), lz = fmaf(-k2, dz, ocz);
             const float dn = fmaf(s.w, s.w, -dot3(lx, ly, lz, lx, ly, lz));  // discriminant / a (sphere.go:28)
             if (dn >= 0.f) {  // most tests miss: the roots are only worked out for the few that do not
                 const float sq = sqrt_fast(dn * a);
@@ -343,7 +350,7 @@ __device__ __forceinline__ void walk_account(Stats& st, unsigned int before, int
 template <bool STATS, bool SMALL>
 __device__ __forceinline__ bool query(const TraceParams& P, float ox, float oy, float oz, float dx, float dy, float dz, float tmin,
                                       float tmax, bool any, float& t_out, int& prim_out, Stats& st) {
-    if (SMALL) return small_query<STATS>(P, ox, oy, oz, dx, dy, dz, tmin, tmax, any, t_out, prim_out, st);
+    if (SMALL) return small_query<STATS, false>(P, 0u, ox, oy, oz, dx, dy, dz, tmin, tmax, any, t_out, prim_out, st);
     return traverse<STATS>(P.scene, ox, oy, oz, dx, dy, dz, tmin, tmax, any, t_out, prim_out, st);
 }
 
@@ -425,6 +432,16 @@ __device__ __forceinline__ bool tri_occludes(const float4* __restrict__ tp, floa
     return !(t < tmin || t > tmax);
 }
 
+// Tangent-plane pruning of shadow-cone candidates.  With n = hit.Normal and a = the unit direction to the light, every
+// ray of the pair's cone has d.n >= (a.n - 0.1) / 1.1 =: mu.  If a.n > 0.105 all of them leave the surface, and a point they
+// reach at t >= tMin = 0.001 lies at height (p - o).n >= 0.001 * mu above the tangent plane: a primitive whose every point is
+// lower cannot occlude the pair (the other faces of a convex object the hit point lies on, everything behind a wall).
+// Returns the height below which a primitive is dropped (minus a rounding allowance for fp32 coordinates); -inf = keep all.
+__device__ __forceinline__ float tangent_threshold(float a_dot_n, float ox, float oy, float oz) {
+    if (!(a_dot_n > 0.105f)) return -__int_as_float(0x7f800000);
+    return 0.001f * (a_dot_n - 0.1f) * (1.0f / 1.1f) - 2e-5f * (1.0f + fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz))));
+}
+
 constexpr int kMaxCand = 6;           // candidate primitives kept per (hit, light) pair on BVH scenes
 constexpr uint32_t kCandOverflow = 0xFFu;  // more than kMaxCand: the pair's rays walk the BVH themselves
 
@@ -433,7 +450,7 @@ constexpr uint32_t kCandOverflow = 0xFFu;  // more than kMaxCand: the pair's ray
 // returns their number, or kCandOverflow.
 template <bool STATS>
 __device__ __forceinline__ uint32_t cone_candidates(const SceneView& S, float ox, float oy, float oz, float ax, float ay, float az, float tmax,
-                                                    uint32_t* __restrict__ out, Stats& st) {
+                                                    float nx, float ny, float nz, float thr, uint32_t* __restrict__ out, Stats& st) {
     if (S.n_nodes == 0) return 0;
     int stack[64];
     int sp = 0;
@@ -462,6 +479,9 @@ __device__ __forceinline__ uint32_t cone_candidates(const SceneView& S, float ox
                 bool hit = (dv <= rb) || (ca >= fmaf(kConeCos, cphi, -kConeSin * sphi) - 1e-4f);
                 if (dv - rb > fmaf(tmax, 1.00001f, 1e-5f)) hit = false;
                 if (!(ex >= 0.f)) hit = false;  // inverted box = empty child
+                // highest point of the box above the hit point's tangent plane (see tangent_threshold)
+                const float top = fmaxf(nx * (lox - ox), nx * (hix - ox)) + fmaxf(ny * (loy - oy), ny * (hiy - oy)) + fmaxf(nz * (loz - oz), nz * (hiz - oz));
+                if (top < thr) hit = false;
                 h[c] = hit;
             }
             const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
@@ -487,6 +507,7 @@ __device__ __forceinline__ uint32_t cone_candidates(const SceneView& S, float ox
                 if (!is_tri) {
                     const float4 s = ldg4(S.spheres + start + i);
                     keep = cone_sphere_candidate(s.x - ox, s.y - oy, s.z - oz, fabsf(s.w), ax, ay, az, tmax);
+                    if (dot3(nx, ny, nz, s.x - ox, s.y - oy, s.z - oz) + fabsf(s.w) < thr) keep = false;  // behind the tangent plane
                 } else {
                     // the triangle's plane: a cone whose every ray moves away from it (or crosses it below
                     // tMin when the apex lies on it — the hit point's own face) cannot hit the triangle
@@ -498,6 +519,13 @@ __device__ __forceinline__ uint32_t cone_candidates(const SceneView& S, float ox
                     if (hgt > eps) keep = !(x - 0.105f >= 0.f);
                     else if (hgt < -eps) keep = !(x + 0.105f <= 0.f);
                     else keep = !(fabsf(x) - 0.105f > fmaxf(0.03f, 1000.0f * eps));
+                    if (keep && thr > -3.0e38f) {
+                        // all three vertices below the tangent-plane threshold (see tangent_threshold)
+                        const float4 e1 = ldg4(tp + 1), e2 = ldg4(tp + 2);
+                        const float h0 = dot3(nx, ny, nz, v0.x - ox, v0.y - oy, v0.z - oz);
+                        const float h1 = h0 + dot3(nx, ny, nz, e1.x, e1.y, e1.z), h2 = h0 + dot3(nx, ny, nz, e2.x, e2.y, e2.z);
+                        if (fmaxf(h0, fmaxf(h1, h2)) < thr) keep = false;
+                    }
                 }
                 if (keep) {
                     if (n >= (uint32_t)kMaxCand) return kCandOverflow;
@@ -538,6 +566,7 @@ struct WarpShared {
     uint16_t pairs[kLightChunk * 32];    // lit (light, item) pairs of the chunk: (light << 8) | item
     uint16_t cmask[SMALL ? kLightChunk : 1][32];  // tiny scenes: spheres the pair's shadow cone can reach
     uint8_t ncand[SMALL ? 4 : 32];                // BVH scenes: candidates of the 32 pairs in flight (or kCandOverflow)
+    uint8_t sel[SMALL ? 4 : 32];                  // BVH scenes: slots of the pairs in flight that have candidates
     uint32_t cand[SMALL ? 1 : 32][kMaxCand];
 };
 
@@ -967,34 +996,51 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel
                 const float inv_d = dist2 > 0.f ? rsqrt_fast(dist2) : 0.f;
                 const float dist = dist2 * inv_d;  // lightDistance
                 dx *= inv_d; dy *= inv_d; dz *= inv_d;
-                const bool go = valid && !(dist < 0.001f);  // renderer.go:252-254
-                bool lit = false;
+                // cosTheta = max(0, hit.Normal . lightDir) (renderer.go:259): at 0 the light's `intensity` is 0 and with it both
+                // the diffuse and the specular term (renderer.go:260-287) — the shadow factor of such a pair is multiplied by
+                // zero, so its 17 shadow rays are never cast.  Same expression as the shading step below: bit-identical image.
+                const float ndl = dot3(qf(SQ, SF_NX, sj), qf(SQ, SF_NY, sj), qf(SQ, SF_NZ, sj), dx, dy, dz);
+                const bool culls = !P.no_cone_cull;
+                const bool go = valid && !(dist < 0.001f) && (ndl > 0.f || !culls);  // renderer.go:252-254
+                if (STATS && valid && !(dist < 0.001f) && !go) stat_add<STATS>(st, kStatBackfacing);
+                uint8_t lit_code = 0;
                 if (go) {
-                    stat_add<STATS>(st, kStatLightEvals);
+                    stat_add<STATS>(st, kStatPairSetups);
                     float tt;
                     int pp;
-                    {
-                        const unsigned int nv0 = STATS ? st.v[kStatNodes] : 0u;
-                        lit = !query<STATS, SMALL>(P, ox, oy, oz, dx, dy, dz, 0.001f, dist, true, tt, pp, st);
-                        walk_account<STATS>(st, nv0, 2);
-                    }
-                }
-                if (valid) W.lit[li][j] = lit ? 1 : 0;
-                if (SMALL && lit && P.soft) {
-                    // which spheres can the pair's 16 jittered rays reach at all?
-                    uint32_t cm = 0;
-                    if (P.no_cone_cull) {
-                        cm = (1u << P.small_n) - 1u;
-                    } else {
+                    if (SMALL && P.soft && culls) {
+                        // Tiny scenes: which spheres can the pair's shadow cone (the hard ray is its axis) reach at all?
+                        const float thr = tangent_threshold(ndl, ox, oy, oz);
+                        const float nnx = qf(SQ, SF_NX, sj), nny = qf(SQ, SF_NY, sj), nnz = qf(SQ, SF_NZ, sj);
+                        uint32_t cm = 0;
 #pragma unroll 1
                         for (int si = 0; si < P.small_n; si++) {
                             stat_add<STATS>(st, kStatConeTests);
                             const float4 s = P.small_sph[si];
-                            if (cone_sphere_candidate(s.x - ox, s.y - oy, s.z - oz, fabsf(s.w), dx, dy, dz, dist)) cm |= 1u << si;
+                            const float vx = s.x - ox, vy = s.y - oy, vz = s.z - oz;
+                            if (dot3(nnx, nny, nnz, vx, vy, vz) + fabsf(s.w) < thr) continue;  // behind the tangent plane
+                            if (cone_sphere_candidate(vx, vy, vz, fabsf(s.w), dx, dy, dz, dist)) cm |= 1u << si;
                         }
+                        W.cmask[li][j] = (uint16_t)cm;
+                        if (cm == 0) {
+                            // Nothing in the cone: the hard ray and every one of the 16 jittered rays are unoccluded, so the
+                            // pair needs neither ray tests nor random numbers (shadowFactor = 16/16, renderer.go:326-328)
+                            lit_code = 2;
+                            W.cnt[li][j] = 16;
+                            stat_add<STATS>(st, kStatSoftSkipped);
+                        } else {
+                            stat_add<STATS>(st, kStatLightEvals);
+                            lit_code = small_query<STATS, true>(P, cm, ox, oy, oz, dx, dy, dz, 0.001f, dist, true, tt, pp, st) ? 0 : 1;
+                        }
+                    } else {
+                        stat_add<STATS>(st, kStatLightEvals);
+                        const unsigned int nv0 = STATS ? st.v[kStatNodes] : 0u;
+                        lit_code = query<STATS, SMALL>(P, ox, oy, oz, dx, dy, dz, 0.001f, dist, true, tt, pp, st) ? 0 : 1;
+                        walk_account<STATS>(st, nv0, 2);
+                        if (SMALL && lit_code && P.soft) W.cmask[li][j] = (uint16_t)((1u << P.small_n) - 1u);  // culls off: every sphere
                     }
-                    W.cmask[li][j] = (uint16_t)cm;
                 }
+                if (valid) W.lit[li][j] = lit_code;
             }
             __syncwarp();
 
@@ -1002,7 +1048,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel
             if (P.soft) {
                 int np = 0;
                 for (int li = 0; li < lc; li++) {
-                    const bool bit = act && W.lit[li][lane];
+                    const bool bit = act && W.lit[li][lane] == 1;  // 2: already resolved (empty cone)
                     const unsigned m = __ballot_sync(FULL_MASK, bit);
                     if (bit) W.pairs[np + __popc(m & lt_mask)] = (uint16_t)((li << 8) | lane);
                     np += __popc(m);
@@ -1010,8 +1056,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel
                 __syncwarp();
                 for (int p0 = 0; p0 < np; p0 += 32) {
                     const int pc = min(32, np - p0);
+                    int pc_rays = pc;  // pairs of this batch that cast their 16 rays
                     if (!SMALL) {
                         // lane = pair: one cone walk collects the pair's candidate primitives
+                        uint32_t nc_mine = 0;
                         if (lane < pc) {
                             const int pr = (int)W.pairs[p0 + lane];
                             const int sj = base + (pr & 31);
@@ -1021,15 +1069,29 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel
                             const float dist2 = dot3(ax, ay, az, ax, ay, az);
                             const float inv_d = rsqrt_fast(dist2);
                             ax *= inv_d; ay *= inv_d; az *= inv_d;
-                            W.ncand[lane] = P.no_cone_cull ? (uint8_t)kCandOverflow
-                                                           : (uint8_t)cone_candidates<STATS>(S, ox, oy, oz, ax, ay, az, dist2 * inv_d, W.cand[lane], st);
+                            const float nnx = qf(SQ, SF_NX, sj), nny = qf(SQ, SF_NY, sj), nnz = qf(SQ, SF_NZ, sj);
+                            const float thr = tangent_threshold(dot3(nnx, nny, nnz, ax, ay, az), ox, oy, oz);
+                            nc_mine = P.no_cone_cull ? kCandOverflow
+                                                     : cone_candidates<STATS>(S, ox, oy, oz, ax, ay, az, dist2 * inv_d, nnx, nny, nnz, thr, W.cand[lane], st);
+                            W.ncand[lane] = (uint8_t)nc_mine;
+                            // an empty cone: all 16 rays are unoccluded whatever their jitter (shadowFactor = 16/16,
+                            // renderer.go:326-328) — no random numbers, no ray tests
+                            if (nc_mine == 0) {
+                                W.cnt[pr >> 8][pr & 31] = 16;
+                                stat_add<STATS>(st, kStatSoftSkipped);
+                            }
                         }
+                        // the pairs that do need their 16 rays, compacted: sel[k] = slot of the k-th of them
+                        const unsigned need = __ballot_sync(FULL_MASK, lane < pc && nc_mine != 0);
+                        if (lane < pc && nc_mine != 0) W.sel[__popc(need & lt_mask)] = (uint8_t)lane;
+                        pc_rays = __popc(need);
                         __syncwarp();
                     }
                     // a quarter warp per pair; lane & 7 = k handles shadow samples 2k and 2k+1 (renderer.go:313)
-                    for (int q0 = 0; q0 < pc; q0 += 4) {
-                        const int qi = q0 + (lane >> 3);
-                        const bool valid = qi < pc;
+                    for (int q0 = 0; q0 < pc_rays; q0 += 4) {
+                        const int qk = q0 + (lane >> 3);
+                        const bool valid = qk < pc_rays;
+                        const int qi = SMALL ? qk : (valid ? (int)W.sel[qk] : 0);  // slot of the pair in this batch
                         const int pr = valid ? (int)W.pairs[p0 + qi] : 0;
                         const int li = pr >> 8, j = pr & 31;
                         const int sj = base + j;

@@ -41,7 +41,10 @@ enum StatIndex {
     // SIMT use of the BVH walk per call site (FILL, EXTEND, SHADE-B, SHADE-C overflow): node visits summed over
     // lanes, and 32 x the longest lane of each warp-level call; their ratio is the lane utilisation
     kStatWalkLane0 = 21, kStatWalkWarp0 = 25,
-    kStatCount = 29
+    kStatSoftSkipped = 29,  // lit (hit, light) pairs whose shadow cone is empty: factor 16/16 without casting the 16 rays
+    kStatBackfacing = 30,   // (hit, light) pairs with hit.Normal . lightDir <= 0: cosTheta = 0 zeroes both lighting terms, no shadow rays
+    kStatPairSetups = 31,   // (hit, light) pairs whose light direction / distance set-up ran and that were not back-facing
+    kStatCount = 32
 };
 
 struct DevCamera {
@@ -90,7 +93,8 @@ struct TraceParams {
     // 0 disables it.
     float dead_bound;
     int urgent_depth;  // > 0: a warp whose newest survivors reached this depth extends them before refilling (tail latency)
-    int no_cone_cull;  // test switch (GORT_NO_CONE_CULL): soft-shadow rays test every primitive / walk the BVH themselves
+    int no_cone_cull;  // test switch (GORT_NO_CONE_CULL): no exact culls — back-facing pairs cast their shadow rays, soft-shadow
+                       // rays test every primitive / walk the BVH themselves
     // tiny sphere-only scene, in the reference's scan order (small_n == 0: use the BVH)
     int small_n;
     int small_mat[kSmallMax];

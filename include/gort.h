@@ -165,6 +165,10 @@ typedef struct gort_stats {
      * candidates}: node visits summed over lanes / 32 x the longest lane of every warp-level call */
     uint64_t walk_lane_visits[4], walk_warp_visits[4];
     double algorithmic_flops; /* SURVEY §8d per-operation costs applied to the counters above */
+    uint64_t soft_pairs_skipped; /* lit (hit, light) pairs whose shadow cone held no primitive: shadowFactor 16/16
+                                  * (renderer.go:326-328) without casting the 16 rays */
+    uint64_t pairs_backfacing;   /* (hit, light) pairs with hit.Normal . lightDir <= 0: cosTheta = 0 (renderer.go:259) zeroes the
+                                  * diffuse and specular terms, so no shadow ray is cast for them */
 } gort_stats;
 
 typedef struct gort_ctx gort_ctx;

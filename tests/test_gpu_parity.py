@@ -251,10 +251,13 @@ def test_c1_golden_fixture(gort, renderer):
 
 
 def test_soft_shadow_candidate_culling_is_exact(gort, renderer):
-    """The per-(hit, light) cone culling of soft-shadow candidates (kernels.cu) only skips tests that must
-    fail: with GORT_NO_CONE_CULL=1 every ray tests every primitive (tiny sphere scenes: same arithmetic,
-    the radiance must be bit-identical) or walks the BVH itself (BVH scenes: same booleans up to the
-    rounding of two formulations of the same test)."""
+    """The exact culls of the shade stage (kernels.cu) only skip work whose result is known: (hit, light) pairs
+    with hit.Normal . lightDir <= 0 (cosTheta = 0 zeroes both lighting terms, renderer.go:259-287) cast no shadow
+    rays; primitives outside a pair's shadow cone or below the hit point's tangent plane are not tested; a pair
+    whose cone is empty gets shadowFactor 16/16 without rays.  With GORT_NO_CONE_CULL=1 every pair casts its 17
+    rays and every ray tests every primitive (tiny sphere scenes: same arithmetic, the radiance must be
+    bit-identical) or walks the BVH itself (BVH scenes: same booleans up to the rounding of two formulations
+    of the same test)."""
     import os
     for d, opts, W, H, exact in ((Cm.c1_view(), 0, 400, 300, True), (Cm.c2_view(), 1, 300, 225, False),
                                  (Cm.random_sphere_scene(300, 7), 0, 256, 192, False)):
