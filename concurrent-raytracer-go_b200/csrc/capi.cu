@@ -433,6 +433,20 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
             tp.small_sph[i] = make_float4((float)sorted[i]->c[0], (float)sorted[i]->c[1], (float)sorted[i]->c[2], (float)sorted[i]->r);
             tp.small_mat[i] = sorted[i]->mat;
         }
+        // small_inside[i]: the spheres a ray can meet while it is INSIDE sphere i — i itself and every sphere whose
+        // surface comes within reach of i's volume (centre distance <= r_i + r_j, with a margin).  A non-overlapping
+        // sphere lies wholly outside i, so it can only be hit beyond i's exit point: never the closest hit.
+        for (int i = 0; i < tp.small_n; i++) {
+            uint32_t m = 1u << i;
+            for (int j = 0; j < tp.small_n; j++) {
+                if (j == i) continue;
+                double d2 = 0;
+                for (int a = 0; a < 3; a++) d2 += (sorted[i]->c[a] - sorted[j]->c[a]) * (sorted[i]->c[a] - sorted[j]->c[a]);
+                const double reach = (std::fabs(sorted[i]->r) + std::fabs(sorted[j]->r)) * (1.0 + 1e-4) + 1e-5;
+                if (std::sqrt(d2) <= reach) m |= 1u << j;
+            }
+            tp.small_inside[i] = (uint16_t)m;
+        }
         for (size_t i = 0; i < ctx->scene.mats.size(); i++) {
             F4 m[4];
             pack_material(ctx->scene.mats[i], m);

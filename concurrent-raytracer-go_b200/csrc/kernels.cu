@@ -921,7 +921,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel
                     float t2;
                     {
                         const unsigned int nv0 = STATS ? st.v[kStatNodes] : 0u;
-                        survive = query<STATS, SMALL>(P, px, py, pz, sx, sy, sz, 0.001f, FLT_MAX * 2.0f, false, t2, prim2, st);
+                        if (SMALL) {
+                            // A scattered ray that heads INTO the sphere it starts on (refraction, internal reflection) stays inside
+                            // it up to its exit point: only that sphere and the ones overlapping it can be the closest hit
+                            // (TraceParams::small_inside).  The 50-bounce chains of a glass sphere scan one sphere instead of all.
+                            // The ray leaves the sphere again at t = -2 g / |s|^2: four times tMin at least, so that the reference
+                            // accepts that root too (sphere.go:35-40) and nothing beyond it can be the closest hit.
+                            const float4 s0 = P.small_sph[prim];
+                            const float g = dot3(sx, sy, sz, px - s0.x, py - s0.y, pz - s0.z);
+                            const float s2 = dot3(sx, sy, sz, sx, sy, sz);
+                            const bool inward = g < -0.002f * s2 && !P.no_cone_cull;
+                            const uint32_t mask = inward ? (uint32_t)P.small_inside[prim] : ((1u << P.small_n) - 1u);
+                            survive = small_query<STATS, true>(P, mask, px, py, pz, sx, sy, sz, 0.001f, FLT_MAX * 2.0f, false, t2, prim2, st);
+                        } else {
+                            survive = query<STATS, SMALL>(P, px, py, pz, sx, sy, sz, 0.001f, FLT_MAX * 2.0f, false, t2, prim2, st);
+                        }
                         walk_account<STATS>(st, nv0, 1);
                     }
                     if (survive) {

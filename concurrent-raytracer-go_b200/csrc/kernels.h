@@ -99,6 +99,7 @@ struct TraceParams {
     int small_n;
     int small_mat[kSmallMax];
     float4 small_sph[kSmallMax];
+    uint16_t small_inside[kSmallMax];  // per sphere: the spheres a ray can hit while it is inside it (itself + overlapping ones)
     float4 small_mats[kSmallMax][4];      // the scene's materials (same packing as SceneView::mats)
     float4 small_lights[kSmallLights][2];  // the scene's lights (same packing as SceneView::lights)
 };
