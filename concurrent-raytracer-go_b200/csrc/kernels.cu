@@ -94,6 +94,29 @@ __device__ __forceinline__ uint4 philox(const uint32_t* __restrict__ rk, uint32_
     return make_uint4(c0, c1, c2, c3);
 }
 
+// BVH kernels: one out-of-line copy for the three stages that draw random numbers (the kernel is bound by instruction
+// fetch: C2-view loses 7 % per 2.5 KB of code).  The round keys are rebuilt from the seed (they sit in the parameter bank,
+// which a non-inlined function can only reach through generic loads).
+__device__ __noinline__ uint4 philox_out(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+template <bool SMALL>
+__device__ __forceinline__ uint4 philox_at(const uint32_t* __restrict__ rk, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+    if (SMALL) return philox(rk, c0, c1, c2, c3);
+    return philox_out(rk[0], rk[1], c0, c1, c2, c3);
+}
+
 __device__ __forceinline__ float ex2_fast(float x) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -128,8 +151,10 @@ __device__ __forceinline__ void ball_from_block(const uint4 r, float& bx, float&
 // otherwise closest hit with the linear scan's tie rule (equal t: later scan order wins).
 // prim: sphere -> leaf-order index; triangle -> index | 0x80000000.
 // ---------------------------------------------------------------------------------------------
+// GEOM (BVH kernels are specialised by what the scene holds, see trace_kernel): 1 spheres only, 2 triangles only, 3 both
+template <int GEOM = 3>
 __device__ __forceinline__ int prim_order(const SceneView& S, int prim) {
-    if (prim >= 0) return __ldg(&S.sphere_meta[prim]).y;
+    if (GEOM == 1 || (GEOM == 3 && prim >= 0)) return __ldg(&S.sphere_meta[prim]).y;
     return __float_as_int(ldg4(S.tris + 4 * (size_t)(prim & 0x7fffffff) + 1).w);
 }
 
@@ -142,7 +167,7 @@ struct RayQuery {
 };
 
 // ---- Sphere.Hit (geometry/sphere.go:22-59) for spheres [start, start+cnt) ----
-template <bool STATS>
+template <bool STATS, int GEOM = 3>
 __device__ __forceinline__ void test_spheres(const SceneView& S, const float4* __restrict__ spheres, RayQuery& q, uint32_t start, int cnt, Stats& st) {
     for (int i = 0; i < cnt; i++) {
         stat_add<STATS>(st, kStatSphereTests);
@@ -164,7 +189,7 @@ __device__ __forceinline__ void test_spheres(const SceneView& S, const float4* _
         stat_add<STATS>(st, kStatSphereHits);
         const int pr = (int)(start + i);
         if (root == q.tbest && q.found) {
-            if (prim_order(S, pr) < prim_order(S, q.best)) continue;
+            if (prim_order<GEOM>(S, pr) < prim_order<GEOM>(S, q.best)) continue;
         }
         q.tbest = root;
         q.best = pr;
@@ -173,7 +198,7 @@ __device__ __forceinline__ void test_spheres(const SceneView& S, const float4* _
 }
 
 // ---- Triangle.Hit (geometry/triangle.go:36-88), Moller-Trumbore, for triangles [start, start+cnt) ----
-template <bool STATS>
+template <bool STATS, int GEOM = 3>
 __device__ __forceinline__ void test_tris(const SceneView& S, const float4* __restrict__ tris, RayQuery& q, uint32_t start, int cnt, Stats& st) {
     for (int i = 0; i < cnt; i++) {
         stat_add<STATS>(st, kStatTriTests);
@@ -194,7 +219,7 @@ __device__ __forceinline__ void test_tris(const SceneView& S, const float4* __re
         stat_add<STATS>(st, kStatTriHits);
         const int pr = (int)((start + i) | 0x80000000u);
         if (t == q.tbest && q.found) {
-            if (prim_order(S, pr) < prim_order(S, q.best)) continue;
+            if (prim_order<GEOM>(S, pr) < prim_order<GEOM>(S, q.best)) continue;
         }
         q.tbest = t;
         q.best = pr;
@@ -208,7 +233,7 @@ __device__ __forceinline__ void test_tris(const SceneView& S, const float4* __re
 // One copy per kernel (__noinline__): inlined at its five call sites the walk was 42 % of an 80 KB kernel,
 // more than the 32 KB instruction cache holds; warps sit in different stages, so they thrashed it
 // (profiles/r1_ncu_trace_c2view_v5.txt: stall_no_instruction 5.2 per issue).
-template <bool STATS>
+template <bool STATS, int GEOM = 3>
 __device__ __noinline__ bool traverse(const SceneView& S, float ox, float oy, float oz, float dx, float dy, float dz,
                                       float tmin, float tmax, bool any, float& t_out, int& prim_out, Stats& st) {
     stat_add<STATS>(st, any ? kStatShadow : kStatClosest);
@@ -227,8 +252,8 @@ __device__ __noinline__ bool traverse(const SceneView& S, float ox, float oy, fl
     // S sits in the kernel's parameter bank behind a reference (this function is not inlined): read the array
     // pointers once, not once per visit — a dependent load ahead of every node fetch otherwise
     const float4* __restrict__ nodes = S.nodes;
-    const float4* __restrict__ spheres = S.spheres;
-    const float4* __restrict__ tris = S.tris;
+    const float4* __restrict__ spheres = GEOM != 2 ? S.spheres : nullptr;
+    const float4* __restrict__ tris = GEOM != 1 ? S.tris : nullptr;
     int stack[64];
     int sp = 0;
     int node = 0;
@@ -272,8 +297,10 @@ __device__ __noinline__ bool traverse(const SceneView& S, float ox, float oy, fl
             const uint32_t v = ~(uint32_t)node;
             const uint32_t start = v & 0x3FFFFFFu;
             const int cnt = (int)((v >> 26) & 15u) + 1;
-            if (((v >> 30) & 1u) == 0) test_spheres<STATS>(S, spheres, q, start, cnt, st);
-            else test_tris<STATS>(S, tris, q, start, cnt, st);
+            if (GEOM == 1) test_spheres<STATS, GEOM>(S, spheres, q, start, cnt, st);
+            else if (GEOM == 2) test_tris<STATS, GEOM>(S, tris, q, start, cnt, st);
+            else if (((v >> 30) & 1u) == 0) test_spheres<STATS, GEOM>(S, spheres, q, start, cnt, st);
+            else test_tris<STATS, GEOM>(S, tris, q, start, cnt, st);
             if ((q.found && any) || sp == 0) break;
             node = stack[--sp];
         }
@@ -347,11 +374,11 @@ __device__ __forceinline__ void walk_account(Stats& st, unsigned int before, int
     }
 }
 
-template <bool STATS, bool SMALL>
+template <bool STATS, bool SMALL, int GEOM = 3>
 __device__ __forceinline__ bool query(const TraceParams& P, float ox, float oy, float oz, float dx, float dy, float dz, float tmin,
                                       float tmax, bool any, float& t_out, int& prim_out, Stats& st) {
     if (SMALL) return small_query<STATS, false>(P, 0u, ox, oy, oz, dx, dy, dz, tmin, tmax, any, t_out, prim_out, st);
-    return traverse<STATS>(P.scene, ox, oy, oz, dx, dy, dz, tmin, tmax, any, t_out, prim_out, st);
+    return traverse<STATS, GEOM>(P.scene, ox, oy, oz, dx, dy, dz, tmin, tmax, any, t_out, prim_out, st);
 }
 
 // material / light records: tiny scenes read them from the kernel parameter bank (no memory latency on
@@ -448,7 +475,7 @@ constexpr uint32_t kCandOverflow = 0xFFu;  // more than kMaxCand: the pair's ray
 // Walk the BVH with the cone (apex o, unit axis a, range tmax); boxes are tested through their bounding
 // spheres.  Writes up to kMaxCand primitive references (sphere: index; triangle: index | 0x80000000) and
 // returns their number, or kCandOverflow.
-template <bool STATS>
+template <bool STATS, int GEOM = 3>
 __device__ __forceinline__ uint32_t cone_candidates(const SceneView& S, float ox, float oy, float oz, float ax, float ay, float az, float tmax,
                                                     float nx, float ny, float nz, float thr, uint32_t* __restrict__ out, Stats& st) {
     if (S.n_nodes == 0) return 0;
@@ -500,7 +527,7 @@ __device__ __forceinline__ uint32_t cone_candidates(const SceneView& S, float ox
             const uint32_t v = ~(uint32_t)node;
             const uint32_t start = v & 0x3FFFFFFu;
             const int cnt = (int)((v >> 26) & 15u) + 1;
-            const bool is_tri = ((v >> 30) & 1u) != 0;
+            const bool is_tri = GEOM == 2 || (GEOM == 3 && ((v >> 30) & 1u) != 0);
             for (int i = 0; i < cnt; i++) {
                 bool keep = true;
                 stat_add<STATS>(st, kStatConeTests);
@@ -626,7 +653,7 @@ __device__ __forceinline__ void ball_from_bits(uint32_t a, uint32_t b, float& bx
 // 100 k / 1 M primitive scenes and the 40-triangle scene, 7 CTAs beat 6 by 5 / 8 / 4 % although the walk then spills
 // ~70 bytes, and 8 is no better than 7.  Shared memory (27 KB per CTA: 6 candidates per pair, 4 lights per pass)
 // is sized so that 7-8 CTAs fit.
-template <bool STATS, bool SMALL>
+template <bool STATS, bool SMALL, int GEOM>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel(const __grid_constant__ TraceParams P) {
     __shared__ WarpShared<SMALL> wsh[kWarpsPerCta];
     const int lane = threadIdx.x & 31;
@@ -730,7 +757,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel
                     if ((s_cur & 1) && jit_valid) {
                         jx = jit_z; jy = jit_w;
                     } else {
-                        const uint4 r = philox(P.rk, pixg, (uint32_t)s_cur >> 1, kStreamJitter, 0u);
+                        const uint4 r = philox_at<SMALL>(P.rk, pixg, (uint32_t)s_cur >> 1, kStreamJitter, 0u);
                         stat_add<STATS>(st, kStatRngBlocks);
                         jit_z = r.z; jit_w = r.w;
                         jx = (s_cur & 1) ? r.z : r.x;
@@ -748,7 +775,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel
                 if (P.max_depth > 0)
                     {
                         const unsigned int nv0 = STATS ? st.v[kStatNodes] : 0u;
-                        hit = query<STATS, SMALL>(P, P.cam.ox, P.cam.oy, P.cam.oz, dx, dy, dz, 0.001f, FLT_MAX * 2.0f, false, t, prim, st);
+                        hit = query<STATS, SMALL, GEOM>(P, P.cam.ox, P.cam.oy, P.cam.oz, dx, dy, dz, 0.001f, FLT_MAX * 2.0f, false, t, prim, st);
                         walk_account<STATS>(st, nv0, 0);
                     }
             }
@@ -806,7 +833,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel
                     const float inv_r = rcp_fast(s.w);
                     nx = (px - s.x) * inv_r; ny = (py - s.y) * inv_r; nz = (pz - s.z) * inv_r;
                     mat = P.small_mat[prim];
-                } else if (prim >= 0) {
+                } else if (GEOM == 1 || (GEOM == 3 && prim >= 0)) {
                     const float4 s = ldg4(S.spheres + prim);
                     const float inv_r = rcp_fast(s.w);
                     nx = (px - s.x) * inv_r; ny = (py - s.y) * inv_r; nz = (pz - s.z) * inv_r;
@@ -843,7 +870,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel
                 const bool rough = (mtype == 2) ? (m1.x > 0.f) : (m1.x > 0.001f);
                 uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
                 if (mtype == 0 || (mtype <= 3 && rough) || mtype == 4 || mtype == 5) {
-                    rnd = philox(P.rk, pixg, sample, bs, 0u);
+                    rnd = philox_at<SMALL>(P.rk, pixg, sample, bs, 0u);
                     stat_add<STATS>(st, kStatRngBlocks);
                 }
                 if (mtype == 0) {  // Lambertian (material.go:26-35)
@@ -934,7 +961,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel
                             const uint32_t mask = inward ? (uint32_t)P.small_inside[prim] : ((1u << P.small_n) - 1u);
                             survive = small_query<STATS, true>(P, mask, px, py, pz, sx, sy, sz, 0.001f, FLT_MAX * 2.0f, false, t2, prim2, st);
                         } else {
-                            survive = query<STATS, SMALL>(P, px, py, pz, sx, sy, sz, 0.001f, FLT_MAX * 2.0f, false, t2, prim2, st);
+                            survive = query<STATS, SMALL, GEOM>(P, px, py, pz, sx, sy, sz, 0.001f, FLT_MAX * 2.0f, false, t2, prim2, st);
                         }
                         walk_account<STATS>(st, nv0, 1);
                     }
@@ -1049,7 +1076,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel
                     } else {
                         stat_add<STATS>(st, kStatLightEvals);
                         const unsigned int nv0 = STATS ? st.v[kStatNodes] : 0u;
-                        lit_code = query<STATS, SMALL>(P, ox, oy, oz, dx, dy, dz, 0.001f, dist, true, tt, pp, st) ? 0 : 1;
+                        lit_code = query<STATS, SMALL, GEOM>(P, ox, oy, oz, dx, dy, dz, 0.001f, dist, true, tt, pp, st) ? 0 : 1;
                         walk_account<STATS>(st, nv0, 2);
                         if (SMALL && lit_code && P.soft) W.cmask[li][j] = (uint16_t)((1u << P.small_n) - 1u);  // culls off: every sphere
                     }
@@ -1086,7 +1113,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel
                             const float nnx = qf(SQ, SF_NX, sj), nny = qf(SQ, SF_NY, sj), nnz = qf(SQ, SF_NZ, sj);
                             const float thr = tangent_threshold(dot3(nnx, nny, nnz, ax, ay, az), ox, oy, oz);
                             nc_mine = P.no_cone_cull ? kCandOverflow
-                                                     : cone_candidates<STATS>(S, ox, oy, oz, ax, ay, az, dist2 * inv_d, nnx, nny, nnz, thr, W.cand[lane], st);
+                                                     : cone_candidates<STATS, GEOM>(S, ox, oy, oz, ax, ay, az, dist2 * inv_d, nnx, nny, nnz, thr, W.cand[lane], st);
                             W.ncand[lane] = (uint8_t)nc_mine;
                             // an empty cone: all 16 rays are unoccluded whatever their jitter (shadowFactor = 16/16,
                             // renderer.go:326-328) — no random numbers, no ray tests
@@ -1119,7 +1146,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel
                             const float dist = dist2 * inv_d;
                             ax *= inv_d; ay *= inv_d; az *= inv_d;
                             const uint32_t sdw = SQ[SF_SD][sj];
-                            const uint4 rb = philox(P.rk, SQ[SF_PIXG][sj], sdw & 0xffffu, ((sdw >> 16) << 8) | kStreamShadow,
+                            const uint4 rb = philox_at<SMALL>(P.rk, SQ[SF_PIXG][sj], sdw & 0xffffu, ((sdw >> 16) << 8) | kStreamShadow,
                                                     ((uint32_t)(l0 + li) << 12) | ((uint32_t)(lane & 7) << 8));
                             stat_add<STATS>(st, kStatRngBlocks);
                             stat_add<STATS>(st, kStatSoftRays, 2);
@@ -1148,14 +1175,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel
                                     float tt;
                                     int pp;
                                     const unsigned int nv0 = STATS ? st.v[kStatNodes] : 0u;
-                                    occA = traverse<STATS>(S, ox, oy, oz, dxa, dya, dza, 0.001f, dist, true, tt, pp, st);
-                                    occB = traverse<STATS>(S, ox, oy, oz, dxb, dyb, dzb, 0.001f, dist, true, tt, pp, st);
+                                    occA = traverse<STATS, GEOM>(S, ox, oy, oz, dxa, dya, dza, 0.001f, dist, true, tt, pp, st);
+                                    occB = traverse<STATS, GEOM>(S, ox, oy, oz, dxb, dyb, dzb, 0.001f, dist, true, tt, pp, st);
                                     walk_account<STATS>(st, nv0, 3);
                                 } else {
                                     stat_add<STATS>(st, kStatShadow, 2);
                                     for (uint32_t k = 0; k < nc; k++) {
                                         const uint32_t ref = W.cand[qi][k];
-                                        if (ref & 0x80000000u) {
+                                        if (GEOM == 2 || (GEOM == 3 && (ref & 0x80000000u))) {
                                             const float4* tp = S.tris + 4 * (size_t)(ref & 0x7fffffffu);
                                             const bool ha = tri_occludes(tp, ox, oy, oz, dxa, dya, dza, 0.001f, dist);
                                             const bool hb = tri_occludes(tp, ox, oy, oz, dxb, dyb, dzb, 0.001f, dist);
@@ -1427,13 +1454,13 @@ cudaError_t launch_cull(const TraceParams& p, uint32_t* active_list, unsigned in
 }
 
 
-template <bool STATS, bool SMALL>
+template <bool STATS, bool SMALL, int GEOM>
 static cudaError_t launch_trace_variant(const TraceParams& p, int sm_count, cudaStream_t stream) {
     // persistent grid: as many CTAs as fit on the chip at once (occupancy is register-bound)
     static int ctas_per_sm = 0;
     if (ctas_per_sm == 0) {
         int n = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_kernel<STATS, SMALL>, kWarpsPerCta * 32, 0);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_kernel<STATS, SMALL, GEOM>, kWarpsPerCta * 32, 0);
         if (e != cudaSuccess) return e;
         ctas_per_sm = n > 0 ? n : 1;
     }
@@ -1441,7 +1468,7 @@ static cudaError_t launch_trace_variant(const TraceParams& p, int sm_count, cuda
         const int nw = sm_count * ctas_per_sm * kWarpsPerCta;
         cudaMemsetAsync(p.debug_times, 0xff, 8, stream);
         cudaMemsetAsync(p.debug_times + 1, 0, (size_t)nw * 64, stream);
-        trace_kernel<STATS, SMALL><<<sm_count * ctas_per_sm, kWarpsPerCta * 32, 0, stream>>>(p);
+        trace_kernel<STATS, SMALL, GEOM><<<sm_count * ctas_per_sm, kWarpsPerCta * 32, 0, stream>>>(p);
         std::vector<unsigned long long> h(1 + 8 * (size_t)nw);
         cudaMemcpyAsync(h.data(), p.debug_times, h.size() * 8, cudaMemcpyDeviceToHost, stream);
         cudaStreamSynchronize(stream);
@@ -1463,20 +1490,33 @@ static cudaError_t launch_trace_variant(const TraceParams& p, int sm_count, cuda
         }
         return cudaGetLastError();
     }
-    trace_kernel<STATS, SMALL><<<sm_count * ctas_per_sm, kWarpsPerCta * 32, 0, stream>>>(p);
+    trace_kernel<STATS, SMALL, GEOM><<<sm_count * ctas_per_sm, kWarpsPerCta * 32, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_trace(const TraceParams& p, bool stats, int sm_count, cudaStream_t stream) {
     if (p.n_local_tiles == 0) return cudaSuccess;
-    const bool small = p.small_n > 0;
-    if (stats) return small ? launch_trace_variant<true, true>(p, sm_count, stream) : launch_trace_variant<true, false>(p, sm_count, stream);
-    return small ? launch_trace_variant<false, true>(p, sm_count, stream) : launch_trace_variant<false, false>(p, sm_count, stream);
+    // kernel variant: tiny sphere scenes scan the parameter bank; BVH scenes run the kernel specialised for what they hold
+    const int geom = p.small_n > 0 ? 0 : ((p.scene.n_spheres > 0 ? 1 : 0) | (p.scene.n_tris > 0 ? 2 : 0));
+    if (stats) {
+        switch (geom) {
+            case 0: return launch_trace_variant<true, true, 1>(p, sm_count, stream);
+            case 1: return launch_trace_variant<true, false, 1>(p, sm_count, stream);
+            case 2: return launch_trace_variant<true, false, 2>(p, sm_count, stream);
+            default: return launch_trace_variant<true, false, 3>(p, sm_count, stream);
+        }
+    }
+    switch (geom) {
+        case 0: return launch_trace_variant<false, true, 1>(p, sm_count, stream);
+        case 1: return launch_trace_variant<false, false, 1>(p, sm_count, stream);
+        case 2: return launch_trace_variant<false, false, 2>(p, sm_count, stream);
+        default: return launch_trace_variant<false, false, 3>(p, sm_count, stream);
+    }
 }
 
 int trace_kernel_regs(bool stats) {
     cudaFuncAttributes a;
-    cudaError_t e = stats ? cudaFuncGetAttributes(&a, trace_kernel<true, false>) : cudaFuncGetAttributes(&a, trace_kernel<false, false>);
+    cudaError_t e = stats ? cudaFuncGetAttributes(&a, trace_kernel<true, false, 3>) : cudaFuncGetAttributes(&a, trace_kernel<false, false, 3>);
     return e == cudaSuccess ? a.numRegs : -1;
 }
 
