@@ -20,7 +20,7 @@ for i in range(frames):
     print(name, W, H, spp, "trace_ms %.3f" % r.lastStats.trace_ms, "bvh_ms %.1f" % r.lastStats.bvh_build_ms, flush=True)
 r.SetCollectStats(True); r.Render(flat, W, H)
 s = r.lastStats.as_dict()
-print({k: s[k] for k in ("closest_queries", "shadow_queries", "shaded_hits", "soft_shadow_rays", "light_evals", "nodes_visited", "sphere_tests", "tri_tests", "cone_tests", "bvh_nodes", "bvh_bytes")})
+print({k: s[k] for k in ("closest_queries", "shadow_queries", "shaded_hits", "soft_shadow_rays", "light_evals", "nodes_visited", "sphere_tests", "tri_tests", "cone_tests", "soft_pairs_skipped", "pairs_backfacing", "diffuse_evals", "bvh_nodes", "bvh_bytes")})
 for k, site in enumerate(("FILL", "EXTEND", "SHADE hard", "SHADE soft (no candidates)")):
     if s["walk_warp_visits"][k]:
         print("walk %-28s lane visits %12d  lane utilisation %.3f" % (site, s["walk_lane_visits"][k], s["walk_lane_visits"][k] / s["walk_warp_visits"][k]))
