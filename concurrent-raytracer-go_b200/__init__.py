@@ -26,7 +26,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GORT_LIB") or os.path.join(_HERE, "lib", "libgort.so")  # GORT_LIB: A/B builds of the same ABI
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 TILE = 32
 CAMERA_REFERENCE, CAMERA_LOOKAT = 0, 1
 LOAD_PRISMS, LOAD_FOG = 1, 2

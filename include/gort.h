@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GORT_ABI_VERSION 1u
+#define GORT_ABI_VERSION 2u /* 2: gort_stats grew by soft_pairs_skipped and pairs_backfacing */
 #define GORT_MAX_DEVICES 8
 #define GORT_TILE 32 /* createRenderTasks tileSize, renderer.go:401 */
 
