@@ -365,7 +365,8 @@ class ParallelRenderer:
         self.collectStats = False
         self._scene_token = None
         self.lastStats: Optional[Stats] = None
-        self.benchmarkData: dict = {}
+        self._bench_raw = None
+        self._params_cache = None
 
     # ---- settings.go:3-25 ----
     def SetSamples(self, samples: int): self.samples = int(samples)
@@ -417,6 +418,10 @@ class ParallelRenderer:
         self._scene_token = scene
 
     def _params(self, width: int, height: int) -> RenderParams:
+        key = (width, height, self.samples, self.maxDepth, self.antiAliasing, self.recursiveReflections, self.softShadows,
+               self.cameraMode, self.shardRank, self.shardCount, self.collectStats, self.seed)
+        if self._params_cache is not None and self._params_cache[0] == key:
+            return self._params_cache[1]
         p = RenderParams()
         p.abi_version = ABI_VERSION
         p.width, p.height, p.samples, p.max_depth = width, height, self.samples, self.maxDepth
@@ -427,6 +432,7 @@ class ParallelRenderer:
         p.shard_rank, p.shard_count = self.shardRank, self.shardCount
         p.collect_stats = int(self.collectStats)
         p.seed = self.seed
+        self._params_cache = (key, p)
         return p
 
     def Render(self, scene, width: int, height: int, out: Optional[np.ndarray] = None) -> np.ndarray:
@@ -440,17 +446,27 @@ class ParallelRenderer:
         p = self._params(width, height)
         self._check(self._L.gort_render(self._ctx, C.byref(p), img.ctypes.data_as(C.c_void_p), img.size, C.byref(st)))
         self.lastStats = st
+        # BenchmarkData (renderer.go:31-42,103-117) is recorded per frame; the dict itself is only built when somebody
+        # reads it (benchmarkData property): the formatting costs more than the cgo-sized call it sits next to
+        self._bench_raw = (width, height, time.time() - start, time.time(), self.samples, self.maxDepth)
+        return img
+
+    @property
+    def benchmarkData(self) -> dict:
+        """BenchmarkData of the last Render (renderer.go:31-42,103-117); {} before the first frame."""
+        if self._bench_raw is None:
+            return {}
+        width, height, seconds, when, samples, depth = self._bench_raw
         counts = self.SceneCounts()
-        self.benchmarkData = {  # BenchmarkData (renderer.go:31-42,103-117)
-            "scene_name": "demo_scene", "resolution": "%dx%d" % (width, height), "render_time_seconds": time.time() - start,
-            "samples": self.samples, "max_depth": self.maxDepth, "num_workers": self.numWorkers,
+        return {
+            "scene_name": "demo_scene", "resolution": "%dx%d" % (width, height), "render_time_seconds": seconds,
+            "samples": samples, "max_depth": depth, "num_workers": self.numWorkers,
             "objects": counts["hittables"], "lights": counts["lights"],
-            "timestamp": time.strftime("%Y-%m-%dT%H:%M:%S%z"),
+            "timestamp": time.strftime("%Y-%m-%dT%H:%M:%S%z", time.localtime(when)),
             "features": ["Improved metallic reflections with Fresnel effect",
                          "Shiny materials with configurable roughness and specular",
                          "Enhanced light source reflections", "Better specular highlights for metallic surfaces"],
         }
-        return img
 
     def RenderDevice(self, width: int, height: int, d_rgba_ptr: int, want_stats: bool = False) -> Optional[Stats]:
         """Frame into device memory (row-major RGBA8 at d_rgba_ptr); asynchronous unless want_stats."""

@@ -116,9 +116,32 @@ def test_stats_counters(gort, renderer):
     assert 0 < st.closest_queries < st.primary_rays and st.shadow_queries == st.light_evals + st.soft_shadow_rays
     assert st.soft_shadow_rays % 16 == 0 and st.shaded_hits > 0 and st.algorithmic_flops > 0
     assert st.sphere_tests > 0 and st.tri_tests == 0
+    # the exact culls of the shade stage: pairs facing away from their light, lit pairs with an empty shadow cone
+    assert st.pairs_backfacing > 0 and st.soft_pairs_skipped > 0
+    assert st.pairs_backfacing + st.light_evals + st.soft_pairs_skipped <= st.shaded_hits * 2  # two lights
     renderer.SetCollectStats(False)
     b = renderer.Render(sc, 400, 300)
     assert (a == b).all()  # the counting variant renders the same image
+
+
+def test_benchmark_data_schema(gort, tmp_path):
+    """BenchmarkData (renderer.go:31-42) is recorded by every Render and written by SaveBenchmarkData (renderer.go:119-126)."""
+    import json
+    r = gort.NewParallelRenderer(1)
+    try:
+        assert r.benchmarkData == {}
+        setup(r, 2, 5, seed=3)
+        r.Render(gort.SceneFromDict(Cm.c1_view()), 64, 48)
+        b = r.benchmarkData
+        assert sorted(b) == sorted(["scene_name", "resolution", "render_time_seconds", "samples", "max_depth", "num_workers", "objects",
+                                    "lights", "timestamp", "features"])
+        assert b["resolution"] == "64x48" and b["samples"] == 2 and b["max_depth"] == 5 and b["objects"] == 5 and b["lights"] == 2
+        assert b["render_time_seconds"] > 0 and len(b["features"]) == 4
+        path = str(tmp_path / "benchmark_data.json")
+        r.SaveBenchmarkData(path)
+        assert json.load(open(path))["resolution"] == "64x48"
+    finally:
+        r.close()
 
 
 def test_error_codes(gort, renderer):
