@@ -629,7 +629,7 @@ int gort_create(const int* device_ids, int n_devices, gort_ctx** out) {
         for (int k = 0; k < 4 && e == cudaSuccess; k++) e = cudaEventCreate(&d.ev[k]);
         if (e == cudaSuccess) e = cudaMalloc(&d.d_counter, 16);
         if (e == cudaSuccess) e = cudaMalloc(&d.d_stats, kStatCount * sizeof(unsigned long long));
-        if (e == cudaSuccess && getenv("GORT_DEBUG_TIMES")) e = cudaMalloc(&d.d_debug, (1 + 8 * 148 * 64) * sizeof(unsigned long long));
+        if (e == cudaSuccess && getenv("GORT_DEBUG_TIMES")) e = cudaMalloc(&d.d_debug, (1 + 16 * 148 * 64) * sizeof(unsigned long long));
         if (e != cudaSuccess) return bail(GORT_ERR_CUDA, std::string("device init: ") + cudaGetErrorString(e));
     }
     if (n_devices > 1) {  // NVLink peer access: the other devices store their tiles straight into the lead's frame

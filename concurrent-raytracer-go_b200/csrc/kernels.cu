@@ -682,6 +682,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel
 
     // per-warp timeline, compiled in only with -DGORT_DEBUG (lib/libgort_dbg.so; tools/debug_times.py)
     unsigned long long t_units_done = 0, dbg_rounds = 0, dbg_paths = 0, dbg_shades = 0, dbg_t_ext = 0, dbg_t_shade = 0, dbg_t0 = 0;
+    // anatomy of the EXTEND rounds after the units ran out (cycles): queue read + hit record + materials / Scatter / hitWorld / rest
+    unsigned long long dbg_sec[4] = {0, 0, 0, 0}, dbg_tp = 0;
+#define GORT_DBG_SECTION(k)                                   \
+    if (kDbg && P.debug_times && !more_units) {               \
+        const unsigned long long t__ = clock64();             \
+        dbg_sec[k] += t__ - dbg_tp;                            \
+        dbg_tp = t__;                                          \
+    }
     if (kDbg && P.debug_times && lane == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -812,6 +820,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel
                 dbg_rounds++;
                 dbg_paths += n;
                 dbg_t0 = clock64();
+                dbg_tp = dbg_t0;
             }
             bool survive = false;
             float px = 0.f, py = 0.f, pz = 0.f, sx = 0.f, sy = 0.f, sz = 0.f, tr = 0.f, tg = 0.f, tb = 0.f, fog = 0.f;
@@ -861,6 +870,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel
 
                 const float4 m0 = mat4<SMALL>(P, mat, 0), m1 = mat4<SMALL>(P, mat, 1), m2 = mat4<SMALL>(P, mat, 2), m3 = mat4<SMALL>(P, mat, 3);
                 const int mtype = __float_as_int(m0.x);
+                GORT_DBG_SECTION(0)
                 const uint32_t depth = sd >> 16, sample = sd & 0xffffu;
                 const uint32_t bs = (depth << 8) | kStreamScatter;
                 bool scattered = true;
@@ -944,6 +954,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel
                 // inside a rough-metal sphere otherwise bounce to max_depth with throughput ~0.03^k.)
                 const float db = P.dead_bound;
                 if (db > 0.f && fabsf(tr) * db < 4.6566e-10f && fabsf(tg) * db < 4.6566e-10f && fabsf(tb) * db < 4.6566e-10f) cont = false;
+                GORT_DBG_SECTION(1)
                 if (cont) {
                     float t2;
                     {
@@ -970,6 +981,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel
                         sd += 0x10000u;
                     }
                 }
+                GORT_DBG_SECTION(2)
                 if (STATS && !survive) {
                     const uint32_t dd = depth + (scattered ? 1u : 0u);
                     if (dd >= 5) stat_add<STATS>(st, kStatDepth5);
@@ -991,6 +1003,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel
             sqn += n;
             urgent = P.urgent_depth > 0 && __any_sync(FULL_MASK, survive && (int)(sd >> 16) >= P.urgent_depth);
             __syncwarp();
+            GORT_DBG_SECTION(3)
             if (kDbg && P.debug_times && !more_units) dbg_t_ext += clock64() - dbg_t0;
             continue;
         }
@@ -1275,8 +1288,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         const unsigned int w = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-        unsigned long long* o = P.debug_times + 1 + 8 * (size_t)w;
+        unsigned long long* o = P.debug_times + 1 + 16 * (size_t)w;
         o[0] = t_units_done; o[1] = t; o[2] = dbg_rounds; o[3] = dbg_paths; o[4] = dbg_shades; o[5] = dbg_t_ext; o[6] = dbg_t_shade;
+        o[7] = dbg_sec[0]; o[8] = dbg_sec[1]; o[9] = dbg_sec[2]; o[10] = dbg_sec[3];
     }
     if (STATS && P.stats) {
 #pragma unroll
@@ -1467,17 +1481,18 @@ static cudaError_t launch_trace_variant(const TraceParams& p, int sm_count, cuda
     if (kDbg && p.debug_times) {  // -DGORT_DEBUG build + GORT_DEBUG_TIMES=1: per-warp timeline of this launch on stderr
         const int nw = sm_count * ctas_per_sm * kWarpsPerCta;
         cudaMemsetAsync(p.debug_times, 0xff, 8, stream);
-        cudaMemsetAsync(p.debug_times + 1, 0, (size_t)nw * 64, stream);
+        cudaMemsetAsync(p.debug_times + 1, 0, (size_t)nw * 128, stream);
         trace_kernel<STATS, SMALL, GEOM><<<sm_count * ctas_per_sm, kWarpsPerCta * 32, 0, stream>>>(p);
-        std::vector<unsigned long long> h(1 + 8 * (size_t)nw);
+        std::vector<unsigned long long> h(1 + 16 * (size_t)nw);
         cudaMemcpyAsync(h.data(), p.debug_times, h.size() * 8, cudaMemcpyDeviceToHost, stream);
         cudaStreamSynchronize(stream);
-        struct Rec { double units, end; unsigned long long rounds, paths, shades; double ext_us, shade_us; };
+        struct Rec { double units, end; unsigned long long rounds, paths, shades; double ext_us, shade_us; double sec[4]; };
         std::vector<Rec> recs;
         for (int w = 0; w < nw; w++) {
-            const unsigned long long* o = &h[1 + 8 * (size_t)w];
+            const unsigned long long* o = &h[1 + 16 * (size_t)w];
             if (!o[1]) continue;
-            recs.push_back(Rec{(double)(o[0] - h[0]) * 1e-3, (double)(o[1] - h[0]) * 1e-3, o[2], o[3], o[4], (double)o[5] / 1965.0, (double)o[6] / 1965.0});
+            recs.push_back(Rec{(double)(o[0] - h[0]) * 1e-3, (double)(o[1] - h[0]) * 1e-3, o[2], o[3], o[4], (double)o[5] / 1965.0, (double)o[6] / 1965.0,
+                                {(double)o[7], (double)o[8], (double)o[9], (double)o[10]}});
         }
         std::sort(recs.begin(), recs.end(), [](const Rec& a, const Rec& b) { return a.end < b.end; });
         auto at = [&](double q) -> const Rec& { return recs[(size_t)(q * (recs.size() - 1))]; };
@@ -1487,6 +1502,15 @@ static cudaError_t launch_trace_variant(const TraceParams& p, int sm_count, cuda
             for (size_t i = recs.size() > 6 ? recs.size() - 6 : 0; i < recs.size(); i++)
                 fprintf(stderr, "[gort debug]   slow warp: units exhausted %.1f us, end %.1f us; after that %llu EXTEND rounds (%llu paths) %.1f us, %llu SHADE rounds %.1f us\n",
                         recs[i].units, recs[i].end, recs[i].rounds, recs[i].paths, recs[i].ext_us, recs[i].shades, recs[i].shade_us);
+            // anatomy of those EXTEND rounds (cycles per round, summed over the slowest 32 warps)
+            double sec[4] = {0, 0, 0, 0}, rounds = 0;
+            for (size_t i = recs.size() > 32 ? recs.size() - 32 : 0; i < recs.size(); i++) {
+                for (int k = 0; k < 4; k++) sec[k] += recs[i].sec[k];
+                rounds += (double)recs[i].rounds;
+            }
+            if (rounds > 0)
+                fprintf(stderr, "[gort debug]   cycles per drain-mode EXTEND round: queue read + hit record + materials %.0f, Scatter %.0f, hitWorld %.0f, compaction + bookkeeping %.0f\n",
+                        sec[0] / rounds, sec[1] / rounds, sec[2] / rounds, sec[3] / rounds);
         }
         return cudaGetLastError();
     }
