@@ -834,6 +834,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel
                 tr = qf(PQ, PF_TR, slot); tg = qf(PQ, PF_TG, slot); tb = qf(PQ, PF_TB, slot);
                 pixg = PQ[PF_PIXG][slot]; pixl2 = PQ[PF_PIXL][slot]; sd = PQ[PF_SD][slot];
                 fog = qf(PQ, PF_FOG, slot);
+                uint4 rnd_early = make_uint4(0u, 0u, 0u, 0u);
+                if (SMALL) rnd_early = philox(P.rk, pixg, sd & 0xffffu, ((sd >> 16) << 8) | kStreamScatter, 0u);
                 // hit record (sphere.go:42-50, triangle.go:69-73)
                 float nx, ny, nz;
                 int mat;
@@ -879,10 +881,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel
                 // Lambertian and rough Metal/Shiny/Mirror turn it into a ball point, Glass/Dielectric use word 0
                 const bool rough = (mtype == 2) ? (m1.x > 0.f) : (m1.x > 0.001f);
                 uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
-                if (mtype == 0 || (mtype <= 3 && rough) || mtype == 4 || mtype == 5) {
+                const bool draws = mtype == 0 || (mtype <= 3 && rough) || mtype == 4 || mtype == 5;
+                if (SMALL) {
+                    // drawn for every hit, up front: the block depends on nothing but the path's counters, so its ten
+                    // dependent rounds overlap the queue reads, the hit record and the material fetch instead of following them
+                    // (the tail of a frame is single glass paths, one dependent chain per round; profiles/README.md)
+                    rnd = rnd_early;
+                } else if (draws) {
                     rnd = philox_at<SMALL>(P.rk, pixg, sample, bs, 0u);
-                    stat_add<STATS>(st, kStatRngBlocks);
                 }
+                if (draws) stat_add<STATS>(st, kStatRngBlocks);
                 if (mtype == 0) {  // Lambertian (material.go:26-35)
                     float bx, by, bz;
                     ball_from_block(rnd, bx, by, bz);
