@@ -5,6 +5,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include <limits>
 #include <atomic>
@@ -59,6 +60,112 @@ struct Deferred {
     int first, count, depth;
 };
 
+struct Bins3 {
+    Box box[3][kBins];
+    int cnt[3][kBins];
+    void reset() {
+        for (int a = 0; a < 3; a++)
+            for (int k = 0; k < kBins; k++) {
+                box[a][k].reset();
+                cnt[a][k] = 0;
+            }
+    }
+};
+
+// threads the top of the tree may use for one node's passes (set by build_bvh; worker builders stay sequential)
+static unsigned g_node_threads = 1;
+constexpr int kParallelNode = 1 << 16;  // ranges of at least this many primitives are scanned in parallel chunks
+
+template <class F>
+static void for_chunks(int first, int count, unsigned threads, F&& f) {
+    const unsigned nt = std::max(1u, std::min<unsigned>(threads, (unsigned)(count / (kParallelNode / 4)) + 1u));
+    if (nt <= 1) {
+        f(0u, first, first + count);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nt; t++) {
+        const int lo = first + (int)((long long)count * t / nt), hi = first + (int)((long long)count * (t + 1) / nt);
+        if (t + 1 < nt) pool.emplace_back([&f, t, lo, hi]() { f(t, lo, hi); });
+        else f(t, lo, hi);
+    }
+    for (auto& th : pool) th.join();
+}
+
+static void bin_range(const std::vector<BPrim>& prims, int lo, int hi, const Box& cb, const double scale3[3], const bool axis_ok[3], Bins3& b) {
+    b.reset();
+    for (int i = lo; i < hi; i++) {
+        const BPrim& p = prims[i];
+        for (int axis = 0; axis < 3; axis++) {
+            if (!axis_ok[axis]) continue;
+            const int k = std::min(kBins - 1, std::max(0, (int)((p.c[axis] - cb.lo[axis]) * scale3[axis])));
+            b.cnt[axis][k]++;
+            b.box[axis][k].grow(p.lo, p.hi);
+        }
+    }
+}
+
+static void fill_bins(const std::vector<BPrim>& prims, int first, int count, const Box& cb, const double scale3[3], const bool axis_ok[3],
+                      Bins3& out) {
+    const unsigned threads = count >= kParallelNode ? g_node_threads : 1u;
+    if (threads <= 1) {
+        bin_range(prims, first, first + count, cb, scale3, axis_ok, out);
+        return;
+    }
+    std::vector<Bins3> part(threads);
+    std::vector<char> used(threads, 0);
+    for_chunks(first, count, threads, [&](unsigned t, int lo, int hi) {
+        bin_range(prims, lo, hi, cb, scale3, axis_ok, part[t]);
+        used[t] = 1;
+    });
+    out.reset();
+    for (unsigned t = 0; t < threads; t++) {
+        if (!used[t]) continue;
+        for (int a = 0; a < 3; a++)
+            for (int k = 0; k < kBins; k++) {
+                out.cnt[a][k] += part[t].cnt[a][k];
+                out.box[a][k].grow(part[t].box[a][k]);
+            }
+    }
+}
+
+// bounds of the primitives and of their centroids over [first, first + count), and whether both types occur
+static void range_bounds(const std::vector<BPrim>& prims, int first, int count, Box& b, Box& cb, bool& mixed) {
+    const unsigned threads = count >= kParallelNode ? g_node_threads : 1u;
+    const int32_t type0 = prims[first].type;
+    auto scan = [&prims, type0](int lo, int hi, Box& bb, Box& cc, bool& mx) {
+        bb.reset();
+        cc.reset();
+        mx = false;
+        for (int i = lo; i < hi; i++) {
+            bb.grow(prims[i].lo, prims[i].hi);
+            cc.grow(prims[i].c, prims[i].c);
+            if (prims[i].type != type0) mx = true;
+        }
+    };
+    if (threads <= 1) {
+        scan(first, first + count, b, cb, mixed);
+        return;
+    }
+    std::vector<Box> pb(threads), pc(threads);
+    std::vector<char> pm(threads, 0), used(threads, 0);
+    for_chunks(first, count, threads, [&](unsigned t, int lo, int hi) {
+        bool mx;
+        scan(lo, hi, pb[t], pc[t], mx);
+        pm[t] = mx ? 1 : 0;
+        used[t] = 1;
+    });
+    b.reset();
+    cb.reset();
+    mixed = false;
+    for (unsigned t = 0; t < threads; t++) {
+        if (!used[t]) continue;
+        b.grow(pb[t]);
+        cb.grow(pc[t]);
+        mixed = mixed || pm[t];
+    }
+}
+
 struct Builder {
     std::vector<BPrim>* prims_ptr = nullptr;  // shared permutation array; builders work on disjoint ranges
     std::vector<BNode> nodes;
@@ -84,14 +191,8 @@ struct Builder {
     int build(int first, int count, int depth) {
         std::vector<BPrim>& prims = *prims_ptr;
         Box b, cb;
-        b.reset();
-        cb.reset();
         bool mixed = false;
-        for (int i = first; i < first + count; i++) {
-            b.grow(prims[i].lo, prims[i].hi);
-            cb.grow(prims[i].c, prims[i].c);
-            if (prims[i].type != prims[first].type) mixed = true;
-        }
+        range_bounds(prims, first, count, b, cb, mixed);
         int split = -1;  // prims [first, split) go left
 
         if (count <= kMaxLeafPrims && mixed) {
@@ -115,21 +216,20 @@ struct Builder {
             double best_cost = std::numeric_limits<double>::infinity();
             int best_axis = -1, best_bin = -1;
             const double parent_area = b.area();
+            // one pass over the primitives fills the bins of all three axes (large ranges: in parallel chunks, merged in a
+            // fixed order — boxes and counts are order-independent, so the tree does not depend on the thread count)
+            Bins3 bins;
+            double scale3[3];
+            bool axis_ok[3];
             for (int axis = 0; axis < 3; axis++) {
-                double cmin = cb.lo[axis], cmax = cb.hi[axis];
-                if (!(cmax > cmin)) continue;
-                Box bin_box[kBins];
-                int bin_cnt[kBins];
-                for (int k = 0; k < kBins; k++) {
-                    bin_box[k].reset();
-                    bin_cnt[k] = 0;
-                }
-                const double scale = kBins / (cmax - cmin);
-                for (int i = first; i < first + count; i++) {
-                    int k = std::min(kBins - 1, std::max(0, (int)((prims[i].c[axis] - cmin) * scale)));
-                    bin_cnt[k]++;
-                    bin_box[k].grow(prims[i].lo, prims[i].hi);
-                }
+                axis_ok[axis] = cb.hi[axis] > cb.lo[axis];
+                scale3[axis] = axis_ok[axis] ? kBins / (cb.hi[axis] - cb.lo[axis]) : 0.0;
+            }
+            fill_bins(prims, first, count, cb, scale3, axis_ok, bins);
+            for (int axis = 0; axis < 3; axis++) {
+                if (!axis_ok[axis]) continue;
+                const Box* bin_box = bins.box[axis];
+                const int* bin_cnt = bins.cnt[axis];
                 double right_area[kBins];
                 int right_cnt[kBins];
                 Box acc;
@@ -268,7 +368,14 @@ void build_bvh(const HostScene& scene, FlatBvh& out) {
     if (const char* e = getenv("GORT_BVH_THREADS")) hw = (unsigned)std::max(1, atoi(e));
     const bool parallel = n >= 20000 && hw > 1;
     if (parallel) B.defer_below = std::max(1024, n / 64);
+    g_node_threads = parallel ? hw : 1u;  // the top of the tree scans its large ranges in parallel chunks
+    const bool times = getenv("GORT_BVH_TIMES") != nullptr;
+    auto lap = [&](const char* what) {
+        if (times) fprintf(stderr, "[gort bvh] %-22s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    };
+    lap("primitive boxes");
     int root = B.build(0, n, 0);
+    lap("top of the tree");
     if (parallel && !B.deferred.empty()) {
         const size_t nj = B.deferred.size();
         std::vector<Builder> subs(nj);
@@ -300,6 +407,7 @@ void build_bvh(const HostScene& scene, FlatBvh& out) {
             B.max_depth = std::max(B.max_depth, subs[j].max_depth);
         }
     }
+    lap("subtrees + splice");
     // Nodes store the children's boxes in the parent, so a leaf root (single-primitive scene) needs
     // a wrapper; both slots reference the same leaf (the second test ties and changes nothing).
     if (B.nodes[root].left < 0) {
@@ -316,43 +424,47 @@ void build_bvh(const HostScene& scene, FlatBvh& out) {
     for (int a = 0; a < 3; a++) extent = std::max(extent, std::max(std::fabs(world.lo[a]), std::fabs(world.hi[a])));
     const double pad = 4e-7 * std::max(1.0, extent);
 
-    // breadth-first numbering of inner nodes
-    std::vector<int32_t> flat_index(B.nodes.size(), -1);
+    // Breadth-first numbering of the inner nodes (the order vector is its own queue).  The same traversal fixes where each
+    // leaf's primitives go in the per-type arrays (leaves are laid out in the order their parents are numbered, child 0
+    // before child 1), so the arrays can then be filled in parallel.
+    std::vector<int32_t> flat_index(B.nodes.size(), -1), leaf_start(B.nodes.size(), -1);
     std::vector<int32_t> order;
     order.reserve(B.nodes.size());
-    {
-        std::queue<int32_t> q;
-        q.push(root);
-        while (!q.empty()) {
-            int32_t t = q.front();
-            q.pop();
-            flat_index[t] = (int32_t)order.size();
-            order.push_back(t);
-            const BNode& nd = B.nodes[t];
-            if (nd.left >= 0 && B.nodes[nd.left].left != -1) q.push(nd.left);
-            if (nd.right >= 0 && B.nodes[nd.right].left != -1) q.push(nd.right);
+    order.push_back(root);
+    flat_index[root] = 0;
+    uint32_t n_sph_out = 0, n_tri_out = 0;
+    for (size_t head = 0; head < order.size(); head++) {
+        const BNode& nd = B.nodes[order[head]];
+        const int32_t kids[2] = {nd.left, nd.right};
+        for (int c = 0; c < 2; c++) {
+            const BNode& k = B.nodes[kids[c]];
+            if (k.left != -1) {
+                flat_index[kids[c]] = (int32_t)order.size();
+                order.push_back(kids[c]);
+            } else if (leaf_start[kids[c]] < 0) {  // (the single-primitive scene references its leaf from both root slots)
+                uint32_t& cursor = k.type == 0 ? n_sph_out : n_tri_out;
+                leaf_start[kids[c]] = (int32_t)cursor;
+                cursor += (uint32_t)k.count;
+            }
         }
     }
     out.n_nodes = (int32_t)order.size();
     out.nodes.resize((size_t)out.n_nodes * 4);
-    out.spheres.reserve(nS);
-    out.sphere_meta.reserve(nS);
-    out.tris.reserve((size_t)nT * 4);
+    out.spheres.resize(n_sph_out);
+    out.sphere_meta.resize(n_sph_out);
+    out.tris.resize((size_t)n_tri_out * 4);
     out.max_depth = B.max_depth + 1;
 
-    auto emit_leaf = [&](const BNode& leaf) -> int32_t {
-        uint32_t start;
+    auto emit_leaf = [&](const BNode& leaf, uint32_t start) -> int32_t {
         if (leaf.type == 0) {
-            start = (uint32_t)out.spheres.size();
-            for (int i = leaf.first; i < leaf.first + leaf.count; i++) {
-                const HostSphere& s = scene.spheres[prims_storage[i].idx];
-                out.spheres.push_back(F4{(float)s.c[0], (float)s.c[1], (float)s.c[2], (float)s.r});
-                out.sphere_meta.push_back(I2{s.mat, s.order});
+            for (int i = 0; i < leaf.count; i++) {
+                const HostSphere& s = scene.spheres[prims_storage[leaf.first + i].idx];
+                out.spheres[start + i] = F4{(float)s.c[0], (float)s.c[1], (float)s.c[2], (float)s.r};
+                out.sphere_meta[start + i] = I2{s.mat, s.order};
             }
         } else {
-            start = (uint32_t)(out.tris.size() / 4);
-            for (int i = leaf.first; i < leaf.first + leaf.count; i++) {
-                const HostTriangle& t = scene.tris[prims_storage[i].idx];
+            for (int i = 0; i < leaf.count; i++) {
+                const HostTriangle& t = scene.tris[prims_storage[leaf.first + i].idx];
                 double e1[3], e2[3], nrm[3];
                 for (int a = 0; a < 3; a++) {
                     e1[a] = t.v[1][a] - t.v[0][a];
@@ -365,44 +477,48 @@ void build_bvh(const HostScene& scene, FlatBvh& out) {
                 double len = std::sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
                 if (len == 0) nrm[0] = nrm[1] = nrm[2] = 0;
                 else for (int a = 0; a < 3; a++) nrm[a] /= len;
-                out.tris.push_back(F4{(float)t.v[0][0], (float)t.v[0][1], (float)t.v[0][2], as_float(t.mat)});
-                out.tris.push_back(F4{(float)e1[0], (float)e1[1], (float)e1[2], as_float(t.order)});
-                out.tris.push_back(F4{(float)e2[0], (float)e2[1], (float)e2[2], 0.f});
-                out.tris.push_back(F4{(float)nrm[0], (float)nrm[1], (float)nrm[2], 0.f});
+                F4* o = &out.tris[4 * (size_t)(start + i)];
+                o[0] = F4{(float)t.v[0][0], (float)t.v[0][1], (float)t.v[0][2], as_float(t.mat)};
+                o[1] = F4{(float)e1[0], (float)e1[1], (float)e1[2], as_float(t.order)};
+                o[2] = F4{(float)e2[0], (float)e2[1], (float)e2[2], 0.f};
+                o[3] = F4{(float)nrm[0], (float)nrm[1], (float)nrm[2], 0.f};
             }
         }
         uint32_t v = (start & kLeafStartMask) | ((uint32_t)(leaf.count - 1) << kLeafCountShift) | ((uint32_t)leaf.type << kLeafTypeBit);
         return (int32_t)~v;
     };
 
-    std::vector<int32_t> leaf_code(B.nodes.size(), 0);
-    std::vector<char> leaf_done(B.nodes.size(), 0);
-    for (int32_t fi = 0; fi < out.n_nodes; fi++) {
-        const BNode& nd = B.nodes[order[fi]];
-        float lo[2][3], hi[2][3];
-        int32_t child[2];
-        const int32_t kids[2] = {nd.left, nd.right};
-        for (int c = 0; c < 2; c++) {
-            const BNode& k = B.nodes[kids[c]];
-            for (int a = 0; a < 3; a++) {
-                lo[c][a] = round_down(k.lo[a] - pad);
-                hi[c][a] = round_up(k.hi[a] + pad);
-            }
-            if (k.left == -1) {
-                if (!leaf_done[kids[c]]) {
-                    leaf_code[kids[c]] = emit_leaf(k);
-                    leaf_done[kids[c]] = 1;
+    auto fill = [&](int32_t f0, int32_t f1) {
+        for (int32_t fi = f0; fi < f1; fi++) {
+            const BNode& nd = B.nodes[order[fi]];
+            float lo[2][3], hi[2][3];
+            int32_t child[2];
+            const int32_t kids[2] = {nd.left, nd.right};
+            for (int c = 0; c < 2; c++) {
+                const BNode& k = B.nodes[kids[c]];
+                for (int a = 0; a < 3; a++) {
+                    lo[c][a] = round_down(k.lo[a] - pad);
+                    hi[c][a] = round_up(k.hi[a] + pad);
                 }
-                child[c] = leaf_code[kids[c]];
-            } else {
-                child[c] = flat_index[kids[c]];
+                child[c] = k.left == -1 ? emit_leaf(k, (uint32_t)leaf_start[kids[c]]) : flat_index[kids[c]];
             }
+            out.nodes[(size_t)fi * 4 + 0] = F4{lo[0][0], hi[0][0], lo[0][1], hi[0][1]};
+            out.nodes[(size_t)fi * 4 + 1] = F4{lo[1][0], hi[1][0], lo[1][1], hi[1][1]};
+            out.nodes[(size_t)fi * 4 + 2] = F4{lo[0][2], hi[0][2], lo[1][2], hi[1][2]};
+            out.nodes[(size_t)fi * 4 + 3] = F4{as_float(child[0]), as_float(child[1]), 0.f, 0.f};
         }
-        out.nodes[(size_t)fi * 4 + 0] = F4{lo[0][0], hi[0][0], lo[0][1], hi[0][1]};
-        out.nodes[(size_t)fi * 4 + 1] = F4{lo[1][0], hi[1][0], lo[1][1], hi[1][1]};
-        out.nodes[(size_t)fi * 4 + 2] = F4{lo[0][2], hi[0][2], lo[1][2], hi[1][2]};
-        out.nodes[(size_t)fi * 4 + 3] = F4{as_float(child[0]), as_float(child[1]), 0.f, 0.f};
+    };
+    {
+        const unsigned nt = (parallel && out.n_nodes >= 32768) ? hw : 1u;
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nt; t++) {
+            const int32_t f0 = (int32_t)((long long)out.n_nodes * t / nt), f1 = (int32_t)((long long)out.n_nodes * (t + 1) / nt);
+            if (t + 1 < nt) pool.emplace_back(fill, f0, f1);
+            else fill(f0, f1);
+        }
+        for (auto& th : pool) th.join();
     }
+    lap("flatten");
     out.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 
