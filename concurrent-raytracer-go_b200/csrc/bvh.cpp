@@ -325,37 +325,48 @@ void build_bvh(const HostScene& scene, FlatBvh& out) {
     out = FlatBvh();
     Builder B;
     const int nS = (int)scene.spheres.size(), nT = (int)scene.tris.size();
-    std::vector<BPrim> prims_storage;
-    prims_storage.reserve((size_t)nS + nT);
+    std::vector<BPrim> prims_storage((size_t)nS + nT);
+    unsigned hw = std::thread::hardware_concurrency();
+    if (const char* e = getenv("GORT_BVH_THREADS")) hw = (unsigned)std::max(1, atoi(e));
+    auto prim_boxes = [&](int lo, int hi) {
+        for (int j = lo; j < hi; j++) {
+            BPrim& p = prims_storage[j];
+            if (j < nS) {
+                const HostSphere& s = scene.spheres[j];
+                const double r = std::fabs(s.r);
+                for (int a = 0; a < 3; a++) {
+                    p.lo[a] = s.c[a] - r;
+                    p.hi[a] = s.c[a] + r;
+                    p.c[a] = s.c[a];
+                }
+                p.type = 0;
+                p.idx = j;
+            } else {
+                const HostTriangle& t = scene.tris[j - nS];
+                for (int a = 0; a < 3; a++) {
+                    p.lo[a] = std::min(t.v[0][a], std::min(t.v[1][a], t.v[2][a]));
+                    p.hi[a] = std::max(t.v[0][a], std::max(t.v[1][a], t.v[2][a]));
+                    p.c[a] = 0.5 * (p.lo[a] + p.hi[a]);
+                }
+                p.type = 1;
+                p.idx = j - nS;
+            }
+        }
+    };
+    {
+        const int np = nS + nT;
+        const unsigned nt = (np >= 20000 && hw > 1) ? hw : 1u;
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nt; t++) {
+            const int lo = (int)((long long)np * t / nt), hi = (int)((long long)np * (t + 1) / nt);
+            if (t + 1 < nt) pool.emplace_back(prim_boxes, lo, hi);
+            else prim_boxes(lo, hi);
+        }
+        for (auto& th : pool) th.join();
+    }
     Box world;
     world.reset();
-    for (int i = 0; i < nS; i++) {
-        const HostSphere& s = scene.spheres[i];
-        BPrim p;
-        double r = std::fabs(s.r);
-        for (int a = 0; a < 3; a++) {
-            p.lo[a] = s.c[a] - r;
-            p.hi[a] = s.c[a] + r;
-            p.c[a] = s.c[a];
-        }
-        p.type = 0;
-        p.idx = i;
-        prims_storage.push_back(p);
-        world.grow(p.lo, p.hi);
-    }
-    for (int i = 0; i < nT; i++) {
-        const HostTriangle& t = scene.tris[i];
-        BPrim p;
-        for (int a = 0; a < 3; a++) {
-            p.lo[a] = std::min(t.v[0][a], std::min(t.v[1][a], t.v[2][a]));
-            p.hi[a] = std::max(t.v[0][a], std::max(t.v[1][a], t.v[2][a]));
-            p.c[a] = 0.5 * (p.lo[a] + p.hi[a]);
-        }
-        p.type = 1;
-        p.idx = i;
-        prims_storage.push_back(p);
-        world.grow(p.lo, p.hi);
-    }
+    for (const BPrim& p : prims_storage) world.grow(p.lo, p.hi);
     const int n = nS + nT;
     if (n == 0) return;
 
@@ -364,8 +375,6 @@ void build_bvh(const HostScene& scene, FlatBvh& out) {
     // the same as the sequential one: every split depends only on the primitives of its own range.
     B.prims_ptr = &prims_storage;
     B.nodes.reserve((size_t)n);
-    unsigned hw = std::thread::hardware_concurrency();
-    if (const char* e = getenv("GORT_BVH_THREADS")) hw = (unsigned)std::max(1, atoi(e));
     const bool parallel = n >= 20000 && hw > 1;
     if (parallel) B.defer_below = std::max(1024, n / 64);
     g_node_threads = parallel ? hw : 1u;  // the top of the tree scans its large ranges in parallel chunks
@@ -395,15 +404,35 @@ void build_bvh(const HostScene& scene, FlatBvh& out) {
         for (unsigned t = 1; t < nt; t++) pool.emplace_back(work);
         work();
         for (auto& th : pool) th.join();
+        // splice: subtree j's nodes go to [off[j], off[j] + size_j) of the top builder's node array (copied in parallel)
+        std::vector<int> off(nj);
+        size_t total = B.nodes.size();
         for (size_t j = 0; j < nj; j++) {
-            const int off = (int)B.nodes.size();
-            for (BNode nd : subs[j].nodes) {
-                if (nd.left >= 0) nd.left += off;
-                if (nd.right >= 0) nd.right += off;
-                B.nodes.push_back(nd);
+            off[j] = (int)total;
+            total += subs[j].nodes.size();
+        }
+        B.nodes.resize(total);
+        std::atomic<size_t> next_copy{0};
+        auto copy = [&]() {
+            for (;;) {
+                const size_t j = next_copy.fetch_add(1);
+                if (j >= nj) break;
+                BNode* dst = B.nodes.data() + off[j];
+                for (size_t i = 0; i < subs[j].nodes.size(); i++) {
+                    BNode nd = subs[j].nodes[i];
+                    if (nd.left >= 0) nd.left += off[j];
+                    if (nd.right >= 0) nd.right += off[j];
+                    dst[i] = nd;
+                }
             }
+        };
+        pool.clear();
+        for (unsigned t = 1; t < nt; t++) pool.emplace_back(copy);
+        copy();
+        for (auto& th : pool) th.join();
+        for (size_t j = 0; j < nj; j++) {
             const Deferred& d = B.deferred[j];
-            (d.which ? B.nodes[d.parent].right : B.nodes[d.parent].left) = sub_root[j] + off;
+            (d.which ? B.nodes[d.parent].right : B.nodes[d.parent].left) = sub_root[j] + off[j];
             B.max_depth = std::max(B.max_depth, subs[j].max_depth);
         }
     }
