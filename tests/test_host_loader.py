@@ -122,13 +122,16 @@ def test_parallel_bvh_build_equals_sequential(gort):
     primitive range, so the tree (inner nodes, depth, leaves, bytes) is the sequential one and passes the invariant check."""
     import json
     import os
-    d = Cm.random_sphere_scene(30000, 11, extent=40.0)
-    hs = gort.HostScene(json.dumps(d))
-    infos = []
-    for th in ("1", "7"):
-        os.environ["GORT_BVH_THREADS"] = th
-        try:
-            infos.append(hs.bvh_validate())
-        finally:
-            del os.environ["GORT_BVH_THREADS"]
-    assert infos[0] == infos[1] and infos[0]["leaves"] == infos[0]["nodes"] + 1
+    # 30 000: worker threads build the subtrees; 70 000: the top of the tree also scans its ranges (>= 65 536 primitives) in
+    # parallel chunks and the flatten pass fills the arrays in parallel
+    for n, seed in ((30000, 11), (70000, 12)):
+        d = Cm.random_sphere_scene(n, seed, extent=40.0)
+        hs = gort.HostScene(json.dumps(d))
+        infos = []
+        for th in ("1", "7"):
+            os.environ["GORT_BVH_THREADS"] = th
+            try:
+                infos.append(hs.bvh_validate())
+            finally:
+                del os.environ["GORT_BVH_THREADS"]
+        assert infos[0] == infos[1] and infos[0]["leaves"] == infos[0]["nodes"] + 1
