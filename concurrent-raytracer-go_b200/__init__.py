@@ -26,7 +26,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GORT_LIB") or os.path.join(_HERE, "lib", "libgort.so")  # GORT_LIB: A/B builds of the same ABI
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 TILE = 32
 CAMERA_REFERENCE, CAMERA_LOOKAT = 0, 1
 LOAD_PRISMS, LOAD_FOG = 1, 2
@@ -69,6 +69,7 @@ class SceneDesc(C.Structure):
         ("light_position", C.POINTER(C.c_double)), ("light_color", C.POINTER(C.c_double)), ("light_intensity", C.POINTER(C.c_double)),
         ("fog_enabled", C.c_int32), ("reserved5", C.c_int32),
         ("fog_density", C.c_double), ("fog_color", C.c_double * 3),
+        ("sky_enabled", C.c_int32), ("reserved6", C.c_int32), ("sky_params", C.c_double * 27),
     ]
 
 
@@ -99,6 +100,7 @@ class Stats(C.Structure):
         ("algorithmic_flops", C.c_double),
         ("soft_pairs_skipped", C.c_uint64),
         ("pairs_backfacing", C.c_uint64),
+        ("cull_ms", C.c_double), ("primary_generated", C.c_uint64), ("render_path", C.c_int32), ("kernel_launches", C.c_int32),
     ]
 
     def as_dict(self) -> dict:

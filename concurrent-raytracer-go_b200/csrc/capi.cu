@@ -16,6 +16,7 @@
 #include "bvh.h"
 #include "host_scene.h"
 #include "kernels.h"
+#include "stream.h"
 
 using namespace gort;
 
@@ -60,6 +61,14 @@ struct DeviceState {
     // cull pass, under the trace kernel; only the kept blocks wait for the end
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_cull = nullptr, ev_aux = nullptr;
+    cudaEvent_t ev_tc = nullptr;  // end of the cull pass (timing): trace_ms starts here
+    // global-queue wavefront pipeline (stream.cu): path / record / pair queues of one batch, counter ring, readback
+    uint8_t* d_stream = nullptr;
+    size_t stream_bytes = 0;
+    unsigned int* d_ctl = nullptr;     // 2 x kCtlWords + the frame's primary cursor (64 bit)
+    unsigned int* h_count = nullptr;   // pinned: {active deep, active other, first 6 counters of the iteration}
+    cudaEvent_t ev_count = nullptr;
+    int last_path = 0, last_launches = 0;
 };
 
 double now_ms() {
@@ -369,6 +378,104 @@ int validate(gort_ctx* ctx, const gort_render_params* p) {
     return GORT_OK;
 }
 
+
+// Which kernel family renders this scene (gort_stats::render_path): tiny sphere scenes scan the parameter bank, small BVH
+// scenes run the per-warp-queue kernel, large ones the global-queue wavefront pipeline (stream.h says why).
+// GORT_PATH=queue|stream overrides the size rule (tests render the same scene through both).
+enum RenderPath { kPathSmall = 0, kPathQueue = 1, kPathStream = 2 };
+
+int choose_path(const gort_ctx* ctx) {
+    const HostScene& hs = ctx->scene;
+    const size_t n_prims = hs.spheres.size() + hs.tris.size();
+    const bool small_ok = hs.tris.empty() && !hs.spheres.empty() && (int)hs.spheres.size() <= kSmallMax && (int)hs.mats.size() <= kSmallMax &&
+                          (int)hs.lights.size() <= kSmallLights;
+    const bool stream_ok = ctx->bvh.n_nodes > 0 && (int)hs.lights.size() <= kStreamLightChunk * kStreamMaxChunks;
+    const char* force = getenv("GORT_PATH");
+    if (force && !strcmp(force, "stream") && stream_ok) return kPathStream;
+    if (force && !strcmp(force, "queue")) return small_ok ? kPathSmall : kPathQueue;
+    if (small_ok) return kPathSmall;
+    const char* mp = getenv("GORT_STREAM_MIN_PRIMS");
+    const size_t min_prims = mp ? (size_t)atoll(mp) : 4096;
+    return (stream_ok && n_prims >= min_prims) ? kPathStream : kPathQueue;
+}
+
+// The wavefront pipeline for one device's share of the frame: batches of samples, one bounce at a time (stream.h).
+// Called after the cull pass has been enqueued on `st`.  Synchronises with the device once per bounce to learn whether
+// any path is still alive (the stages of the bounce are already enqueued by then, so the GPU does not idle).
+int run_stream(gort_ctx* ctx, DeviceState& d, const TraceParams& tp, const gort_render_params* p, cudaStream_t st) {
+    const bool stats = p->collect_stats != 0;
+    const int geom = (tp.scene.n_spheres > 0 ? 1 : 0) | (tp.scene.n_tris > 0 ? 2 : 0);
+    CUDA_TRY(ctx, cudaMemcpyAsync(d.h_count, d.d_counter + 1, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    const uint32_t n_deep = d.h_count[0], n_active = d.h_count[0] + d.h_count[1];
+    if (n_active == 0) return GORT_OK;
+    const uint64_t per_sample = (uint64_t)n_active * 32u;
+    const uint64_t prim_total = per_sample * (uint64_t)p->samples;
+    // path slots: every launch works on (up to) this many paths; the queue is topped up with new primary rays each iteration
+    const char* be = getenv("GORT_STREAM_BATCH");
+    const uint64_t want = be ? std::max<uint64_t>(1024, (uint64_t)atoll(be)) : (uint64_t)16 << 20;
+    const uint64_t cap = std::min<uint64_t>(std::min(want, prim_total), (uint64_t)1 << 26);
+
+    // carve the queues out of one allocation (grows only)
+    const size_t slot_bytes = stream_bytes_per_slot();
+    if (int rc = ensure(ctx, d.d_stream, d.stream_bytes, (size_t)cap * slot_bytes + 8192)) return rc;
+    StreamView v;
+    memset(&v, 0, sizeof(v));
+    {
+        uint8_t* q = d.d_stream;
+        auto take = [&](size_t bytes_per_slot) { uint8_t* r = q; q += ((size_t)cap * bytes_per_slot + 255) / 256 * 256; return r; };
+        for (int b = 0; b < 2; b++) {
+            v.qa[b] = (float4*)take(16); v.qb[b] = (float4*)take(16); v.qc[b] = (float4*)take(16); v.qd[b] = (uint2*)take(8);
+        }
+        v.ra = (float4*)take(16); v.rb = (float4*)take(16); v.rc = (float4*)take(16); v.racc = (float4*)take(16); v.rd = (uint2*)take(8);
+        v.lit = (uint8_t*)take(kStreamLightChunk);
+        v.cnt = (unsigned int*)take(4 * kStreamLightChunk);
+        v.hard_list = (uint32_t*)take(4 * kStreamLightChunk);
+        v.walk_list = (uint32_t*)take(4 * kStreamLightChunk);
+        if ((size_t)(q - d.d_stream) > d.stream_bytes) return fail(ctx, GORT_ERR_INVALID, "stream buffer carve-out overflow");
+    }
+    v.cap = (uint32_t)cap;
+    v.n_active = n_active; v.n_deep = n_deep;
+    v.prim_total = prim_total;
+    v.prim_cursor = reinterpret_cast<unsigned long long*>(d.d_ctl + 2 * kCtlWords);
+    const int n_lights = tp.scene.n_lights;
+    const int n_chunks = std::max(1, (n_lights + kStreamLightChunk - 1) / kStreamLightChunk);  // no lights: one pass adds the ambient term
+
+    // iteration i: scatter the current queue (paths of any depth) -> shade records + survivors in the next queue; top the
+    // next queue up with new primary rays; trace both; shade the records.  Ring of two counter blocks.
+    CUDA_TRY(ctx, cudaMemsetAsync(d.d_ctl, 0, (2 * kCtlWords + 2) * sizeof(unsigned int), st));
+    uint64_t generated = 0;
+    for (int it = 0;; it++) {
+        v.cur = it & 1;
+        v.ctl = d.d_ctl + (size_t)(it & 1) * kCtlWords;
+        v.ctl_prev = d.d_ctl + (size_t)((it & 1) ^ 1) * kCtlWords;
+        v.chunk = 0;
+        if (it > 0) {
+            CUDA_TRY(ctx, cudaMemsetAsync(v.ctl, 0, kCtlWords * sizeof(unsigned int), st));
+            CUDA_TRY(ctx, stream_launch_scatter(tp, v, geom, stats, d.sm_count, st));
+            d.last_launches++;
+        }
+        CUDA_TRY(ctx, stream_launch_plan(v, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(d.h_count + 2, v.ctl, 6 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaEventRecord(d.ev_count, st));
+        if (it > 0) CUDA_TRY(ctx, stream_launch_trace_ext(tp, v, geom, stats, d.sm_count, st));
+        if (generated < prim_total) CUDA_TRY(ctx, stream_launch_primary(tp, v, geom, stats, d.sm_count, st));
+        d.last_launches += 1 + (it > 0 ? 1 : 0) + (generated < prim_total ? 1 : 0);
+        if (it > 0) {
+            for (int c = 0; c < n_chunks; c++) {
+                v.chunk = c; v.l0 = c * kStreamLightChunk; v.lc = std::max(0, std::min(kStreamLightChunk, n_lights - v.l0));
+                v.last_chunk = c == n_chunks - 1;
+                CUDA_TRY(ctx, stream_launch_shade_chunk(tp, v, geom, stats, d.sm_count, st));
+                d.last_launches += tp.soft ? 5 : 3;
+            }
+        }
+        CUDA_TRY(ctx, cudaEventSynchronize(d.ev_count));
+        generated += d.h_count[2 + kCtlNew];
+        if (d.h_count[2 + kCtlNextTotal] == 0 && generated >= prim_total) break;  // nothing left to scatter, nothing left to generate
+    }
+    return GORT_OK;
+}
+
 // Enqueue one device's share of the frame: zero accumulators, trace, resolve into d.d_out.
 // eff_rank/eff_count: the tiles this device owns.  slab_mode: tile-major slab vs row-major frame.
 // out_override: write the resolved pixels there instead of d.d_out (device pointer on this device).
@@ -423,8 +530,10 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     tp.inv_w = 1.0f / (float)p->width; tp.inv_h = 1.0f / (float)p->height;
     // tiny sphere-only scenes: the spheres ride in the kernel parameters, in scan order
     tp.small_n = 0;
-    if (ctx->scene.tris.empty() && !ctx->scene.spheres.empty() && (int)ctx->scene.spheres.size() <= kSmallMax &&
-        (int)ctx->scene.mats.size() <= kSmallMax && (int)ctx->scene.lights.size() <= kSmallLights) {
+    const int path = choose_path(ctx);
+    d.last_path = path;
+    d.last_launches = 0;
+    if (path == kPathSmall) {
         std::vector<const HostSphere*> sorted;
         for (const HostSphere& hs : ctx->scene.spheres) sorted.push_back(&hs);
         std::sort(sorted.begin(), sorted.end(), [](const HostSphere* a, const HostSphere* b) { return a->order < b->order; });
@@ -489,6 +598,7 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     tp.fog_density = (float)ctx->scene.fog_density;
     tp.fog_r = (float)ctx->scene.fog_color[0]; tp.fog_g = (float)ctx->scene.fog_color[1]; tp.fog_b = (float)ctx->scene.fog_color[2];
     CUDA_TRY(ctx, launch_cull(tp, d.d_active, d.d_counter + 1, st));
+    CUDA_TRY(ctx, cudaEventRecord(d.ev_tc, st));
     ResolveParams rp;
     rp.block_active = tp.block_active;
     rp.accum = d.d_accum; rp.n_local_tiles = n_local; rp.shard_rank = eff_rank; rp.shard_count = eff_count;
@@ -508,7 +618,13 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
         CUDA_TRY(ctx, cudaEventRecord(d.ev_aux, d.aux_stream));
         rp.part = 2;
     }
-    CUDA_TRY(ctx, launch_trace(tp, p->collect_stats != 0, d.sm_count, st));
+    if (path == kPathStream) {
+        if (int rc = run_stream(ctx, d, tp, p, st)) return rc;
+    } else {
+        CUDA_TRY(ctx, launch_trace(tp, p->collect_stats != 0, d.sm_count, st));
+        d.last_launches++;
+    }
+    d.last_launches += 2 + (early ? 1 : 0);  // cull + resolve (+ the early pass over the culled blocks)
     CUDA_TRY(ctx, cudaEventRecord(d.ev[1], st));
 
     if (hooks && hooks->wait_flag) CUDA_TRY(ctx, launch_link_wait(hooks->wait_flag, hooks->wait_target, hooks->timed_out, st));
@@ -535,12 +651,16 @@ int collect_stats(gort_ctx* ctx, const gort_render_params* p, gort_stats* s, dou
         DeviceState& d = ctx->devs[i];
         CUDA_TRY(ctx, cudaSetDevice(d.dev));
         CUDA_TRY(ctx, cudaEventSynchronize(d.ev[2]));
-        float a = 0, b = 0;
-        CUDA_TRY(ctx, cudaEventElapsedTime(&a, d.ev[0], d.ev[1]));
+        float c = 0, a = 0, b = 0;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&c, d.ev[0], d.ev_tc));  // memsets + cull pass
+        CUDA_TRY(ctx, cudaEventElapsedTime(&a, d.ev_tc, d.ev[1]));  // the trace kernel(s) alone
         CUDA_TRY(ctx, cudaEventElapsedTime(&b, d.ev[1], d.ev[2]));
-        s->device_ms[i] = a + b;
-        if (i == 0) { s->trace_ms = a; s->resolve_ms = b; }
-        s->kernel_ms = std::max(s->kernel_ms, (double)(a + b));
+        s->device_ms[i] = c + a + b;
+        if (i == 0) {
+            s->cull_ms = c; s->trace_ms = a; s->resolve_ms = b;
+            s->render_path = d.last_path; s->kernel_launches = d.last_launches;
+        }
+        s->kernel_ms = std::max(s->kernel_ms, (double)(c + a + b));
         s->n_tiles += ctx->last_local_tiles[i];
         if (p->collect_stats) {
             unsigned long long h[kStatCount];
@@ -575,14 +695,17 @@ int collect_stats(gort_ctx* ctx, const gort_render_params* p, gort_stats* s, dou
         // SURVEY §8d operation costs (FMA = 2 flops): ray generation 12, AABB slab 24 (two per node),
         // sphere 23 miss / 47 hit, triangle 20/30/46/52 staged rejects / 92 accept, 30 per (hit, light)
         // set-up, 36 per soft-shadow direction, 50 per diffuse term, 45 per specular term, ~70 per
-        // scatter, 20 per pixel of tone-map; 30 per cone test of the soft-shadow candidate pass (this
-        // implementation's own pruning work, like the BVH slabs).
-        s->algorithmic_flops = 12.0 * (double)s->primary_rays + 48.0 * (double)s->nodes_visited +
+        // scatter; 30 per cone test of the soft-shadow candidate pass (this implementation's own pruning
+        // work, like the BVH slabs).
+        // Only work the trace kernels execute is counted: ray generation for the samples actually generated (the
+        // blocks the cull pass drops never produce a ray), no tone-map term (that is resolve_kernel's work).
+        s->primary_generated = tot[kStatPrimary];
+        s->algorithmic_flops = 12.0 * (double)s->primary_generated + 48.0 * (double)s->nodes_visited +
                                23.0 * (double)(s->sphere_tests - s->sphere_hits) + 47.0 * (double)s->sphere_hits +
                                20.0 * (double)s->tri_rejects[0] + 30.0 * (double)s->tri_rejects[1] + 46.0 * (double)s->tri_rejects[2] +
                                52.0 * (double)s->tri_rejects[3] + 92.0 * (double)s->tri_hits + 30.0 * (double)tot[kStatPairSetups] +
                                36.0 * (double)s->soft_shadow_rays + 50.0 * (double)s->diffuse_evals + 45.0 * (double)s->specular_evals +
-                               70.0 * (double)s->shaded_hits + 20.0 * (double)pixels + 30.0 * (double)s->cone_tests;
+                               70.0 * (double)s->shaded_hits + 30.0 * (double)s->cone_tests;
     }
     s->total_ms = now_ms() - t_start_ms;
     return GORT_OK;
@@ -627,6 +750,10 @@ int gort_create(const int* device_ids, int n_devices, gort_ctx** out) {
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.dev);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.own_stream, cudaStreamNonBlocking);
         for (int k = 0; k < 4 && e == cudaSuccess; k++) e = cudaEventCreate(&d.ev[k]);
+        if (e == cudaSuccess) e = cudaEventCreate(&d.ev_tc);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_count, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaMalloc(&d.d_ctl, (2 * kCtlWords + 4) * sizeof(unsigned int));
+        if (e == cudaSuccess) e = cudaMallocHost(&d.h_count, 64);
         if (e == cudaSuccess) e = cudaMalloc(&d.d_counter, 16);
         if (e == cudaSuccess) e = cudaMalloc(&d.d_stats, kStatCount * sizeof(unsigned long long));
         if (e == cudaSuccess && getenv("GORT_DEBUG_TIMES")) e = cudaMalloc(&d.d_debug, (1 + 16 * 148 * 64) * sizeof(unsigned long long));
@@ -670,6 +797,10 @@ void gort_destroy(gort_ctx* ctx) {
         if (d.aux_stream) { cudaStreamSynchronize(d.aux_stream); cudaStreamDestroy(d.aux_stream); }
         if (d.ev_cull) cudaEventDestroy(d.ev_cull);
         if (d.ev_aux) cudaEventDestroy(d.ev_aux);
+        if (d.ev_tc) cudaEventDestroy(d.ev_tc);
+        if (d.ev_count) cudaEventDestroy(d.ev_count);
+        cudaFree(d.d_stream); cudaFree(d.d_ctl);
+        if (d.h_count) cudaFreeHost(d.h_count);
         if (d.own_stream) cudaStreamDestroy(d.own_stream);
     }
     delete ctx;
@@ -833,7 +964,7 @@ static int render_frame_device(gort_ctx* ctx, const gort_render_params* p, uint8
             CUDA_TRY(ctx, cudaSetDevice(ctx->devs[0].dev));
             CUDA_TRY(ctx, cudaEventElapsedTime(&g, ctx->devs[0].ev[0], ctx->devs[0].ev[3]));
             stats_out->kernel_ms = std::max(stats_out->kernel_ms, (double)g);
-            stats_out->resolve_ms = g - stats_out->trace_ms;
+            stats_out->resolve_ms = g - stats_out->trace_ms - stats_out->cull_ms;
         }
     }
     return GORT_OK;
@@ -947,7 +1078,7 @@ int gort_render(gort_ctx* ctx, const gort_render_params* p, uint8_t* rgba_out, s
             CUDA_TRY(ctx, cudaSetDevice(lead.dev));
             CUDA_TRY(ctx, cudaEventElapsedTime(&g, lead.ev[0], lead.ev[3]));
             stats_out->kernel_ms = std::max(stats_out->kernel_ms, (double)g);
-            stats_out->resolve_ms = g - stats_out->trace_ms;
+            stats_out->resolve_ms = g - stats_out->trace_ms - stats_out->cull_ms;
         }
         stats_out->total_ms = now_ms() - t0;
     }

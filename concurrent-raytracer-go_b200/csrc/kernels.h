@@ -44,7 +44,8 @@ enum StatIndex {
     kStatSoftSkipped = 29,  // lit (hit, light) pairs whose shadow cone is empty: factor 16/16 without casting the 16 rays
     kStatBackfacing = 30,   // (hit, light) pairs with hit.Normal . lightDir <= 0: cosTheta = 0 zeroes both lighting terms, no shadow rays
     kStatPairSetups = 31,   // (hit, light) pairs whose light direction / distance set-up ran and that were not back-facing
-    kStatCount = 32
+    kStatPrimary = 32,      // primary rays actually generated (samples of the pixel blocks the cull pass kept)
+    kStatCount = 33
 };
 
 struct DevCamera {

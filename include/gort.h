@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GORT_ABI_VERSION 2u /* 2: gort_stats grew by soft_pairs_skipped and pairs_backfacing */
+#define GORT_ABI_VERSION 3u /* 3: sky extension in gort_scene_desc; gort_stats: cull_ms, primary_generated, render_path, kernel_launches */
 #define GORT_MAX_DEVICES 8
 #define GORT_TILE 32 /* createRenderTasks tileSize, renderer.go:401 */
 
@@ -115,6 +115,15 @@ typedef struct gort_scene_desc {
     int32_t reserved5;
     double fog_density;
     double fog_color[3];
+
+    /* extension (second half): sky gradient as the colour of a ray that leaves the scene, after
+     * AtmosphereConfig.GetSkyColor (internal/atmosphere/atmosphere.go:100-135; the reference never calls it: a miss is
+     * black, renderer.go:171-173).  0 = reference behaviour.  sky_params = the AtmosphereConfig fields in declaration order
+     * (atmosphere.go:8-26): SkyColorTop[3] SkyColorBottom[3] SunDirection[3] SunColor[3] SunIntensity SunSize
+     * RayleighScattering[3] MieScattering[3] AtmosphericDepth FogDensity FogColor[3] HazeIntensity TimeOfDay. */
+    int32_t sky_enabled;
+    int32_t reserved6;
+    double sky_params[27];
 } gort_scene_desc;
 
 /* ParallelRenderer fields (renderer.go:20-29) + the additive knobs of this implementation. */
@@ -169,6 +178,12 @@ typedef struct gort_stats {
                                   * (renderer.go:326-328) without casting the 16 rays */
     uint64_t pairs_backfacing;   /* (hit, light) pairs with hit.Normal . lightDir <= 0: cosTheta = 0 (renderer.go:259) zeroes the
                                   * diffuse and specular terms, so no shadow ray is cast for them */
+    double cull_ms;              /* the beam-cull pass (device 0); trace_ms no longer includes it */
+    uint64_t primary_generated;  /* collect_stats: primary rays actually generated (samples of the pixel blocks the cull pass
+                                  * kept); primary_rays - primary_generated samples were resolved as misses without a ray */
+    int32_t render_path;         /* 0 parameter-bank scan (tiny sphere scenes), 1 per-warp-queue BVH kernel, 2 global-queue
+                                  * wavefront pipeline (large scenes) */
+    int32_t kernel_launches;     /* kernels of libgort launched for this frame on device 0 */
 } gort_stats;
 
 typedef struct gort_ctx gort_ctx;

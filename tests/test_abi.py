@@ -26,7 +26,7 @@ def test_header_symbols_exported(gort):
 
 
 def test_abi_version(gort):
-    assert gort.load_library().gort_abi_version() == gort.ABI_VERSION == 2
+    assert gort.load_library().gort_abi_version() == gort.ABI_VERSION == 3
 
 
 def test_struct_sizes_match_header(gort):
