@@ -478,7 +478,20 @@ void build_bvh(const HostScene& scene, FlatBvh& out) {
         }
     }
     out.n_nodes = (int32_t)order.size();
-    out.nodes.resize((size_t)out.n_nodes * 4);
+    out.nodes.resize((size_t)out.n_nodes * 6);
+    // 16-bit grid over the (padded) world box, two spare cells on every side
+    double qo[3], qc[3];
+    for (int a = 0; a < 3; a++) {
+        const double lo = world.lo[a] - pad, hi = world.hi[a] + pad;
+        qc[a] = std::max((hi - lo) / 65520.0, 1e-30);
+        qo[a] = lo - 8.0 * qc[a];
+        out.qcell[a] = (float)qc[a];
+        out.qorigin[a] = (float)qo[a];
+        // the kernel decodes with the float values: quantise against exactly those
+        qc[a] = (double)out.qcell[a];
+        qo[a] = (double)out.qorigin[a];
+    }
+    F4* qbase = out.nodes.data() + (size_t)out.n_nodes * 4;
     out.spheres.resize(n_sph_out);
     out.sphere_meta.resize(n_sph_out);
     out.tris.resize((size_t)n_tri_out * 4);
@@ -535,6 +548,18 @@ void build_bvh(const HostScene& scene, FlatBvh& out) {
             out.nodes[(size_t)fi * 4 + 1] = F4{lo[1][0], hi[1][0], lo[1][1], hi[1][1]};
             out.nodes[(size_t)fi * 4 + 2] = F4{lo[0][2], hi[0][2], lo[1][2], hi[1][2]};
             out.nodes[(size_t)fi * 4 + 3] = F4{as_float(child[0]), as_float(child[1]), 0.f, 0.f};
+            uint32_t qw[2][4];
+            for (int c = 0; c < 2; c++) {
+                for (int a = 0; a < 3; a++) {
+                    const double ql = std::floor(((double)lo[c][a] - qo[a]) / qc[a]) - 2.0, qh = std::ceil(((double)hi[c][a] - qo[a]) / qc[a]) + 2.0;
+                    const uint32_t l = (uint32_t)std::min(65535.0, std::max(0.0, ql)), h = (uint32_t)std::min(65535.0, std::max(0.0, qh));
+                    qw[c][a] = l | (h << 16);
+                }
+                qw[c][3] = (uint32_t)child[c];
+            }
+            auto bits = [](uint32_t u) { float f; memcpy(&f, &u, 4); return f; };
+            qbase[(size_t)fi * 2 + 0] = F4{bits(qw[0][0]), bits(qw[0][1]), bits(qw[0][2]), bits(qw[0][3])};
+            qbase[(size_t)fi * 2 + 1] = F4{bits(qw[1][0]), bits(qw[1][1]), bits(qw[1][2]), bits(qw[1][3])};
         }
     };
     {

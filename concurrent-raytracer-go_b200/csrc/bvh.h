@@ -40,10 +40,14 @@ constexpr int kMaxLeafPrims = 4;
 constexpr int kMaxBvhDepth = 56;  // traversal stack is 64 entries
 
 struct FlatBvh {
-    std::vector<F4> nodes;        // 4 per inner node
+    std::vector<F4> nodes;        // 4 per inner node, followed by the quantised copy (2 per inner node, see qorigin)
     std::vector<F4> spheres;      // 1 per sphere
     std::vector<I2> sphere_meta;  // (material, order)
     std::vector<F4> tris;         // 4 per triangle
+    // Quantised copy of the nodes for the wavefront pipeline's walk (stream.cu): 32 bytes per node = ONE 256-bit load,
+    //   word k (k = 0..2: x, y, z) of child c: lo | hi << 16 on the grid  coordinate = qorigin[k] + q * qcell[k];  word 3: the child link
+    // boxes are rounded outward by two cells, so a quantised box always contains the fp32 box (same hits, a few more visits)
+    float qorigin[3] = {0, 0, 0}, qcell[3] = {1, 1, 1};
     int32_t n_nodes = 0;
     int32_t max_depth = 0;
     double build_ms = 0;

@@ -432,6 +432,8 @@ int run_stream(gort_ctx* ctx, DeviceState& d, const TraceParams& tp, const gort_
         v.cnt = (unsigned int*)take(4 * kStreamLightChunk);
         v.hard_list = (uint32_t*)take(4 * kStreamLightChunk);
         v.walk_list = (uint32_t*)take(4 * kStreamLightChunk);
+        v.lit_list = (uint32_t*)take(4 * kStreamLightChunk);
+        v.cand_recs = (uint4*)take(32 * kStreamLightChunk);
         if ((size_t)(q - d.d_stream) > d.stream_bytes) return fail(ctx, GORT_ERR_INVALID, "stream buffer carve-out overflow");
     }
     v.cap = (uint32_t)cap;
@@ -466,7 +468,7 @@ int run_stream(gort_ctx* ctx, DeviceState& d, const TraceParams& tp, const gort_
                 v.chunk = c; v.l0 = c * kStreamLightChunk; v.lc = std::max(0, std::min(kStreamLightChunk, n_lights - v.l0));
                 v.last_chunk = c == n_chunks - 1;
                 CUDA_TRY(ctx, stream_launch_shade_chunk(tp, v, geom, stats, d.sm_count, st));
-                d.last_launches += tp.soft ? 5 : 3;
+                d.last_launches += tp.soft ? 6 : 3;
             }
         }
         CUDA_TRY(ctx, cudaEventSynchronize(d.ev_count));
@@ -525,6 +527,8 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     tp.scene.mats = d.d_mats; tp.scene.lights = d.d_lights;
     tp.scene.n_nodes = ctx->bvh.n_nodes; tp.scene.n_lights = (int)ctx->scene.lights.size();
     tp.scene.n_spheres = (int)ctx->scene.spheres.size(); tp.scene.n_tris = (int)ctx->scene.tris.size();
+    tp.scene.qox = ctx->bvh.qorigin[0]; tp.scene.qoy = ctx->bvh.qorigin[1]; tp.scene.qoz = ctx->bvh.qorigin[2];
+    tp.scene.qcx = ctx->bvh.qcell[0]; tp.scene.qcy = ctx->bvh.qcell[1]; tp.scene.qcz = ctx->bvh.qcell[2];
     tp.cam = make_camera(ctx->scene, p->camera_mode);
     tp.width = p->width; tp.height = p->height; tp.samples = p->samples; tp.max_depth = p->max_depth;
     tp.inv_w = 1.0f / (float)p->width; tp.inv_h = 1.0f / (float)p->height;
@@ -1276,6 +1280,7 @@ int gort_trace_rays(gort_ctx* ctx, int32_t n, const double* origins3, const doub
     sv.nodes = d.d_nodes; sv.spheres = d.d_spheres; sv.sphere_meta = d.d_meta; sv.tris = d.d_tris; sv.mats = d.d_mats; sv.lights = d.d_lights;
     sv.n_nodes = ctx->bvh.n_nodes; sv.n_lights = (int)ctx->scene.lights.size();
     sv.n_spheres = (int)ctx->scene.spheres.size(); sv.n_tris = (int)ctx->scene.tris.size();
+    sv.qox = sv.qoy = sv.qoz = 0.f; sv.qcx = sv.qcy = sv.qcz = 1.f;  // (the test hook walks the fp32 nodes)
     const float tmax_f = std::isinf(t_max) ? INFINITY : (float)t_max;
     CUDA_TRY(ctx, launch_trace_rays(sv, n, d_o, d_d, (float)t_min, tmax_f, any_hit, d_t, d_ord, st));
     std::vector<float> ht(n);

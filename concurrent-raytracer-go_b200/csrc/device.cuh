@@ -467,6 +467,60 @@ __device__ __forceinline__ float tangent_threshold(float a_dot_n, float ox, floa
 constexpr int kMaxCand = 6;           // candidate primitives kept per (hit, light) pair on BVH scenes
 constexpr uint32_t kCandOverflow = 0xFFu;  // more than kMaxCand: the pair's rays walk the BVH themselves
 
+// One child box of a BVH node against the shadow cone of a (hit, light) pair (apex o, unit axis a, range tmax): the box is
+// tested through its bounding sphere, and dropped when it lies wholly below the hit point's tangent plane (thr).
+__device__ __forceinline__ bool cone_box_hit(float lox, float hix, float loy, float hiy, float loz, float hiz, float ox, float oy, float oz, float ax,
+                                             float ay, float az, float tmax, float nx, float ny, float nz, float thr) {
+    const float ex = 0.5f * (hix - lox), ey = 0.5f * (hiy - loy), ez = 0.5f * (hiz - loz);
+    const float vx = fmaf(0.5f, hix + lox, -ox), vy = fmaf(0.5f, hiy + loy, -oy), vz = fmaf(0.5f, hiz + loz, -oz);
+    const float rb2 = dot3(ex, ey, ez, ex, ey, ez);
+    const float rb = rb2 * rsqrt_fast(fmaxf(rb2, 1e-30f)) * 1.00001f + 1e-6f;
+    const float dv2 = dot3(vx, vy, vz, vx, vy, vz);
+    const float inv_dv = rsqrt_fast(fmaxf(dv2, 1e-30f));
+    const float dv = dv2 * inv_dv;
+    const float ca = dot3(ax, ay, az, vx, vy, vz) * inv_dv;
+    const float sphi = fminf(1.0f, rb * inv_dv);
+    const float cphi = sqrt_fast(fmaxf(0.f, fmaf(-sphi, sphi, 1.0f)));
+    bool hit = (dv <= rb) || (ca >= fmaf(kConeCos, cphi, -kConeSin * sphi) - 1e-4f);
+    if (dv - rb > fmaf(tmax, 1.00001f, 1e-5f)) hit = false;
+    if (!(ex >= 0.f)) hit = false;  // inverted box = empty child
+    // highest point of the box above the hit point's tangent plane (see tangent_threshold)
+    const float top = fmaxf(nx * (lox - ox), nx * (hix - ox)) + fmaxf(ny * (loy - oy), ny * (hiy - oy)) + fmaxf(nz * (loz - oz), nz * (hiz - oz));
+    if (top < thr) hit = false;
+    return hit;
+}
+
+// One leaf primitive against the cone: false only if no ray of the cone can hit it within [tMin, tmax].
+template <int GEOM = 3>
+__device__ __forceinline__ bool cone_prim_keep(const SceneView& S, bool is_tri, uint32_t idx, float ox, float oy, float oz, float ax, float ay, float az,
+                                               float tmax, float nx, float ny, float nz, float thr) {
+    bool keep = true;
+    if (!is_tri) {
+        const float4 s = ldg4(S.spheres + idx);
+        keep = cone_sphere_candidate(s.x - ox, s.y - oy, s.z - oz, fabsf(s.w), ax, ay, az, tmax);
+        if (dot3(nx, ny, nz, s.x - ox, s.y - oy, s.z - oz) + fabsf(s.w) < thr) keep = false;  // behind the tangent plane
+    } else {
+        // the triangle's plane: a cone whose every ray moves away from it (or crosses it below
+        // tMin when the apex lies on it — the hit point's own face) cannot hit the triangle
+        const float4* tp = S.tris + 4 * (size_t)idx;
+        const float4 v0 = ldg4(tp), nn = ldg4(tp + 3);
+        const float hgt = dot3(nn.x, nn.y, nn.z, ox - v0.x, oy - v0.y, oz - v0.z);
+        const float x = dot3(nn.x, nn.y, nn.z, ax, ay, az);  // n . d ranges over [x - 0.105, x + 0.105]
+        const float eps = 2e-5f + 1e-6f * (fabsf(ox) + fabsf(oy) + fabsf(oz) + fabsf(v0.x) + fabsf(v0.y) + fabsf(v0.z));
+        if (hgt > eps) keep = !(x - 0.105f >= 0.f);
+        else if (hgt < -eps) keep = !(x + 0.105f <= 0.f);
+        else keep = !(fabsf(x) - 0.105f > fmaxf(0.03f, 1000.0f * eps));
+        if (keep && thr > -3.0e38f) {
+            // all three vertices below the tangent-plane threshold (see tangent_threshold)
+            const float4 e1 = ldg4(tp + 1), e2 = ldg4(tp + 2);
+            const float h0 = dot3(nx, ny, nz, v0.x - ox, v0.y - oy, v0.z - oz);
+            const float h1 = h0 + dot3(nx, ny, nz, e1.x, e1.y, e1.z), h2 = h0 + dot3(nx, ny, nz, e2.x, e2.y, e2.z);
+            if (fmaxf(h0, fmaxf(h1, h2)) < thr) keep = false;
+        }
+    }
+    return keep;
+}
+
 // Walk the BVH with the cone (apex o, unit axis a, range tmax); boxes are tested through their bounding
 // spheres.  Writes up to kMaxCand primitive references (sphere: index; triangle: index | 0x80000000) and
 // returns their number, or kCandOverflow.
@@ -483,36 +537,15 @@ __device__ __forceinline__ uint32_t cone_candidates(const SceneView& S, float ox
             stat_add<STATS>(st, kStatConeTests, 2);
             const float4* np = S.nodes + 4 * (size_t)node;
             const float4 n0 = ldg4(np), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3);
-            bool h[2];
-#pragma unroll
-            for (int c = 0; c < 2; c++) {
-                const float lox = c ? n1.x : n0.x, hix = c ? n1.y : n0.y, loy = c ? n1.z : n0.z, hiy = c ? n1.w : n0.w;
-                const float loz = c ? n2.z : n2.x, hiz = c ? n2.w : n2.y;
-                const float ex = 0.5f * (hix - lox), ey = 0.5f * (hiy - loy), ez = 0.5f * (hiz - loz);
-                const float vx = fmaf(0.5f, hix + lox, -ox), vy = fmaf(0.5f, hiy + loy, -oy), vz = fmaf(0.5f, hiz + loz, -oz);
-                const float rb2 = dot3(ex, ey, ez, ex, ey, ez);
-                const float rb = rb2 * rsqrt_fast(fmaxf(rb2, 1e-30f)) * 1.00001f + 1e-6f;
-                const float dv2 = dot3(vx, vy, vz, vx, vy, vz);
-                const float inv_dv = rsqrt_fast(fmaxf(dv2, 1e-30f));
-                const float dv = dv2 * inv_dv;
-                const float ca = dot3(ax, ay, az, vx, vy, vz) * inv_dv;
-                const float sphi = fminf(1.0f, rb * inv_dv);
-                const float cphi = sqrt_fast(fmaxf(0.f, fmaf(-sphi, sphi, 1.0f)));
-                bool hit = (dv <= rb) || (ca >= fmaf(kConeCos, cphi, -kConeSin * sphi) - 1e-4f);
-                if (dv - rb > fmaf(tmax, 1.00001f, 1e-5f)) hit = false;
-                if (!(ex >= 0.f)) hit = false;  // inverted box = empty child
-                // highest point of the box above the hit point's tangent plane (see tangent_threshold)
-                const float top = fmaxf(nx * (lox - ox), nx * (hix - ox)) + fmaxf(ny * (loy - oy), ny * (hiy - oy)) + fmaxf(nz * (loz - oz), nz * (hiz - oz));
-                if (top < thr) hit = false;
-                h[c] = hit;
-            }
+            const bool h0 = cone_box_hit(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, ox, oy, oz, ax, ay, az, tmax, nx, ny, nz, thr);
+            const bool h1 = cone_box_hit(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, ox, oy, oz, ax, ay, az, tmax, nx, ny, nz, thr);
             const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
-            if (h[0] && h[1]) {
+            if (h0 && h1) {
                 stack[sp++] = c1;
                 node = c0;
-            } else if (h[0]) {
+            } else if (h0) {
                 node = c0;
-            } else if (h[1]) {
+            } else if (h1) {
                 node = c1;
             } else {
                 if (sp == 0) break;
@@ -524,32 +557,8 @@ __device__ __forceinline__ uint32_t cone_candidates(const SceneView& S, float ox
             const int cnt = (int)((v >> 26) & 15u) + 1;
             const bool is_tri = GEOM == 2 || (GEOM == 3 && ((v >> 30) & 1u) != 0);
             for (int i = 0; i < cnt; i++) {
-                bool keep = true;
                 stat_add<STATS>(st, kStatConeTests);
-                if (!is_tri) {
-                    const float4 s = ldg4(S.spheres + start + i);
-                    keep = cone_sphere_candidate(s.x - ox, s.y - oy, s.z - oz, fabsf(s.w), ax, ay, az, tmax);
-                    if (dot3(nx, ny, nz, s.x - ox, s.y - oy, s.z - oz) + fabsf(s.w) < thr) keep = false;  // behind the tangent plane
-                } else {
-                    // the triangle's plane: a cone whose every ray moves away from it (or crosses it below
-                    // tMin when the apex lies on it — the hit point's own face) cannot hit the triangle
-                    const float4* tp = S.tris + 4 * (size_t)(start + i);
-                    const float4 v0 = ldg4(tp), nn = ldg4(tp + 3);
-                    const float hgt = dot3(nn.x, nn.y, nn.z, ox - v0.x, oy - v0.y, oz - v0.z);
-                    const float x = dot3(nn.x, nn.y, nn.z, ax, ay, az);  // n . d ranges over [x - 0.105, x + 0.105]
-                    const float eps = 2e-5f + 1e-6f * (fabsf(ox) + fabsf(oy) + fabsf(oz) + fabsf(v0.x) + fabsf(v0.y) + fabsf(v0.z));
-                    if (hgt > eps) keep = !(x - 0.105f >= 0.f);
-                    else if (hgt < -eps) keep = !(x + 0.105f <= 0.f);
-                    else keep = !(fabsf(x) - 0.105f > fmaxf(0.03f, 1000.0f * eps));
-                    if (keep && thr > -3.0e38f) {
-                        // all three vertices below the tangent-plane threshold (see tangent_threshold)
-                        const float4 e1 = ldg4(tp + 1), e2 = ldg4(tp + 2);
-                        const float h0 = dot3(nx, ny, nz, v0.x - ox, v0.y - oy, v0.z - oz);
-                        const float h1 = h0 + dot3(nx, ny, nz, e1.x, e1.y, e1.z), h2 = h0 + dot3(nx, ny, nz, e2.x, e2.y, e2.z);
-                        if (fmaxf(h0, fmaxf(h1, h2)) < thr) keep = false;
-                    }
-                }
-                if (keep) {
+                if (cone_prim_keep<GEOM>(S, is_tri, start + i, ox, oy, oz, ax, ay, az, tmax, nx, ny, nz, thr)) {
                     if (n >= (uint32_t)kMaxCand) return kCandOverflow;
                     out[n++] = (start + i) | (is_tri ? 0x80000000u : 0u);
                 }

@@ -65,6 +65,8 @@ struct SceneView {
     int n_nodes;
     int n_lights;
     int n_spheres, n_tris;
+    // quantised copy of the nodes behind the fp32 ones (nodes + 4 n_nodes, 32 bytes each; bvh.h): grid origin and cell size
+    float qox, qoy, qoz, qcx, qcy, qcz;
 };
 
 struct TraceParams {

@@ -5,13 +5,27 @@
 // those of kernels.cu (trace_kernel), stage by stage; the reference lines are cited there and again here.
 #include "stream.h"
 
+#include <cooperative_groups.h>
+
 #include "device.cuh"
 
 namespace gort {
 
 constexpr uint32_t kDeadPrim = 0x7FFFFFFFu;  // qa.w of a path that ended (miss, no scatter, depth, dead-path cut)
-constexpr int kPoolRefill = 8;               // pool_trace refills as soon as this many lanes of a warp are idle
-constexpr uint32_t kPoolChunk = 128;         // rays a warp takes from the global cursor at a time
+#ifndef GORT_POOL_REFILL
+#define GORT_POOL_REFILL 8
+#endif
+#ifndef GORT_POOL_CHUNK
+#define GORT_POOL_CHUNK 128
+#endif
+#ifndef GORT_POOL_QNODES
+#define GORT_POOL_QNODES 1
+#endif
+#ifndef GORT_POOL_MINB
+#define GORT_POOL_MINB 10
+#endif
+constexpr int kPoolRefill = GORT_POOL_REFILL;      // pool_trace refills as soon as this many lanes of a warp are idle
+constexpr uint32_t kPoolChunk = GORT_POOL_CHUNK;   // rays a warp takes from the global cursor at a time
 constexpr int kLC = kStreamLightChunk;
 
 enum PoolSrc { SRC_PRIMARY = 0, SRC_EXT = 1, SRC_HARD = 2, SRC_SOFT = 3 };
@@ -59,7 +73,7 @@ __device__ __forceinline__ void light_dir(const float4 L0, float ox, float oy, f
 // ANY sources (shadow rays) stop at the first accepted primitive.
 // ---------------------------------------------------------------------------------------------
 template <int SRC, bool STATS, int GEOM>
-__global__ void __launch_bounds__(128, 8) pool_trace_kernel(const __grid_constant__ TraceParams P, const __grid_constant__ StreamView V) {
+__global__ void __launch_bounds__(128, GORT_POOL_MINB) pool_trace_kernel(const __grid_constant__ TraceParams P, const __grid_constant__ StreamView V) {
     constexpr bool ANY = SRC == SRC_HARD || SRC == SRC_SOFT;
     const SceneView& S = P.scene;
     const int lane = threadIdx.x & 31;
@@ -83,7 +97,11 @@ __global__ void __launch_bounds__(128, 8) pool_trace_kernel(const __grid_constan
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t chunk = total >= n_warps * kPoolChunk ? kPoolChunk : max(32u, ((total / n_warps) + 31u) & ~31u);
 
+#if GORT_POOL_QNODES
+    const float4* __restrict__ nodes = S.nodes + 4 * (size_t)S.n_nodes;  // the quantised copy: 32 bytes per node
+#else
     const float4* __restrict__ nodes = S.nodes;
+#endif
     const float4* __restrict__ spheres = GEOM != 2 ? S.spheres : nullptr;
     const float4* __restrict__ tris = GEOM != 1 ? S.tris : nullptr;
 
@@ -196,7 +214,17 @@ __global__ void __launch_bounds__(128, 8) pool_trace_kernel(const __grid_constan
                         idx = rcp_fast(fabsf(q.dx) > ooeps ? q.dx : copysignf(ooeps, q.dx));
                         idy = rcp_fast(fabsf(q.dy) > ooeps ? q.dy : copysignf(ooeps, q.dy));
                         idz = rcp_fast(fabsf(q.dz) > ooeps ? q.dz : copysignf(ooeps, q.dz));
+#if GORT_POOL_QNODES
+                        // slab distance of grid plane k: (origin + k cell - o) / d = k (cell / d) + (origin - o) / d.  The node's
+                        // 16-bit k becomes the float 2^23 + k by OR-ing it into the mantissa of 2^23 (no conversion instruction);
+                        // the 2^23 is taken out again through the additive term.  That term's rounding moves the distance by at
+                        // most half a cell: the builder rounds every box outward by two.
+                        oodx = (q.ox - S.qox) * idx; oody = (q.oy - S.qoy) * idy; oodz = (q.oz - S.qoz) * idz;
+                        idx *= S.qcx; idy *= S.qcy; idz *= S.qcz;
+                        oodx = fmaf(8388608.0f, idx, oodx); oody = fmaf(8388608.0f, idy, oody); oodz = fmaf(8388608.0f, idz, oodz);
+#else
                         oodx = q.ox * idx; oody = q.oy * idy; oodz = q.oz * idz;
+#endif
                         sp = 0;
                         node = 0;
                         have = true;
@@ -217,6 +245,23 @@ __global__ void __launch_bounds__(128, 8) pool_trace_kernel(const __grid_constan
             if (node >= 0) {
                 stat_add<STATS>(st, kStatNodes);
                 stat_add<STATS>(st, kStatWalkLane0 + SRC);
+#if GORT_POOL_QNODES
+                float4 w0, w1;
+                ldg8(nodes + 2 * (size_t)node, w0, w1);
+                const uint32_t magic = 0x4B000000u;  // 2^23
+#define GORT_QLO(w) __uint_as_float((__float_as_uint(w) & 0xffffu) | magic)
+#define GORT_QHI(w) __uint_as_float(__byte_perm(__float_as_uint(w), magic, 0x7632))
+                const float c0lox = fmaf(GORT_QLO(w0.x), idx, -oodx), c0hix = fmaf(GORT_QHI(w0.x), idx, -oodx);
+                const float c0loy = fmaf(GORT_QLO(w0.y), idy, -oody), c0hiy = fmaf(GORT_QHI(w0.y), idy, -oody);
+                const float c0loz = fmaf(GORT_QLO(w0.z), idz, -oodz), c0hiz = fmaf(GORT_QHI(w0.z), idz, -oodz);
+                const float c1lox = fmaf(GORT_QLO(w1.x), idx, -oodx), c1hix = fmaf(GORT_QHI(w1.x), idx, -oodx);
+                const float c1loy = fmaf(GORT_QLO(w1.y), idy, -oody), c1hiy = fmaf(GORT_QHI(w1.y), idy, -oody);
+                const float c1loz = fmaf(GORT_QLO(w1.z), idz, -oodz), c1hiz = fmaf(GORT_QHI(w1.z), idz, -oodz);
+#undef GORT_QLO
+#undef GORT_QHI
+                float4 n3;
+                n3.x = w0.w; n3.y = w1.w;
+#else
                 const float4* np = nodes + 4 * (size_t)node;
                 float4 n0, n1, n2, n3;
                 ldg8(np, n0, n1);
@@ -227,6 +272,7 @@ __global__ void __launch_bounds__(128, 8) pool_trace_kernel(const __grid_constan
                 const float c1lox = fmaf(n1.x, idx, -oodx), c1hix = fmaf(n1.y, idx, -oodx);
                 const float c1loy = fmaf(n1.z, idy, -oody), c1hiy = fmaf(n1.w, idy, -oody);
                 const float c1loz = fmaf(n2.z, idz, -oodz), c1hiz = fmaf(n2.w, idz, -oodz);
+#endif
                 const float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), q.tmin));
                 const float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), q.tbest));
                 const float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), q.tmin));
@@ -289,6 +335,13 @@ __global__ void __launch_bounds__(128, 8) pool_trace_kernel(const __grid_constan
                     if (!q.found) {
                         const uint32_t e = __ldg(V.hard_list + my);
                         V.lit[(size_t)(e & 0x3FFFFFFFu) * kLC + (e >> 30)] = 1;
+                        if (P.soft) {  // a lit pair casts its 16 jittered rays (renderer.go:311): queue its cone walk
+                            namespace cg = cooperative_groups;
+                            cg::coalesced_group g = cg::coalesced_threads();
+                            uint32_t lb = 0;
+                            if (g.thread_rank() == 0) lb = atomicAdd(V.ctl + cb + kCtlLit, g.size());
+                            V.lit_list[g.shfl(lb, 0) + g.thread_rank()] = e;
+                        }
                     }
                 } else {
                     if (!q.found) {
@@ -538,144 +591,232 @@ __global__ void __launch_bounds__(128) stream_pair_setup_kernel(const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------
-// soft_setup: calculateSmartShadow's 16 jittered rays (renderer.go:311-328) for the lit pairs of a warp's 32 records,
-// as the C phase of trace_kernel's shade stage: one cone walk per pair collects its candidate primitives; an empty
-// cone is 16/16 without rays; <= kMaxCand candidates are tested by a quarter warp per pair (two rays per lane from
-// one Philox block); pairs with more go to the walk list (pool_trace<SOFT>).
+// pool_cone: the shadow-cone walk of every lit (record, light) pair (soft-shadow candidate culling, device.cuh), with the
+// same lane refill as pool_trace — a cone walk ends after a handful of nodes (empty cone) or at the seventh candidate, so
+// statically assigned lanes sat idle 28 of 32 (profiles/r2_ncu_pool_c4_v2.txt: 4.4 lanes per instruction).
+// A finished pair goes one of three ways (calculateSmartShadow, renderer.go:311-328):
+//   no candidate        all 16 jittered rays are unoccluded: cnt = 16, no rays
+//   1..kMaxCand         a 32-byte record (pair, count, candidates) for soft_cand
+//   more                the walk list: its 16 rays walk the BVH (pool_trace<SOFT>)
 // ---------------------------------------------------------------------------------------------
-struct SoftShared {
-    uint16_t pairs[kLC * 32];
-    uint8_t ncand[32];
-    uint8_t sel[32];
-    uint32_t cand[32][kMaxCand];
-};
-
 template <bool STATS, int GEOM>
-__global__ void __launch_bounds__(128) stream_soft_setup_kernel(const __grid_constant__ TraceParams P, const __grid_constant__ StreamView V) {
-    __shared__ SoftShared wsh[4];
-    SoftShared& W = wsh[threadIdx.x >> 5];
+__global__ void __launch_bounds__(128, GORT_POOL_MINB) pool_cone_kernel(const __grid_constant__ TraceParams P, const __grid_constant__ StreamView V) {
+    namespace cg = cooperative_groups;
     const SceneView& S = P.scene;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     Stats st;
     stats_zero<STATS>(st);
-    const uint32_t n_rec = V.ctl[kCtlRec];
     const int cb = kCtlChunk0 + 8 * V.chunk;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t base = warp * 32u; base < n_rec; base += n_warps * 32u) {
-        const bool act = base + lane < n_rec;
-        int np = 0;
-        for (int li = 0; li < V.lc; li++) {
-            const bool bit = act && V.lit[(size_t)(base + lane) * kLC + li] == 1;
-            const unsigned m = __ballot_sync(FULL_MASK, bit);
-            if (bit) W.pairs[np + __popc(m & lt_mask)] = (uint16_t)((li << 8) | lane);
-            np += __popc(m);
-        }
-        __syncwarp();
-        for (int p0 = 0; p0 < np; p0 += 32) {
-            const int pc = min(32, np - p0);
-            // lane = pair: one cone walk collects the pair's candidate primitives
-            uint32_t nc_mine = 0;
-            if (lane < pc) {
-                const int pr = (int)W.pairs[p0 + lane];
-                const uint32_t rec = base + (uint32_t)(pr & 31);
-                const float4 a = __ldg(V.ra + rec), n = __ldg(V.rb + rec);
-                const float4 L0 = light4<false>(P, V.l0 + (pr >> 8), 0);
-                float ax = L0.x - a.x, ay = L0.y - a.y, az = L0.z - a.z;
-                const float dist2 = dot3(ax, ay, az, ax, ay, az);
-                const float inv_d = rsqrt_fast(dist2);
-                ax *= inv_d; ay *= inv_d; az *= inv_d;
-                const float thr = tangent_threshold(dot3(n.x, n.y, n.z, ax, ay, az), a.x, a.y, a.z);
-                nc_mine = P.no_cone_cull ? kCandOverflow
-                                         : cone_candidates<STATS, GEOM>(S, a.x, a.y, a.z, ax, ay, az, dist2 * inv_d, n.x, n.y, n.z, thr, W.cand[lane], st);
-                W.ncand[lane] = (uint8_t)nc_mine;
-                // an empty cone: all 16 rays are unoccluded whatever their jitter (shadowFactor = 16/16, renderer.go:326-328)
-                if (nc_mine == 0) {
-                    V.cnt[(size_t)rec * kLC + (pr >> 8)] = 16u;
-                    stat_add<STATS>(st, kStatSoftSkipped);
+    const uint32_t total = V.ctl[cb + kCtlLit];
+    unsigned int* fetch = V.ctl + cb + kCtlFetchCone;
+    if (total == 0) return;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t chunk = total >= n_warps * kPoolChunk ? kPoolChunk : max(32u, ((total / n_warps) + 31u) & ~31u);
+    const float4* __restrict__ nodes = S.nodes;
+
+    uint32_t wnext = 0, wend = 0;
+    bool pool_done = false, have = false;
+    uint32_t e = 0;  // the lane's pair: record | light-in-chunk << 30
+    float ox = 0.f, oy = 0.f, oz = 0.f, ax = 0.f, ay = 0.f, az = 0.f, tmax = 0.f, nx = 0.f, ny = 0.f, nz = 0.f, thr = 0.f;
+    uint32_t n = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
+    int stack[64];
+    int sp = 0, node = 0;
+
+    for (;;) {
+        const unsigned act = __ballot_sync(FULL_MASK, have);
+        if (!pool_done && __popc(act) <= 32 - kPoolRefill) {
+            if (wnext >= wend) {
+                uint32_t b = total;
+                if (lane == 0 && *reinterpret_cast<volatile unsigned int*>(fetch) < total) b = atomicAdd(fetch, chunk);
+                b = __shfl_sync(FULL_MASK, b, 0);
+                if (b >= total) {
+                    pool_done = true;
+                } else {
+                    wnext = b;
+                    wend = min(b + chunk, total);
                 }
             }
-            // more candidates than the list holds: the pair's 16 rays walk the BVH (pool_trace<SOFT>)
-            const bool over = lane < pc && nc_mine == kCandOverflow;
-            const unsigned om = __ballot_sync(FULL_MASK, over);
-            if (om) {
-                uint32_t wb = 0;
-                if (lane == 0) wb = atomicAdd(V.ctl + cb + kCtlWalk, (unsigned int)__popc(om));
-                wb = __shfl_sync(FULL_MASK, wb, 0);
-                if (over) {
-                    const int pr = (int)W.pairs[p0 + lane];
-                    V.walk_list[wb + (uint32_t)__popc(om & lt_mask)] = (base + (uint32_t)(pr & 31)) | ((uint32_t)(pr >> 8) << 30);
-                }
-            }
-            // the pairs that test their 16 rays against the candidates, compacted: sel[k] = slot of the k-th of them
-            const bool mine = lane < pc && nc_mine != 0 && nc_mine != kCandOverflow;
-            const unsigned need = __ballot_sync(FULL_MASK, mine);
-            if (mine) W.sel[__popc(need & lt_mask)] = (uint8_t)lane;
-            const int pc_rays = __popc(need);
-            __syncwarp();
-            // a quarter warp per pair; lane & 7 = k handles shadow samples 2k and 2k+1 (renderer.go:313)
-            for (int q0 = 0; q0 < pc_rays; q0 += 4) {
-                const int qk = q0 + (lane >> 3);
-                const bool valid = qk < pc_rays;
-                const int qi = valid ? (int)W.sel[qk] : 0;
-                const int pr = valid ? (int)W.pairs[p0 + qi] : 0;
-                const int li = pr >> 8;
-                const uint32_t rec = base + (uint32_t)(pr & 31);
-                bool unA = false, unB = false;
-                if (valid) {
-                    const float4 a = __ldg(V.ra + rec);
-                    const float ox = a.x, oy = a.y, oz = a.z;
-                    const float4 L0 = light4<false>(P, V.l0 + li, 0);
-                    float ax = L0.x - ox, ay = L0.y - oy, az = L0.z - oz;
+            if (!pool_done) {
+                const unsigned idle = ~act;
+                const uint32_t avail = wend - wnext;
+                const uint32_t r = (uint32_t)__popc(idle & lt_mask);
+                if (!have && r < avail) {
+                    e = V.lit_list[wnext + r];
+                    const uint32_t rec = e & 0x3FFFFFFFu;
+                    const float4 a = __ldg(V.ra + rec), nn = __ldg(V.rb + rec);
+                    const float4 L0 = light4<false>(P, V.l0 + (int)(e >> 30), 0);
+                    ox = a.x; oy = a.y; oz = a.z;
+                    ax = L0.x - ox; ay = L0.y - oy; az = L0.z - oz;
                     const float dist2 = dot3(ax, ay, az, ax, ay, az);
                     const float inv_d = rsqrt_fast(dist2);
-                    const float dist = dist2 * inv_d;
                     ax *= inv_d; ay *= inv_d; az *= inv_d;
-                    const uint32_t sdw = __float_as_uint(__ldg(V.rb + rec).w);
-                    const uint4 rb = philox(P.rk, __ldg(V.rd + rec).x, sdw & 0xffffu, ((sdw >> 16) << 8) | kStreamShadow,
-                                            ((uint32_t)(V.l0 + li) << 12) | ((uint32_t)(lane & 7) << 8));
-                    stat_add<STATS>(st, kStatRngBlocks);
-                    stat_add<STATS>(st, kStatSoftRays, 2);
-                    stat_add<STATS>(st, kStatShadow, 2);
-                    float bx, by, bz;
-                    ball_from_bits(rb.x, rb.y, bx, by, bz);
-                    float dxa = fmaf(0.1f, bx, ax), dya = fmaf(0.1f, by, ay), dza = fmaf(0.1f, bz, az);
-                    normalize3(dxa, dya, dza);
-                    ball_from_bits(rb.z, rb.w, bx, by, bz);
-                    float dxb = fmaf(0.1f, bx, ax), dyb = fmaf(0.1f, by, ay), dzb = fmaf(0.1f, bz, az);
-                    normalize3(dxb, dyb, dzb);
-                    bool occA = false, occB = false;
-                    const uint32_t nc = W.ncand[qi];
-                    for (uint32_t k = 0; k < nc; k++) {
-                        const uint32_t ref = W.cand[qi][k];
-                        if (GEOM == 2 || (GEOM == 3 && (ref & 0x80000000u))) {
-                            const float4* tp = S.tris + 4 * (size_t)(ref & 0x7fffffffu);
-                            const bool ha = tri_occludes(tp, ox, oy, oz, dxa, dya, dza, 0.001f, dist);
-                            const bool hb = tri_occludes(tp, ox, oy, oz, dxb, dyb, dzb, 0.001f, dist);
-                            if (STATS) {
-                                stat_add<STATS>(st, kStatTriTests, 2);
-                                stat_add<STATS>(st, ha ? kStatTriHits : kStatTriRejA);  // rejects counted at the cheapest stage
-                                stat_add<STATS>(st, hb ? kStatTriHits : kStatTriRejA);
-                            }
-                            occA = occA || ha;
-                            occB = occB || hb;
-                        } else {
-                            stat_add<STATS>(st, kStatSphereTests, 2);
-                            const float4 s = ldg4(S.spheres + ref);
-                            occA = occA || sphere_occludes_unit(s, ox, oy, oz, dxa, dya, dza, 0.001f, dist);
-                            occB = occB || sphere_occludes_unit(s, ox, oy, oz, dxb, dyb, dzb, 0.001f, dist);
-                        }
+                    tmax = dist2 * inv_d;
+                    nx = nn.x; ny = nn.y; nz = nn.z;
+                    thr = tangent_threshold(dot3(nx, ny, nz, ax, ay, az), ox, oy, oz);
+                    if (P.no_cone_cull) {  // test switch: every pair's rays walk the BVH
+                        cg::coalesced_group g = cg::coalesced_threads();
+                        uint32_t wb = 0;
+                        if (g.thread_rank() == 0) wb = atomicAdd(V.ctl + cb + kCtlWalk, g.size());
+                        V.walk_list[g.shfl(wb, 0) + g.thread_rank()] = e;
+                    } else {
+                        n = 0; sp = 0; node = 0;
+                        have = true;
                     }
-                    unA = !occA;
-                    unB = !occB;
                 }
-                const unsigned ua = __ballot_sync(FULL_MASK, unA), ub = __ballot_sync(FULL_MASK, unB);
-                if (valid && (lane & 7) == 0) {
-                    const int sh = lane & 24;
-                    V.cnt[(size_t)rec * kLC + li] = (unsigned int)(__popc((ua >> sh) & 0xFFu) + __popc((ub >> sh) & 0xFFu));
+                wnext += min((uint32_t)__popc(idle), avail);
+                continue;
+            }
+        }
+        if (act == 0) break;
+
+        if (have) {
+            bool fin = false, over = false;
+            if (node >= 0) {
+                stat_add<STATS>(st, kStatConeTests, 2);
+                const float4* np = nodes + 4 * (size_t)node;
+                float4 n0, n1, n2, n3;
+                ldg8(np, n0, n1);
+                ldg8(np + 2, n2, n3);
+                const bool h0 = cone_box_hit(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, ox, oy, oz, ax, ay, az, tmax, nx, ny, nz, thr);
+                const bool h1 = cone_box_hit(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, ox, oy, oz, ax, ay, az, tmax, nx, ny, nz, thr);
+                const int k0 = __float_as_int(n3.x), k1 = __float_as_int(n3.y);
+                if (h0 && h1) {
+                    stack[sp++] = k1;
+                    node = k0;
+                } else if (h0) {
+                    node = k0;
+                } else if (h1) {
+                    node = k1;
+                } else {
+                    if (sp == 0) fin = true;
+                    else node = stack[--sp];
+                }
+            } else {
+                const uint32_t v = ~(uint32_t)node;
+                const uint32_t start = v & 0x3FFFFFFu;
+                const int cnt = (int)((v >> 26) & 15u) + 1;
+                const bool is_tri = GEOM == 2 || (GEOM == 3 && ((v >> 30) & 1u) != 0);
+                for (int i = 0; i < cnt && !over; i++) {
+                    stat_add<STATS>(st, kStatConeTests);
+                    if (cone_prim_keep<GEOM>(S, is_tri, start + i, ox, oy, oz, ax, ay, az, tmax, nx, ny, nz, thr)) {
+                        const uint32_t ref = (start + i) | (is_tri ? 0x80000000u : 0u);
+                        if (n >= (uint32_t)kMaxCand) over = true;
+                        else if (n == 0) c0 = ref;
+                        else if (n == 1) c1 = ref;
+                        else if (n == 2) c2 = ref;
+                        else if (n == 3) c3 = ref;
+                        else if (n == 4) c4 = ref;
+                        else c5 = ref;
+                        if (!over) n++;
+                    }
+                }
+                if (over || sp == 0) fin = true;
+                else node = stack[--sp];
+            }
+            if (fin) {
+                have = false;
+                if (over) {
+                    cg::coalesced_group g = cg::coalesced_threads();
+                    uint32_t wb = 0;
+                    if (g.thread_rank() == 0) wb = atomicAdd(V.ctl + cb + kCtlWalk, g.size());
+                    V.walk_list[g.shfl(wb, 0) + g.thread_rank()] = e;
+                } else if (n == 0) {
+                    // an empty cone: all 16 rays are unoccluded whatever their jitter (shadowFactor = 16/16, renderer.go:326-328)
+                    V.cnt[(size_t)(e & 0x3FFFFFFFu) * kLC + (e >> 30)] = 16u;
+                    stat_add<STATS>(st, kStatSoftSkipped);
+                } else {
+                    cg::coalesced_group g = cg::coalesced_threads();
+                    uint32_t wb = 0;
+                    if (g.thread_rank() == 0) wb = atomicAdd(V.ctl + cb + kCtlCand, g.size());
+                    const size_t slot = (size_t)g.shfl(wb, 0) + g.thread_rank();
+                    V.cand_recs[2 * slot] = make_uint4(e, n, c0, c1);
+                    V.cand_recs[2 * slot + 1] = make_uint4(c2, c3, c4, c5);
                 }
             }
-            __syncwarp();
+        }
+    }
+    stats_flush<STATS>(P, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// soft_cand: the 16 jittered rays (renderer.go:311-328) of the pairs with 1..kMaxCand candidates, tested against the
+// candidates only: a quarter warp per pair; lane & 7 = k handles shadow samples 2k and 2k+1 from one Philox block
+// (the C phase of trace_kernel's shade stage).
+// ---------------------------------------------------------------------------------------------
+template <bool STATS, int GEOM>
+__global__ void __launch_bounds__(128) stream_soft_cand_kernel(const __grid_constant__ TraceParams P, const __grid_constant__ StreamView V) {
+    const SceneView& S = P.scene;
+    const int lane = threadIdx.x & 31;
+    Stats st;
+    stats_zero<STATS>(st);
+    const int cb = kCtlChunk0 + 8 * V.chunk;
+    const uint32_t n_pairs = V.ctl[cb + kCtlCand];
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t base = warp * 4u; base < n_pairs; base += n_warps * 4u) {
+        const uint32_t qk = base + (uint32_t)(lane >> 3);
+        const bool valid = qk < n_pairs;
+        bool unA = false, unB = false;
+        uint32_t rec = 0;
+        int li = 0;
+        if (valid) {
+            const uint4 r0 = __ldg(V.cand_recs + 2 * (size_t)qk), r1 = __ldg(V.cand_recs + 2 * (size_t)qk + 1);
+            rec = r0.x & 0x3FFFFFFFu;
+            li = (int)(r0.x >> 30);
+            const uint32_t nc = r0.y;
+            const uint32_t cand[kMaxCand] = {r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+            const float4 a = __ldg(V.ra + rec);
+            const float ox = a.x, oy = a.y, oz = a.z;
+            const float4 L0 = light4<false>(P, V.l0 + li, 0);
+            float ax = L0.x - ox, ay = L0.y - oy, az = L0.z - oz;
+            const float dist2 = dot3(ax, ay, az, ax, ay, az);
+            const float inv_d = rsqrt_fast(dist2);
+            const float dist = dist2 * inv_d;
+            ax *= inv_d; ay *= inv_d; az *= inv_d;
+            const uint32_t sdw = __float_as_uint(__ldg(V.rb + rec).w);
+            const uint4 rb = philox(P.rk, __ldg(V.rd + rec).x, sdw & 0xffffu, ((sdw >> 16) << 8) | kStreamShadow,
+                                    ((uint32_t)(V.l0 + li) << 12) | ((uint32_t)(lane & 7) << 8));
+            stat_add<STATS>(st, kStatRngBlocks);
+            stat_add<STATS>(st, kStatSoftRays, 2);
+            stat_add<STATS>(st, kStatShadow, 2);
+            float bx, by, bz;
+            ball_from_bits(rb.x, rb.y, bx, by, bz);
+            float dxa = fmaf(0.1f, bx, ax), dya = fmaf(0.1f, by, ay), dza = fmaf(0.1f, bz, az);
+            normalize3(dxa, dya, dza);
+            ball_from_bits(rb.z, rb.w, bx, by, bz);
+            float dxb = fmaf(0.1f, bx, ax), dyb = fmaf(0.1f, by, ay), dzb = fmaf(0.1f, bz, az);
+            normalize3(dxb, dyb, dzb);
+            bool occA = false, occB = false;
+#pragma unroll
+            for (uint32_t k = 0; k < (uint32_t)kMaxCand; k++) {
+                if (k < nc) {
+                    const uint32_t ref = cand[k];
+                    if (GEOM == 2 || (GEOM == 3 && (ref & 0x80000000u))) {
+                        const float4* tp = S.tris + 4 * (size_t)(ref & 0x7fffffffu);
+                        const bool ha = tri_occludes(tp, ox, oy, oz, dxa, dya, dza, 0.001f, dist);
+                        const bool hb = tri_occludes(tp, ox, oy, oz, dxb, dyb, dzb, 0.001f, dist);
+                        if (STATS) {
+                            stat_add<STATS>(st, kStatTriTests, 2);
+                            stat_add<STATS>(st, ha ? kStatTriHits : kStatTriRejA);  // rejects counted at the cheapest stage
+                            stat_add<STATS>(st, hb ? kStatTriHits : kStatTriRejA);
+                        }
+                        occA = occA || ha;
+                        occB = occB || hb;
+                    } else {
+                        stat_add<STATS>(st, kStatSphereTests, 2);
+                        const float4 s = ldg4(S.spheres + ref);
+                        occA = occA || sphere_occludes_unit(s, ox, oy, oz, dxa, dya, dza, 0.001f, dist);
+                        occB = occB || sphere_occludes_unit(s, ox, oy, oz, dxb, dyb, dzb, 0.001f, dist);
+                    }
+                }
+            }
+            unA = !occA;
+            unB = !occB;
+        }
+        const unsigned ua = __ballot_sync(FULL_MASK, unA), ub = __ballot_sync(FULL_MASK, unB);
+        if (valid && (lane & 7) == 0) {
+            const int sh = lane & 24;
+            V.cnt[(size_t)rec * kLC + li] = (unsigned int)(__popc((ua >> sh) & 0xFFu) + __popc((ub >> sh) & 0xFFu));
         }
     }
     stats_flush<STATS>(P, st);
@@ -779,7 +920,7 @@ cudaError_t stream_launch_plan(const StreamView& v, cudaStream_t st) {
 // launchers
 // ---------------------------------------------------------------------------------------------
 size_t stream_bytes_per_slot() {
-    return 2 * (3 * sizeof(float4) + sizeof(uint2)) + 4 * sizeof(float4) + sizeof(uint2) + kLC * (1 + 4 + 4 + 4);
+    return 2 * (3 * sizeof(float4) + sizeof(uint2)) + 4 * sizeof(float4) + sizeof(uint2) + kLC * (1 + 4 + 4 + 4 + 4 + 32);
 }
 
 template <int SRC, bool STATS, int GEOM>
@@ -810,6 +951,35 @@ static cudaError_t launch_pool_variant(const TraceParams& p, const StreamView& v
         case 1: return launch_pool<SRC, false, 1>(p, v, sm_count, st);
         case 2: return launch_pool<SRC, false, 2>(p, v, sm_count, st);
         default: return launch_pool<SRC, false, 3>(p, v, sm_count, st);
+    }
+}
+
+template <bool STATS, int GEOM>
+static cudaError_t launch_cone_variant(const TraceParams& p, const StreamView& v, int sm_count, cudaStream_t st) {
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+        cudaFuncSetAttribute(pool_cone_kernel<STATS, GEOM>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+        int n = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, pool_cone_kernel<STATS, GEOM>, 128, 0);
+        if (e != cudaSuccess) return e;
+        ctas_per_sm = n > 0 ? n : 1;
+    }
+    pool_cone_kernel<STATS, GEOM><<<sm_count * ctas_per_sm, 128, 0, st>>>(p, v);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_cone(const TraceParams& p, const StreamView& v, int geom, bool stats, int sm_count, cudaStream_t st) {
+    if (stats) {
+        switch (geom) {
+            case 1: return launch_cone_variant<true, 1>(p, v, sm_count, st);
+            case 2: return launch_cone_variant<true, 2>(p, v, sm_count, st);
+            default: return launch_cone_variant<true, 3>(p, v, sm_count, st);
+        }
+    }
+    switch (geom) {
+        case 1: return launch_cone_variant<false, 1>(p, v, sm_count, st);
+        case 2: return launch_cone_variant<false, 2>(p, v, sm_count, st);
+        default: return launch_cone_variant<false, 3>(p, v, sm_count, st);
     }
 }
 
@@ -848,7 +1018,9 @@ cudaError_t stream_launch_shade_chunk(const TraceParams& p, const StreamView& v,
     e = launch_pool_variant<SRC_HARD>(p, v, geom, stats, sm_count, st);
     if (e != cudaSuccess) return e;
     if (p.soft) {
-        GORT_GEOM_DISPATCH(stream_soft_setup_kernel, grid)
+        e = launch_cone(p, v, geom, stats, sm_count, st);
+        if (e != cudaSuccess) return e;
+        GORT_GEOM_DISPATCH(stream_soft_cand_kernel, grid)
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         e = launch_pool_variant<SRC_SOFT>(p, v, geom, stats, sm_count, st);

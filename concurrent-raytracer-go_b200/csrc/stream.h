@@ -17,7 +17,8 @@
 //     per chunk of <= 4 lights:
 //       pair_setup        light direction, back-facing cull, hard-shadow ray list             (:248-257,303-309)
 //       pool_trace<HARD>  calculateSmartShadow's hard ray (boolean hitWorld)
-//       soft_setup        shadow-cone candidates of every lit pair; 16 jittered rays against <= 6 candidates (:311-328)
+//       pool_cone         shadow-cone walk of every lit pair: its candidate primitives (device.cuh), lanes refilled
+//       soft_cand         16 jittered rays against <= 6 candidates, a quarter warp per pair             (:311-328)
 //       pool_trace<SOFT>  the 16 rays of the pairs whose cone holds more than that, through the BVH
 //       shade_accum       calculateDirectLighting's arithmetic + traceRay's weighting, one fixed-point add per hit (:258-297,191-226)
 //
@@ -44,7 +45,10 @@ enum StreamCtl {
     kCtlNextTotal = 5,  // kCtlNext + kCtlNew: entries of the next queue
     kCtlPrimStart = 6,  // (two words, low first) index of the first new primary ray in the frame's primary sequence
     kCtlChunk0 = 8,     // per light chunk c at kCtlChunk0 + 8 c:
-    kCtlHard = 0, kCtlFetchHard = 1, kCtlWalk = 2, kCtlFetchWalk = 3
+    kCtlHard = 0, kCtlFetchHard = 1, kCtlWalk = 2, kCtlFetchWalk = 3,
+    kCtlLit = 4,        // lit pairs (hard shadow ray unoccluded) == cone walks of pool_cone
+    kCtlFetchCone = 5,
+    kCtlCand = 6        // pairs with 1..6 shadow-cone candidates (records of soft_cand)
 };
 
 struct StreamView {
@@ -65,6 +69,8 @@ struct StreamView {
     unsigned int* cnt;       // [cap * 4] unoccluded soft shadow rays (of 16)
     uint32_t* hard_list;     // [cap * 4] record | light-in-chunk << 30
     uint32_t* walk_list;     // [cap * 4] lit pairs whose 16 rays walk the BVH themselves
+    uint32_t* lit_list;      // [cap * 4] lit pairs, in the order their hard shadow rays finished
+    uint4* cand_recs;        // [cap * 4] x 2: (pair, candidate count, candidates 0-1) (candidates 2-5)
     unsigned int* ctl;       // this iteration's counter block
     const unsigned int* ctl_prev;  // previous iteration's block (kCtlNextTotal = entries of the current queue)
     unsigned long long* prim_cursor;  // primary rays of the frame generated so far
