@@ -51,6 +51,14 @@ WORKLOADS = {
 }
 
 
+def config_of(wl, world, link):
+    """the `config` object of a bench line: identical keys and values for the GPU arm and the reference arm"""
+    kind, W, H, spp, depth, options, desc = wl
+    return {"workload": desc, "width": W, "height": H, "samples": spp, "max_depth": depth, "camera_mode": "reference",
+            "anti_aliasing": kind != "c3", "soft_shadows": kind != "c3", "recursive_reflections": True,
+            "prism_extension": bool(options & 1), "fog_extension": bool(options & 2)}
+
+
 class Workload:
     """Scene of a workload for both arms: .flat(G) -> gort FlatScene (the gort_scene_desc a Go host would
     pass after Flatten()); .oracle(O) -> the oracle's scene built independently from the same description."""
@@ -173,7 +181,7 @@ def run_reference(args, wl):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "camera_mode": "reference"},
+        "config": config_of(wl, 1, None),
         "pixels_per_second": value * 1e6 / s_spp,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "note": "C++ -O2 float64 transcription of the Go renderer (no Go toolchain here); GOMAXPROCS n/a, threads = %d" % cores},
@@ -191,6 +199,7 @@ def main():
     ap.add_argument("--impl", default="gort", choices=["gort", "reference"])
     ap.add_argument("--workload", default="c1_view", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-scale-c5", action="store_true", help="skip the 4K 1 M-primitive sub-record of the default line")
     ap.add_argument("--gather", default="link", choices=["link", "nccl"], help="N > 1: how the frame is assembled on rank 0")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "gort" else args.warmup
@@ -260,11 +269,13 @@ def main():
     host_frame = torch.zeros(W * H * 4, dtype=torch.uint8).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    launches_per_frame = [3]  # cull + trace + resolve; replaced by gort_stats.kernel_launches of the measured frame below
+
     def step_device():
         """one frame, everything resident in HBM; returns number of kernels launched"""
         if world == 1:
             r.RenderDevice(W, H, frame.data_ptr())
-            return 3  # cull + trace + resolve (libgort kernels; memsets and the L2 flush are not counted)
+            return launches_per_frame[0]  # libgort kernels (memsets and the L2 flush are not counted)
         if link is not None:
             r.RenderLinked(W, H, link)
             return 5  # (release | -) + cull + trace + (- | wait) + resolve + (wait | signal)
@@ -305,6 +316,8 @@ def main():
     for _ in range(args.warmup):
         step_device()
     barrier()
+    if world == 1:
+        launches_per_frame[0] = int(r.RenderDevice(W, H, frame.data_ptr(), want_stats=True).kernel_launches)
 
     # ---- timed: K steps, device events per step, L2 flushed between steps (outside the events) ----
     sampler = ClockSampler(local_rank)
@@ -383,6 +396,13 @@ def main():
         e2e_value = rays * args.steps / e2e_s / 1e6
         tr = sum(trace_ms) / len(trace_ms)
         achieved = (st.algorithmic_flops / (tr * 1e-3)) / 1e12
+        # measured FLOPs of the same kernel(s): ncu smsp__sass_thread_inst_executed_op_{fadd,fmul,ffma}_pred_on of the committed
+        # capture (tools/gpu_round.sh writes profiles/flops.json: fadd + fmul + 2 ffma per launch)
+        measured = None
+        try:
+            measured = json.load(open(os.path.join(ROOT, "profiles", "flops.json"))).get(args.workload)
+        except (OSError, ValueError):
+            pass
         h2d = int(st.bvh_bytes + flat.desc.n_materials * 64 + flat.desc.n_lights * 32)
         traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of trace_kernel from the committed ncu capture
         try:
@@ -403,10 +423,11 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "width": W, "height": H, "samples": spp, "max_depth": depth,
-                       "camera_mode": "reference", "l2": "flushed between timed steps (256 MiB fill outside the events)",
-                       "sharding": ("tile_id %% %d == rank, " % world + ("tiles stored into rank 0's frame over NVLink peer memory (frame link)" if link is not None else "NCCL all-gather of RGBA8 slabs")) if world > 1 else "single GPU",
-                       "rng": "philox4x32-10 seed 20240601"},
+            "config": config_of(wl, world, link),
+            "run": {"l2": "flushed between timed steps (256 MiB fill outside the events)",
+                    "sharding": ("tile_id %% %d == rank, " % world + ("tiles stored into rank 0's frame over NVLink peer memory (frame link)" if link is not None else "NCCL all-gather of RGBA8 slabs")) if world > 1 else "single GPU",
+                    "rng": "philox4x32-10 seed 20240601",
+                    "render_path": {0: "parameter-bank scan (per-warp-queue kernel)", 1: "per-warp-queue BVH kernel", 2: "global-queue wavefront pipeline"}[st.render_path]},
             "pixels_per_second": value * 1e6 / spp,
             "ray_segments_per_second": segs / (ms_per_step * 1e-3),
             "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps,
@@ -415,23 +436,125 @@ def main():
                     "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": launches,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-                         "traffic": traffic, "kernel": "trace_kernel", "kernel_ms": tr, "algorithmic_flops_per_launch": st.algorithmic_flops,
+                         "traffic": traffic,
+                         "kernel": "trace_kernel" if st.render_path != 2 else "wavefront pipeline (pool_trace / pool_cone / scatter / shade kernels of one frame)",
+                         "kernel_ms": tr, "cull_ms": st.cull_ms, "algorithmic_flops_per_launch": st.algorithmic_flops,
+                         "flops_model": "SURVEY 8d per-operation costs x device counters of the same frame; ray generation only for the "
+                                        "%d of %d primary samples that were generated (the rest sit in pixel blocks the cull pass proved empty); no tone-map term" % (st.primary_generated, st.primary_rays),
+                         "measured_flops_per_launch": measured,
+                         "frac_measured": (measured / (tr * 1e-3) / 1e12 / peak_tflops) if measured else None,
                          "peak_source": "measured live: dependent-FFMA microbenchmark (MEASURED_PEAKS.json has no fp32 entry; nominal %.1f)" % NOMINAL_FP32_TFLOPS,
-                         "note": "divergent traversal + shading: bounded by FP32/INT issue, not HBM (scene fits L1/L2)",
+                         "note": "divergent traversal + shading: bounded by FP32/INT issue and node-fetch latency, not HBM (scene fits L1/L2)",
                          "hbm": hbm},
+            "culled_sample_fraction": 1.0 - st.primary_generated / max(1, st.primary_rays),
         }
         if frame_check is not None:
-            line["config"]["frame_link_vs_nccl_gather"] = frame_check
+            line["run"]["frame_link_vs_nccl_gather"] = frame_check
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(wl, work)
-        print(json.dumps(line))
     if world > 1:
         dist.barrier()
         if link is not None:
             torch.cuda.synchronize()
             r.LinkClose(link)
+    r.close()
+    c5 = None
+    if args.workload == "c1_view" and not args.no_scale_c5:
+        c5 = scale_c5(args, G, torch, dist, world, rank, local_rank, dev, stream)
+    if rank == 0:
+        if c5 is not None:
+            line["scale_c5"] = c5
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def scale_c5(args, G, torch, dist, world, rank, local_rank, dev, stream):
+    """The north-star's multi-GPU configuration next to the headline line: the 4K synthetic 1 M-primitive scene (C5, fog on,
+    depth 32) at 32 spp — a frame of ~1.5 s on one GPU, where tile sharding is throughput- and not latency-bound.
+    ms/frame device-resident (max over ranks, NCCL all-gather of the RGBA8 slabs + un-swizzle on rank 0), end to end with
+    host buffers (scene upload incl. BVH build every step + frame D2H), and the same frame on ONE GPU in the same run
+    (rank 0, the other ranks idle) for `efficiency_vs_n1` = t(1) / (N t(N))."""
+    kind, W, H, spp, depth, options, desc = WORKLOADS["c5_spp32"]
+    flat = Workload(kind, options).flat(G)
+    r = G.NewParallelRenderer(1, devices=[local_rank])
+    r.SetSamples(spp); r.SetMaxDepth(depth); r.SetSeed(20240602); r.SetShard(rank, world)
+    r.set_stream(stream.cuda_stream)
+    t0 = time.perf_counter()
+    r.UploadScene(flat)
+    upload_s = time.perf_counter() - t0
+    slab_bytes = G.shard_slab_bytes(W, H, world)
+    slab = torch.zeros(slab_bytes, dtype=torch.uint8, device=dev)
+    gathered = torch.zeros(slab_bytes * world, dtype=torch.uint8, device=dev) if world > 1 else None
+    frame = torch.zeros(W * H * 4, dtype=torch.uint8, device=dev)
+    host_frame = torch.zeros(W * H * 4, dtype=torch.uint8).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        if world == 1:
+            r.RenderDevice(W, H, frame.data_ptr())
+            return
+        r.RenderShardDevice(W, H, slab.data_ptr())
+        dist.all_gather_into_tensor(gathered, slab)
+        if rank == 0:
+            r.UnswizzleDevice(gathered.data_ptr(), world, W, H, frame.data_ptr())
+
+    def reduce_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    step()
+    barrier()
+    steps = 2
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        a.record(stream)
+        step()
+        b.record(stream)
+    barrier()
+    ms = reduce_max(sum(a.elapsed_time(b) for a, b in ev) / steps)
+    # end to end: scene upload (host flatten + BVH build + H2D) and frame D2H inside the timed region
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(steps):
+        r.UploadScene(flat)
+        step()
+        if rank == 0:
+            host_frame.copy_(frame, non_blocking=True)
+        torch.cuda.synchronize()
+    barrier()
+    e2e_ms = reduce_max(1e3 * (time.perf_counter() - e0) / steps)
+    st = r.RenderShardDevice(W, H, slab.data_ptr(), want_stats=True) if world > 1 else r.RenderDevice(W, H, frame.data_ptr(), want_stats=True)
+    n1_ms = ms
+    if world > 1:
+        barrier()
+        if rank == 0:  # the same frame on one GPU, same process, same run
+            r.SetShard(0, 1)
+            r.RenderDevice(W, H, frame.data_ptr())
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            r.RenderDevice(W, H, frame.data_ptr())
+            b.record(stream)
+            torch.cuda.synchronize()
+            n1_ms = a.elapsed_time(b)
+        barrier()
+        n1_ms = reduce_max(n1_ms if rank == 0 else 0.0)
+    r.close()
+    rays = W * H * spp
+    return {"workload": desc, "width": W, "height": H, "samples": spp, "max_depth": depth, "n_gpus": world,
+            "ms_per_frame": ms, "value": rays / (ms * 1e-3) / 1e6, "unit": UNIT,
+            "e2e_ms_per_frame": e2e_ms, "scene_upload_s": upload_s, "bvh_build_ms": st.bvh_build_ms,
+            "n1_ms_per_frame_same_run": n1_ms, "efficiency_vs_n1": n1_ms / (world * ms),
+            "render_path": int(st.render_path), "gather": "NCCL all-gather of RGBA8 slabs" if world > 1 else "none"}
 
 
 def cpu_baseline(wl, work):
@@ -458,9 +581,19 @@ def cpu_baseline(wl, work):
         total += time.perf_counter() - t0
         samples += cnt["samples"]
         passes += 1
-    return {"value": samples / total / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%s, %d passes" % (sample, passes), "seconds": total,
-            "note": "C++ -O2 float64 transcription of the Go renderer, one thread per host core (no Go toolchain in this image)"}
+    out = {"value": samples / total / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": "%s, %d passes" % (sample, passes), "seconds": total,
+           "note": "C++ -O2 float64 transcription of the Go renderer, one thread per host core (no Go toolchain in this image)"}
+    if n_prims > 1000:
+        # the fairer CPU number for large scenes: the same float64 port with hitWorld over the oracle's own BVH
+        # (identical hits to the linear scan, tests/test_oracle_accel.py) on a centred 256x256 crop at the same 2 spp
+        crop2 = ((W - 256) // 2, (H - 256) // 2, (W + 256) // 2, (H + 256) // 2)
+        scene.render(W, H, samples=s_spp, max_depth=depth, rng_mode=O.RNG_MT, seed=0, threads=cores, crop=crop2, use_accel=True)
+        t0 = time.perf_counter()
+        _, _, cnt = scene.render(W, H, samples=s_spp, max_depth=depth, rng_mode=O.RNG_MT, seed=1, threads=cores, crop=crop2, use_accel=True)
+        dt = time.perf_counter() - t0
+        out["with_bvh"] = {"value": cnt["samples"] / dt / 1e6, "unit": UNIT, "sample": "centred 256x256 crop at %d spp, oracle-side BVH" % s_spp, "seconds": dt}
+    return out
 
 
 if __name__ == "__main__":
