@@ -438,7 +438,9 @@ class ParallelRenderer:
         return p
 
     def Render(self, scene, width: int, height: int, out: Optional[np.ndarray] = None) -> np.ndarray:
-        """ParallelRenderer.Render (renderer.go:67-126): blocking; returns image.RGBA.Pix as [H, W, 4] uint8."""
+        """ParallelRenderer.Render (renderer.go:67-126): blocking; returns image.RGBA.Pix as [H, W, 4] uint8.
+        A scene object is uploaded when it is first seen and is treated as immutable afterwards (the reference's Scene is
+        not mutated during Render either): after changing a FlatScene in place, call UploadScene(scene) again."""
         start = time.time()
         if scene is not self._scene_token:
             self.UploadScene(scene)

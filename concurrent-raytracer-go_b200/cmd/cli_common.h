@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <sys/stat.h>
 #include <vector>
 
 namespace cli {
@@ -83,6 +84,12 @@ inline std::string json_str(const std::string& s) {
 inline std::string dir_of(const std::string& p) {
     size_t k = p.find_last_of('/');
     return k == std::string::npos ? "." : (k == 0 ? "/" : p.substr(0, k));
+}
+
+// os.MkdirAll: every missing level of the path (errors surface when the file is opened)
+inline void mkdir_all(const std::string& dir) {
+    for (size_t k = 1; k <= dir.size(); k++)
+        if (k == dir.size() || dir[k] == '/') mkdir(dir.substr(0, k).c_str(), 0755);
 }
 
 }  // namespace cli

@@ -45,6 +45,7 @@ int main(int argc, char** argv) {
         else if (a == "-camera-mode" || a == "--camera-mode") camera_mode = std::string(val("-camera-mode")) == "lookat" ? GORT_CAMERA_LOOKAT : GORT_CAMERA_REFERENCE;
         else if (a == "-prisms" || a == "--prisms") options |= 1u;
         else if (a == "-fog" || a == "--fog") options |= 2u;
+        else if (a == "-sky" || a == "--sky") options |= 4u;
         else if (a == "-readme-json" || a == "--readme-json") readme_json = val("-readme-json");
         else args.push_back(a);
     }
@@ -117,7 +118,7 @@ int main(int argc, char** argv) {
     if (!has_ext(output)) output += ".png";
     printf("Saving to: %s\n", output.c_str());
     const std::string dir = cli::dir_of(output);
-    mkdir(dir.c_str(), 0755);
+    cli::mkdir_all(dir);  // os.MkdirAll (renderer.go:439-441)
     if (!cli::write_png(output, pix.data(), (int)width, (int)height)) {
         printf("Error saving image: cannot write %s\n", output.c_str());
         gort_destroy(ctx);
@@ -146,14 +147,17 @@ int main(int argc, char** argv) {
         FILE* f = fopen(readme_json.c_str(), "w");
         if (f) {
             const double px = (double)width * height;
-            fprintf(f, "{\n  \"anti_aliasing\": true,\n  \"atmosphere\": \"none\",\n  \"bvh_build_time\": %s,\n  \"cpu_usage\": 0,\n  \"depth_of_field\": false,\n",
-                    cli::json_str(cli::go_duration(st.bvh_build_ms * 1e-3)).c_str());
+            // the switches as they were rendered (-scene-settings may have turned them off); atmosphere: what the loader enabled
+            const char* atmosphere = (options & 2u) ? ((options & 4u) ? "fog+sky" : "fog") : ((options & 4u) ? "sky" : "none");
+            fprintf(f, "{\n  \"anti_aliasing\": %s,\n  \"atmosphere\": \"%s\",\n  \"bvh_build_time\": %s,\n  \"cpu_usage\": 0,\n  \"depth_of_field\": false,\n",
+                    aa ? "true" : "false", atmosphere, cli::json_str(cli::go_duration(st.bvh_build_ms * 1e-3)).c_str());
             fprintf(f, "  \"height\": %ld,\n  \"max_depth\": %d,\n  \"memory_usage\": %llu,\n  \"output_file\": %s,\n", height, max_depth,
                     (unsigned long long)(st.bvh_bytes + (unsigned long long)px * 28), cli::json_str(output).c_str());
-            fprintf(f, "  \"pixels_per_second\": %.0f,\n  \"rays_per_second\": %.0f,\n  \"recursive_reflections\": true,\n  \"render_time\": %s,\n", px / render_s,
-                    px * samples / render_s, cli::json_str(cli::go_duration(render_s)).c_str());
-            fprintf(f, "  \"samples\": %d,\n  \"scene_file\": %s,\n  \"setup_time\": %s,\n  \"soft_shadows\": true,\n  \"total_time\": %s,\n", samples,
-                    cli::json_str(scene_file).c_str(), cli::json_str(cli::go_duration(setup_s)).c_str(), cli::json_str(cli::go_duration(setup_s + render_s)).c_str());
+            fprintf(f, "  \"pixels_per_second\": %.0f,\n  \"rays_per_second\": %.0f,\n  \"recursive_reflections\": %s,\n  \"render_time\": %s,\n", px / render_s,
+                    px * samples / render_s, rr ? "true" : "false", cli::json_str(cli::go_duration(render_s)).c_str());
+            fprintf(f, "  \"samples\": %d,\n  \"scene_file\": %s,\n  \"setup_time\": %s,\n  \"soft_shadows\": %s,\n  \"total_time\": %s,\n", samples,
+                    cli::json_str(scene_file).c_str(), cli::json_str(cli::go_duration(setup_s)).c_str(), ss ? "true" : "false",
+                    cli::json_str(cli::go_duration(setup_s + render_s)).c_str());
             fprintf(f, "  \"width\": %ld,\n  \"worker_count\": %d\n}\n", width, st.n_devices);
             fclose(f);
         }

@@ -100,6 +100,7 @@ struct gort_link {
     unsigned int* ctrl = nullptr;  // {arrived, consumed, timed_out} behind the frame
     unsigned int frame_no = 0;
     bool local_alias = false;      // test hook: peer link sharing the owner's pointer inside one process
+    bool has_local_peers = false;  // owner: some peers are local aliases (ranks run one after the other on this GPU)
 };
 
 namespace {
@@ -211,8 +212,17 @@ void pack_material(const HostMaterial& m, F4 out[4]) {
 
 int upload_scene(gort_ctx* ctx) {
     const double t0 = now_ms();
+    // limits of the device code: a leaf's first primitive is a 26-bit index per primitive type; the walks keep a 64-entry stack
+    if (ctx->scene.spheres.size() > (size_t)kLeafStartMask + 1 || ctx->scene.tris.size() > (size_t)kLeafStartMask + 1) {
+        ctx->has_scene = false;
+        return fail(ctx, GORT_ERR_INVALID, "scene too large: at most 2^26 spheres and 2^26 triangles");
+    }
     build_bvh(ctx->scene, ctx->bvh);
     ctx->bvh_ms = ctx->bvh.build_ms;
+    if (ctx->bvh.max_depth > 62) {
+        ctx->has_scene = false;
+        return fail(ctx, GORT_ERR_INVALID, "BVH deeper than the traversal stack (62 levels): degenerate geometry");
+    }
     const HostScene& hs = ctx->scene;
     std::vector<F4> mats(hs.mats.size() * 4);
     for (size_t i = 0; i < hs.mats.size(); i++) pack_material(hs.mats[i], &mats[4 * i]);
@@ -371,6 +381,9 @@ int validate(gort_ctx* ctx, const gort_render_params* p) {
     if ((int64_t)p->width * p->height > (int64_t)1 << 28) return fail(ctx, GORT_ERR_INVALID, "image too large");
     if (p->width > 65535 || p->height > 65535) return fail(ctx, GORT_ERR_INVALID, "width/height must be <= 65535");
     if (p->samples <= 0 || p->samples > 65535) return fail(ctx, GORT_ERR_INVALID, "samples must be in 1..65535");
+    // the per-warp-queue kernel numbers its work units (8x4 pixel block, sample batch) in 32 bits
+    if ((int64_t)p->width * p->height * (int64_t)p->samples > ((int64_t)1 << 36))
+        return fail(ctx, GORT_ERR_INVALID, "width*height*samples must be <= 2^36 per call");
     if (p->max_depth < 0 || p->max_depth > 65535) return fail(ctx, GORT_ERR_INVALID, "max_depth must be in 0..65535");
     const int sc = p->shard_count <= 0 ? 1 : p->shard_count;
     if (p->shard_rank < 0 || p->shard_rank >= sc) return fail(ctx, GORT_ERR_INVALID, "shard_rank out of range");
@@ -1156,10 +1169,11 @@ int gort_link_open(gort_ctx* ctx, const uint8_t* handle, int32_t width, int32_t 
     return GORT_OK;
 }
 
-int gort_link_open_local(gort_ctx* ctx, const gort_link* owner, int32_t rank, gort_link** out) {
+int gort_link_open_local(gort_ctx* ctx, gort_link* owner, int32_t rank, gort_link** out) {
     if (!ctx || !owner || !out || !owner->owner || rank < 1 || rank >= owner->n_ranks) return GORT_ERR_INVALID;
     gort_link* l = new gort_link(*owner);
-    l->owner = false; l->local_alias = true; l->rank = rank; l->frame_no = 0;
+    l->owner = false; l->local_alias = true; l->rank = rank; l->frame_no = 0; l->has_local_peers = false;
+    owner->has_local_peers = true;
     *out = l;
     return GORT_OK;
 }
@@ -1173,7 +1187,10 @@ int gort_link_read(gort_ctx* ctx, gort_link* l, uint8_t* rgba_out, size_t rgba_b
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     unsigned int timed_out = 0;
     CUDA_TRY(ctx, cudaMemcpy(&timed_out, l->ctrl + 2, sizeof(timed_out), cudaMemcpyDeviceToHost));
-    if (timed_out) return fail(ctx, GORT_ERR_CUDA, "frame link: a rank did not deliver its tiles within 20 s (frame incomplete)");
+    if (timed_out) {
+        CUDA_TRY(ctx, cudaMemset(l->ctrl + 2, 0, sizeof(unsigned int)));  // reported once: later frames start clean
+        return fail(ctx, GORT_ERR_CUDA, "frame link: a rank did not deliver its tiles within 20 s (frame incomplete)");
+    }
     return GORT_OK;
 }
 
@@ -1207,10 +1224,22 @@ int gort_render_linked(gort_ctx* ctx, const gort_render_params* p, gort_link* l,
     if (l->owner) {
         // everything this stream did with frame k-1 is done when this runs: the peers may overwrite it
         CUDA_TRY(ctx, launch_link_store(l->ctrl + 1, k - 1, st));
+        if (l->has_local_peers) {
+            // Ranks that share this GPU cannot run concurrently with a kernel that waits for them: the peers must have rendered
+            // (and finished) frame k already.  Checked on the host instead of enqueuing a wait that could only time out.
+            unsigned int arrived = 0;
+            CUDA_TRY(ctx, cudaDeviceSynchronize());
+            CUDA_TRY(ctx, cudaMemcpy(&arrived, l->ctrl + 0, sizeof(arrived), cudaMemcpyDeviceToHost));
+            if ((int)(arrived - k * (unsigned int)(l->n_ranks - 1)) < 0) {
+                l->frame_no--;
+                return fail(ctx, GORT_ERR_INVALID, "frame link on one GPU: render every peer rank's frame before the owner's");
+            }
+        }
         if (int rc = enqueue_device(ctx, 0, p, 0, l->n_ranks, 0, l->base, 0, nullptr)) return rc;
-        if (l->n_ranks > 1) CUDA_TRY(ctx, launch_link_wait(l->ctrl + 0, k * (unsigned int)(l->n_ranks - 1), l->ctrl + 2, st));
+        if (l->n_ranks > 1 && !l->has_local_peers) CUDA_TRY(ctx, launch_link_wait(l->ctrl + 0, k * (unsigned int)(l->n_ranks - 1), l->ctrl + 2, st));
     } else {
-        hk.wait_flag = l->ctrl + 1; hk.wait_target = k - 1; hk.timed_out = l->ctrl + 2;
+        // (a local alias renders before its owner and on the same GPU: there is no one to wait for)
+        if (!l->local_alias) { hk.wait_flag = l->ctrl + 1; hk.wait_target = k - 1; hk.timed_out = l->ctrl + 2; }
         hk.signal_flag = l->ctrl + 0;
         if (int rc = enqueue_device(ctx, 0, p, l->rank, l->n_ranks, 0, l->base, 0, &hk)) return rc;
     }

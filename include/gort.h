@@ -265,8 +265,10 @@ int gort_render_linked(gort_ctx* ctx, const gort_render_params* params, gort_lin
 /* owner: copy the assembled frame to host memory (stream-ordered after gort_render_linked, then synchronised) */
 int gort_link_read(gort_ctx* ctx, gort_link* link, uint8_t* rgba_out, size_t rgba_bytes);
 /* test hook: a peer link onto an owner link of the SAME process (CUDA IPC cannot open a handle in the process that
- * made it); lets a single-GPU box exercise the protocol with the ranks run one after the other, peers first. */
-int gort_link_open_local(gort_ctx* ctx, const gort_link* owner, int32_t rank, gort_link** out);
+ * made it); lets a single-GPU box exercise the protocol with the ranks run one after the other, peers first.  An owner
+ * with local peers never enqueues a device-side wait: gort_render_linked checks on the host that every peer's tiles of
+ * the frame have arrived and returns GORT_ERR_INVALID if the owner was rendered first. */
+int gort_link_open_local(gort_ctx* ctx, gort_link* owner, int32_t rank, gort_link** out);
 
 /* Sample-averaged linear radiance (before tone-map) of the last render on this ctx, float64 RGB
  * [height][width][3] on the host; tiles not owned by the shard are left untouched.  Test hook. */

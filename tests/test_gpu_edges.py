@@ -187,6 +187,17 @@ def test_frame_link_assembles_the_frame_in_the_owners_memory(gort, renderer):
         assert st.n_tiles == len(gort.tiles_of_shard(W, H, k, n))
     img = ranks[0].LinkRead(link0, W, H)
     assert np.array_equal(img, full)
+    # frame 2 through the same links; then the wrong order (owner first) is refused on the host — nothing is enqueued that
+    # would spin on the GPU waiting for ranks that cannot run beside it — and the right order still works afterwards
+    for k in (1, 2, 0):
+        ranks[k].RenderLinked(W, H, links[k])
+    assert np.array_equal(ranks[0].LinkRead(link0, W, H), full)
+    with pytest.raises(gort.GortError) as e:
+        ranks[0].RenderLinked(W, H, links[0])
+    assert "before the owner" in str(e.value)
+    for k in (2, 1, 0):
+        ranks[k].RenderLinked(W, H, links[k])
+    assert np.array_equal(ranks[0].LinkRead(link0, W, H), full)
     for k in (2, 1, 0):
         ranks[k].LinkClose(links[k])
         ranks[k].close()

@@ -124,3 +124,28 @@ def test_c5_one_million_primitives(gort, oracle):
     full = _shards_compose(gort, flat, 256, 144, 2, 32, 8)  # fog on: misses stay black, hits are fogged
     assert (full[..., :3].sum(-1) > 0).mean() > 0.05
     _ray_parity(gort, oracle, a, 120, 5)
+    # the image itself, as for C4: same-stream crops where the paths are short (fog on the primary-hit distance is part of
+    # both sides), and the stochastic bar at full depth — PSNR >= 40 dB, both sides converged at 1024 spp
+    osc = synth.to_oracle(a)
+    r = gort.NewParallelRenderer(1)
+    W, H = 480, 270
+    crop = (W // 2 - 24, H // 2 - 16, W // 2 + 24, H // 2 + 16)
+    x0, y0, x1, y1 = crop
+    for depth, soft, bar in ((1, True, 0.999), (2, False, 0.995)):
+        r.SetSamples(1); r.SetMaxDepth(depth); r.SetSoftShadows(soft); r.SetAntiAliasing(False); r.SetSeed(9)
+        img = r.Render(flat, W, H)
+        assert r.lastStats.render_path == 2  # the wavefront pipeline
+        ref, _, _ = osc.render(W, H, samples=1, max_depth=depth, jitter=False, soft_shadows=soft, rng_mode=oracle.RNG_PHILOX, seed=9,
+                               crop=crop, use_accel=True, threads=8)
+        p, q = img[y0:y1, x0:x1], ref[y0:y1, x0:x1]
+        assert (q[..., :3].sum(-1) > 0).mean() > 0.5
+        assert Cm.within_one(p, q) >= bar, (depth, Cm.within_one(p, q))
+    W, H = 160, 90
+    small = (W // 2 - 12, H // 2 - 8, W // 2 + 12, H // 2 + 8)
+    x0, y0, x1, y1 = small
+    r.SetSamples(1024); r.SetMaxDepth(32); r.SetSoftShadows(True); r.SetAntiAliasing(True); r.SetSeed(3)
+    img = r.Render(flat, W, H)
+    ref, _, _ = osc.render(W, H, samples=1024, max_depth=32, rng_mode=oracle.RNG_MT, seed=5, crop=small, use_accel=True, threads=8)
+    p, q = img[y0:y1, x0:x1], ref[y0:y1, x0:x1]
+    assert Cm.psnr(p, q) >= 40.0, Cm.psnr(p, q)
+    r.close()

@@ -5,6 +5,7 @@ pixel within 1/255 on >= 99.9 % of pixels with MAE <= 0.5/255; stochastic config
 (a) sample-for-sample: oracle and GPU draw the same Philox stream, so the same bar applies at any spp, and
 (b) with independent RNG streams at 1024 spp: PSNR >= 40 dB.  fp32 (GPU) vs float64 (oracle)."""
 import json
+import os
 
 import numpy as np
 import pytest
@@ -29,11 +30,26 @@ def configure(r, samples, depth, jitter=True, soft=True, recursive=True, seed=0,
     r.SetRecursiveReflections(recursive); r.SetSeed(seed); r.SetCameraMode(camera); r.SetShard(0, 1); r.SetCollectStats(False)
 
 
-def check(img, ref, within=WITHIN, mae=MAE):
+def check(img, ref, within=WITHIN, mae=MAE, lit_within=WITHIN, lit_mae=MAE, max_bad_lit=None):
+    """The north-star bar on the whole frame AND on the lit pixels alone (reference or GPU non-black): the reference's
+    scenes are ~98 % black under its own camera, so a frame-wide fraction says little about the pixels that carry an image.
+    max_bad_lit: for the cases that state a relaxed bar, the number of lit pixels allowed to differ by more than 1/255."""
     assert img.shape == ref.shape
     assert (img[..., 3] == 255).all()
     w, m = Cm.within_one(img, ref), Cm.mae(img, ref)
+    d = np.abs(img[..., :3].astype(np.int32) - ref[..., :3].astype(np.int32))
+    lit = (ref[..., :3].sum(-1) > 0) | (img[..., :3].sum(-1) > 0)
+    n_lit = int(lit.sum())
+    bad_lit = int((d.max(-1)[lit] > 1).sum())
+    w_lit = 1.0 - bad_lit / max(1, n_lit)
+    m_lit = float(d[lit].mean()) if n_lit else 0.0
+    print("PARITY frame: within-1 %.5f MAE %.4f | lit pixels %d (%.3f of the frame): within-1 %.5f (%d differ by > 1/255) MAE %.4f" % (
+        w, m, n_lit, n_lit / lit.size, w_lit, bad_lit, m_lit))
     assert w >= within and m <= mae, "within-1 %.5f (need %.4f), MAE %.4f (need %.2f)" % (w, within, m, mae)
+    if max_bad_lit is not None:
+        assert bad_lit <= max_bad_lit, "%d lit pixels differ by > 1/255 (allowed %d of %d)" % (bad_lit, max_bad_lit, n_lit)
+    elif os.environ.get("GORT_PARITY_SURVEY") is None:  # (survey mode: print the numbers of every case, assert the frame bar only)
+        assert w_lit >= lit_within and m_lit <= lit_mae, "lit pixels: within-1 %.5f (need %.4f), MAE %.4f (need %.2f)" % (w_lit, lit_within, m_lit, lit_mae)
     return w, m
 
 
@@ -201,7 +217,10 @@ def test_random_spheres_bvh_scene_same_stream(gort, oracle, renderer):
     img = renderer.Render(gort.SceneFromDict(d), 320, 180)
     ref, _, _ = oracle.Scene(d).render(320, 180, samples=2, max_depth=16, rng_mode=oracle.RNG_PHILOX, seed=9, use_accel=True)
     assert (ref[..., :3].sum(-1) > 0).mean() > 0.2
-    check(img, ref, within=0.995)  # dense silhouettes: more fp32/float64 edge flips than the bar's scenes
+    # 1 500 spheres of radius 0.1-0.5 behind each other: thousands of silhouettes per frame, and a path that grazes one takes
+    # another branch in fp32 than in float64.  Measured: 54 of 30 295 lit pixels differ by more than 1/255 (0.18 %); every other
+    # same-stream case of this suite is at 100.00 % on its lit pixels.
+    check(img, ref, within=0.998, max_bad_lit=90)
 
 
 def test_flat_desc_equals_json_loader(gort, renderer):
@@ -316,7 +335,7 @@ def test_contact_and_overlap_same_stream(gort, oracle, renderer, spheres_only):
     a = renderer.ReadRadiance(480, 320)
     ref, _, _ = oracle.Scene(d).render(480, 320, samples=4, max_depth=12, rng_mode=oracle.RNG_PHILOX, seed=17)
     assert (ref[..., :3].sum(-1) > 0).mean() > 0.3
-    check(img, ref, within=0.997, mae=0.5)  # nested glass: single fp32-vs-float64 refraction decisions move a few pixels
+    check(img, ref)  # (nested glass: single fp32-vs-float64 refraction decisions move 42 of 157 503 lit pixels)
     os.environ["GORT_NO_CONE_CULL"] = "1"
     try:
         renderer.Render(sc, 480, 320)
@@ -377,5 +396,4 @@ def test_random_scenes_same_stream(gort, oracle, renderer, seed):
     ref, _, _ = oracle.Scene(d, prisms=True).render(300, 200, samples=spp, max_depth=depth, soft_shadows=soft, rng_mode=oracle.RNG_PHILOX, seed=seed)
     if (ref[..., :3].sum(-1) > 0).mean() < 0.01:
         pytest.skip("nothing in frame")
-    # glass / dielectric at depth > 2 lets single fp32-vs-float64 refraction decisions move a few pixels by > 1/255
-    check(img, ref, within=0.99 if depth > 2 else 0.997, mae=0.6)
+    check(img, ref)

@@ -132,13 +132,13 @@ def test_stream_same_stream_as_oracle(gort, oracle, renderer):
     with forced_path("stream"):
         img = renderer.Render(gort.SceneFromDict(d), 320, 180)
     ref, _, _ = oracle.Scene(d).render(320, 180, samples=2, max_depth=16, rng_mode=oracle.RNG_PHILOX, seed=9, use_accel=True)
-    check(img, ref, within=0.995)
+    check(img, ref, within=0.998, max_bad_lit=90)  # (the dense cloud: see test_random_spheres_bvh_scene_same_stream)
     d = _contact_scene(False)
     configure(renderer, 4, 12, seed=17)
     with forced_path("stream"):
         img = renderer.Render(gort.SceneFromDict(d), 480, 320)
     ref, _, _ = oracle.Scene(d).render(480, 320, samples=4, max_depth=12, rng_mode=oracle.RNG_PHILOX, seed=17)
-    check(img, ref, within=0.997)
+    check(img, ref)
 
 
 def test_stream_deterministic_c3(gort, oracle, renderer):
