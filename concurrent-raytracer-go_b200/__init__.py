@@ -29,7 +29,7 @@ LIB_PATH = os.environ.get("GORT_LIB") or os.path.join(_HERE, "lib", "libgort.so"
 ABI_VERSION = 3
 TILE = 32
 CAMERA_REFERENCE, CAMERA_LOOKAT = 0, 1
-LOAD_PRISMS, LOAD_FOG = 1, 2
+LOAD_PRISMS, LOAD_FOG, LOAD_SKY = 1, 2, 4
 
 MAT_TYPES = {"lambertian": 0, "metal": 1, "shiny": 2, "perfectmirror": 3, "glass": 4, "dielectric": 5, "diffuselight": 6}
 
@@ -287,7 +287,7 @@ class HostScene:
 class FlatScene:
     """A gort_scene_desc built from Python arrays (what a Go host would pass after Flatten())."""
 
-    def __init__(self, camera: dict, materials: Sequence[dict], spheres=(), triangles=(), lights=(), fog=None):
+    def __init__(self, camera: dict, materials: Sequence[dict], spheres=(), triangles=(), lights=(), fog=None, sky=None):
         """materials: dicts with type (int), color, roughness, metallic, specular, ior (post-constructor values).
         spheres: (center3, radius, material, order); triangles: (v9, material, order); lights: (pos3, color3, intensity)."""
         self._keep = []
@@ -332,6 +332,9 @@ class FlatScene:
             d.fog_enabled = 1
             d.fog_density = fog["density"]
             d.fog_color[:] = fog["color"]
+        if sky:  # the 27 AtmosphereConfig values (atmosphere/atmosphere.go:8-26), extension
+            d.sky_enabled = 1
+            d.sky_params[:] = [float(x) for x in sky]
         self.desc = d
 
 

@@ -401,7 +401,7 @@ int choose_path(const gort_ctx* ctx) {
     const HostScene& hs = ctx->scene;
     const size_t n_prims = hs.spheres.size() + hs.tris.size();
     const bool small_ok = hs.tris.empty() && !hs.spheres.empty() && (int)hs.spheres.size() <= kSmallMax && (int)hs.mats.size() <= kSmallMax &&
-                          (int)hs.lights.size() <= kSmallLights;
+                          (int)hs.lights.size() <= kSmallLights && !hs.sky_enabled;  // (the sky extension lives in the BVH kernels)
     const bool stream_ok = ctx->bvh.n_nodes > 0 && (int)hs.lights.size() <= kStreamLightChunk * kStreamMaxChunks;
     const char* force = getenv("GORT_PATH");
     if (force && !strcmp(force, "stream") && stream_ok) return kPathStream;
@@ -614,6 +614,8 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     tp.fog_enabled = ctx->scene.fog_enabled;
     tp.fog_density = (float)ctx->scene.fog_density;
     tp.fog_r = (float)ctx->scene.fog_color[0]; tp.fog_g = (float)ctx->scene.fog_color[1]; tp.fog_b = (float)ctx->scene.fog_color[2];
+    tp.sky_enabled = ctx->scene.sky_enabled;
+    for (int k = 0; k < 27; k++) tp.sky[k] = (float)ctx->scene.sky_params[k];
     CUDA_TRY(ctx, launch_cull(tp, d.d_active, d.d_counter + 1, st));
     CUDA_TRY(ctx, cudaEventRecord(d.ev_tc, st));
     ResolveParams rp;

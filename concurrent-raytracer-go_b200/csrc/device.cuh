@@ -581,6 +581,32 @@ __device__ __forceinline__ void add_radiance(const TraceParams& P, uint32_t pixl
     if (b != 0.f && b == b) atomicAdd(acc + 2, (unsigned long long)__float2ll_rn(fminf(fmaxf(b, -kSampleClamp), kSampleClamp) * scale));
 }
 
+// AtmosphereConfig.GetSkyColor (atmosphere/atmosphere.go:100-135; oracle.cpp sky_color), extension: the colour of a ray that
+// leaves the scene.  Out of line: it runs once per finished path, and the trace kernels are bound by their code footprint.
+static __device__ __noinline__ float3 sky_color(const float* __restrict__ q, float dx, float dy, float dz) {
+    normalize3(dx, dy, dz);
+    const float t = 0.5f * (dy + 1.0f);
+    float r = fmaf(q[0], t, q[3] * (1.0f - t)), g = fmaf(q[1], t, q[4] * (1.0f - t)), b = fmaf(q[2], t, q[5] * (1.0f - t));
+    const float atm = __expf(-fmaxf(0.f, dy) * q[20]);
+    const float sr = fmaf(q[17], atm, q[14] * (1.0f - atm)), sg = fmaf(q[18], atm, q[15] * (1.0f - atm)), sb = fmaf(q[19], atm, q[16] * (1.0f - atm));
+    r = fmaf(sr, 0.25f, r * 0.75f); g = fmaf(sg, 0.25f, g * 0.75f); b = fmaf(sb, 0.25f, b * 0.75f);
+    const float sun_dot = dot3(dx, dy, dz, q[6], q[7], q[8]);
+    if (sun_dot > 1.0f - q[13]) {
+        const float x = (sun_dot - (1.0f - q[13])) / q[13];
+        const float si = fminf(x * sqrt_fast(x), 1.0f) * q[12] * 0.9f;  // pow(x, 1.5)
+        r = fmaf(q[9], si, r * (1.0f - si)); g = fmaf(q[10], si, g * (1.0f - si)); b = fmaf(q[11], si, b * (1.0f - si));
+    }
+    float tf = q[26];
+    if (tf > 0.5f) tf = 1.0f - tf;
+    const float dark = 1.0f - 2.0f * tf * 0.3f;
+    r *= dark; g *= dark; b *= dark;
+    if (q[21] > 0.f) {
+        const float ff = __expf(-q[21]);
+        r = fmaf(r, ff, q[22] * (1.0f - ff)); g = fmaf(g, ff, q[23] * (1.0f - ff)); b = fmaf(b, ff, q[24] * (1.0f - ff));
+    }
+    return make_float3(fminf(fmaxf(r, 0.1f), 0.98f), fminf(fmaxf(g, 0.1f), 0.98f), fminf(fmaxf(b, 0.1f), 0.98f));
+}
+
 __device__ __forceinline__ float pow5(float x) {  // math.Pow(x, 5): sign-preserving for negative x
     const float x2 = x * x;
     return x2 * x2 * x;

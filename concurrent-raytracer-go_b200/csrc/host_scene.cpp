@@ -270,6 +270,47 @@ std::string scene_from_json(const char* text, size_t len, uint32_t options, Host
             if (!vec3_field(field(fog, "color"), out.fog_color, err, "fog.color")) return err;
         }
     }
+    if (options & 4u) {
+        // "sky" block (extension): {"enabled": true, "preset": "default"|"white"|"sunset"|"night", per-field overrides} ->
+        // AtmosphereConfig.  Presets: NewDefault/White/Sunset/NightAtmosphere (atmosphere/atmosphere.go:28-98).
+        const json::Value* sky = field(root.get(), "sky");
+        const json::Value* en = field(sky, "enabled");
+        if (en && en->kind == json::Value::Bool && en->b) {
+            static const double presets[4][27] = {
+                {0.6, 0.8, 1.0, 0.9, 0.95, 1.0, 0.0, 0.8, -0.6, 1.0, 0.98, 0.95, 1.2, 0.015, 0.6, 0.8, 1.0, 1.0, 0.98, 0.95, 0.3, 0.0, 0.9, 0.92, 0.95, 0.05, 0.6},
+                {0.98, 0.98, 1.0, 0.92, 0.92, 0.95, 0.0, 0.8, -0.6, 1.0, 0.99, 0.97, 0.8, 0.012, 0.9, 0.9, 0.95, 0.95, 0.95, 0.98, 0.2, 0.0, 0.95, 0.95, 0.98, 0.02, 0.6},
+                {1.0, 0.4, 0.2, 1.0, 0.8, 0.6, 0.0, 0.3, -0.9, 1.0, 0.6, 0.3, 1.2, 0.03, 1.0, 0.4, 0.2, 1.0, 0.8, 0.6, 0.8, 0.1, 1.0, 0.8, 0.6, 0.3, 0.8},
+                {0.1, 0.1, 0.3, 0.2, 0.2, 0.4, 0.0, -0.7, -0.7, 0.8, 0.8, 1.0, 0.3, 0.005, 0.1, 0.1, 0.3, 0.8, 0.8, 1.0, 0.2, 0.0, 0.1, 0.1, 0.2, 0.0, 0.0}};
+            int which = 0;
+            const json::Value* pv = field(sky, "preset");
+            if (pv && pv->kind == json::Value::String) {
+                const std::string name = lower(pv->str);
+                if (name == "default") which = 0;
+                else if (name == "white") which = 1;
+                else if (name == "sunset") which = 2;
+                else if (name == "night") which = 3;
+                else return "sky.preset: unknown preset " + pv->str;
+            }
+            memcpy(out.sky_params, presets[which], sizeof(out.sky_params));
+            struct F { const char* name; int off, n; };
+            static const F fields[] = {{"skyColorTop", 0, 3}, {"skyColorBottom", 3, 3}, {"sunDirection", 6, 3}, {"sunColor", 9, 3},
+                                       {"sunIntensity", 12, 1}, {"sunSize", 13, 1}, {"rayleighScattering", 14, 3}, {"mieScattering", 17, 3},
+                                       {"atmosphericDepth", 20, 1}, {"fogDensity", 21, 1}, {"fogColor", 22, 3}, {"hazeIntensity", 25, 1},
+                                       {"timeOfDay", 26, 1}};
+            for (const F& f : fields) {
+                const json::Value* v = field(sky, f.name);
+                if (!v) continue;
+                if (f.n == 3) {
+                    double t[3];
+                    if (!vec3_field(v, t, err, f.name)) return err;
+                    memcpy(out.sky_params + f.off, t, sizeof(t));
+                } else if (v->is_number()) {
+                    out.sky_params[f.off] = v->num;
+                }
+            }
+            out.sky_enabled = 1;
+        }
+    }
     return "";
 }
 
@@ -337,6 +378,8 @@ std::string scene_from_desc(const gort_scene_desc& d, HostScene& out) {
     out.fog_enabled = d.fog_enabled;
     out.fog_density = d.fog_density;
     memcpy(out.fog_color, d.fog_color, sizeof(out.fog_color));
+    out.sky_enabled = d.sky_enabled;
+    memcpy(out.sky_params, d.sky_params, sizeof(out.sky_params));
     return "";
 }
 

@@ -44,6 +44,9 @@ struct HostScene {
     int32_t n_hittables = 0;  // len(scene.GetHittables()): spheres + meshes
     int32_t fog_enabled = 0;
     double fog_density = 0, fog_color[3] = {0, 0, 0};
+    // sky extension: AtmosphereConfig in declaration order (atmosphere/atmosphere.go:8-26), see gort_scene_desc::sky_params
+    int32_t sky_enabled = 0;
+    double sky_params[27] = {0};
     // the scene's own "renderer" block (README.md:285-291; ignored by the reference loader):
     // {samples, maxDepth, antiAliasing, recursiveReflections, softShadows}, -1 = key absent
     int32_t render_hints[5] = {-1, -1, -1, -1, -1};
@@ -55,7 +58,7 @@ struct HostScene {
 std::string scene_from_desc(const gort_scene_desc& d, HostScene& out);
 
 // Host mirror of scene.LoadFromFile + GetHittables for the reference's JSON schema
-// (scene.go:12-39): returns "" or an error message.  options: bit0 prisms, bit1 fog.
+// (scene.go:12-39): returns "" or an error message.  options: bit0 prisms, bit1 fog, bit2 sky.
 std::string scene_from_json(const char* text, size_t len, uint32_t options, HostScene& out);
 
 // createMaterial's defaults and constructor clamps (scene.go:104-148; material.go:65-73,159-167;

@@ -79,7 +79,9 @@ __device__ __forceinline__ float qf(const uint32_t (*Q)[kQueueCap], int f, int s
 // 100 k / 1 M primitive scenes and the 40-triangle scene, 7 CTAs beat 6 by 5 / 8 / 4 % although the walk then spills
 // ~70 bytes, and 8 is no better than 7.  Shared memory (27 KB per CTA: 6 candidates per pair, 4 lights per pass)
 // is sized so that 7-8 CTAs fit.
-template <bool STATS, bool SMALL, int GEOM>
+// SKY (BVH variants only): the sky extension's two call sites are compiled in only for scenes that enable it — the kernel is
+// bound by its code footprint (the same sites, present but never executed, cost C2-view 8 %)
+template <bool STATS, bool SMALL, int GEOM, bool SKY = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel(const __grid_constant__ TraceParams P) {
     __shared__ WarpShared<SMALL> wsh[kWarpsPerCta];
     const int lane = threadIdx.x & 31;
@@ -213,6 +215,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel
                         hit = query<STATS, SMALL, GEOM>(P, P.cam.ox, P.cam.oy, P.cam.oz, dx, dy, dz, 0.001f, FLT_MAX * 2.0f, false, t, prim, st);
                         walk_account<STATS>(st, nv0, 0);
                     }
+            }
+            if (SKY && lane_valid && !hit && P.max_depth > 0) {
+                // sky extension: a primary ray that leaves the scene sees the sky (the reference returns black, renderer.go:171-173)
+                const float3 c = sky_color(P.sky, dx, dy, dz);
+                add_radiance(P, pixl, c.x, c.y, c.z);
             }
             const unsigned hm = __ballot_sync(FULL_MASK, hit);
             if (hit) {
@@ -416,6 +423,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel
                     if (survive) {
                         px = fmaf(t2, sx, px); py = fmaf(t2, sy, py); pz = fmaf(t2, sz, pz);
                         sd += 0x10000u;
+                    } else if (SKY) {
+                        // sky extension: traceRay(scattered) = sky colour; it reaches the pixel through the updated throughput
+                        // (and the primary hit's fog factor)
+                        const float3 c = sky_color(P.sky, sx, sy, sz);
+                        const float k = P.fog_enabled ? 1.0f - fog : 1.0f;
+                        add_radiance(P, pixl2, tr * c.x * k, tg * c.y * k, tb * c.z * k);
                     }
                 }
                 GORT_DBG_SECTION(2)
@@ -778,7 +791,7 @@ __global__ void __launch_bounds__(128) cull_kernel(const __grid_constant__ Trace
     // The frame's accumulators are not cleared wholesale (12 MB for 800x600): a kept block clears its own 32 pixels
     // here, a culled block is marked and resolve_kernel writes black for it without reading them.
     P.block_active[id] = 0;
-    if (S.n_nodes == 0 || P.max_depth <= 0) return;
+    if (P.max_depth <= 0 || (S.n_nodes == 0 && !P.sky_enabled)) return;
     const uint32_t gtile = (uint32_t)P.shard_rank + ltile * (uint32_t)P.shard_count;
     const uint32_t tx = gtile % (uint32_t)P.tiles_x, ty = gtile / (uint32_t)P.tiles_x;
     const uint32_t x0 = tx * kTile + ((block & 3u) << 3), y0 = ty * kTile + ((block >> 2) << 2);
@@ -811,11 +824,12 @@ __global__ void __launch_bounds__(128) cull_kernel(const __grid_constant__ Trace
     }
     // active: some primitive may be visible; deep: one of them is glass/dielectric (paths can stay trapped
     // by total internal reflection up to max_depth) -> those blocks are scheduled first
-    bool active = degenerate, deep = false;
+    // (sky extension: a block that sees no geometry is not black — every block of the image is traced)
+    bool active = degenerate || P.sky_enabled != 0, deep = false;
     int stack[64];
     int sp = 0;
     int node = 0;
-    while (!deep) {
+    while (!deep && S.n_nodes > 0) {
         if (node >= 0) {
             const float4* np = S.nodes + 4 * (size_t)node;
             const float4 n0 = ldg4(np), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3);
@@ -905,13 +919,13 @@ cudaError_t launch_cull(const TraceParams& p, uint32_t* active_list, unsigned in
 }
 
 
-template <bool STATS, bool SMALL, int GEOM>
+template <bool STATS, bool SMALL, int GEOM, bool SKY = false>
 static cudaError_t launch_trace_variant(const TraceParams& p, int sm_count, cudaStream_t stream) {
     // persistent grid: as many CTAs as fit on the chip at once (occupancy is register-bound)
     static int ctas_per_sm = 0;
     if (ctas_per_sm == 0) {
         int n = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_kernel<STATS, SMALL, GEOM>, kWarpsPerCta * 32, 0);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_kernel<STATS, SMALL, GEOM, SKY>, kWarpsPerCta * 32, 0);
         if (e != cudaSuccess) return e;
         ctas_per_sm = n > 0 ? n : 1;
     }
@@ -919,7 +933,7 @@ static cudaError_t launch_trace_variant(const TraceParams& p, int sm_count, cuda
         const int nw = sm_count * ctas_per_sm * kWarpsPerCta;
         cudaMemsetAsync(p.debug_times, 0xff, 8, stream);
         cudaMemsetAsync(p.debug_times + 1, 0, (size_t)nw * 128, stream);
-        trace_kernel<STATS, SMALL, GEOM><<<sm_count * ctas_per_sm, kWarpsPerCta * 32, 0, stream>>>(p);
+        trace_kernel<STATS, SMALL, GEOM, SKY><<<sm_count * ctas_per_sm, kWarpsPerCta * 32, 0, stream>>>(p);
         std::vector<unsigned long long> h(1 + 16 * (size_t)nw);
         cudaMemcpyAsync(h.data(), p.debug_times, h.size() * 8, cudaMemcpyDeviceToHost, stream);
         cudaStreamSynchronize(stream);
@@ -951,28 +965,28 @@ static cudaError_t launch_trace_variant(const TraceParams& p, int sm_count, cuda
         }
         return cudaGetLastError();
     }
-    trace_kernel<STATS, SMALL, GEOM><<<sm_count * ctas_per_sm, kWarpsPerCta * 32, 0, stream>>>(p);
+    trace_kernel<STATS, SMALL, GEOM, SKY><<<sm_count * ctas_per_sm, kWarpsPerCta * 32, 0, stream>>>(p);
     return cudaGetLastError();
+}
+
+template <bool STATS, bool SKY>
+static cudaError_t launch_trace_bvh(const TraceParams& p, int geom, int sm_count, cudaStream_t stream) {
+    switch (geom) {
+        case 1: return launch_trace_variant<STATS, false, 1, SKY>(p, sm_count, stream);
+        case 2: return launch_trace_variant<STATS, false, 2, SKY>(p, sm_count, stream);
+        default: return launch_trace_variant<STATS, false, 3, SKY>(p, sm_count, stream);
+    }
 }
 
 cudaError_t launch_trace(const TraceParams& p, bool stats, int sm_count, cudaStream_t stream) {
     if (p.n_local_tiles == 0) return cudaSuccess;
-    // kernel variant: tiny sphere scenes scan the parameter bank; BVH scenes run the kernel specialised for what they hold
-    const int geom = p.small_n > 0 ? 0 : ((p.scene.n_spheres > 0 ? 1 : 0) | (p.scene.n_tris > 0 ? 2 : 0));
-    if (stats) {
-        switch (geom) {
-            case 0: return launch_trace_variant<true, true, 1>(p, sm_count, stream);
-            case 1: return launch_trace_variant<true, false, 1>(p, sm_count, stream);
-            case 2: return launch_trace_variant<true, false, 2>(p, sm_count, stream);
-            default: return launch_trace_variant<true, false, 3>(p, sm_count, stream);
-        }
-    }
-    switch (geom) {
-        case 0: return launch_trace_variant<false, true, 1>(p, sm_count, stream);
-        case 1: return launch_trace_variant<false, false, 1>(p, sm_count, stream);
-        case 2: return launch_trace_variant<false, false, 2>(p, sm_count, stream);
-        default: return launch_trace_variant<false, false, 3>(p, sm_count, stream);
-    }
+    // kernel variant: tiny sphere scenes scan the parameter bank (an empty scene without sky is the degenerate case of that);
+    // BVH scenes run the kernel specialised for what they hold
+    const int geom = (p.scene.n_spheres > 0 ? 1 : 0) | (p.scene.n_tris > 0 ? 2 : 0);
+    if (p.small_n > 0 || (geom == 0 && !p.sky_enabled))
+        return stats ? launch_trace_variant<true, true, 1>(p, sm_count, stream) : launch_trace_variant<false, true, 1>(p, sm_count, stream);
+    if (p.sky_enabled) return stats ? launch_trace_bvh<true, true>(p, geom, sm_count, stream) : launch_trace_bvh<false, true>(p, geom, sm_count, stream);
+    return stats ? launch_trace_bvh<true, false>(p, geom, sm_count, stream) : launch_trace_bvh<false, false>(p, geom, sm_count, stream);
 }
 
 int trace_kernel_regs(bool stats) {

@@ -90,6 +90,10 @@ struct TraceParams {
     uint32_t rk[20];             // Philox4x32-10 round keys: rk[2r] = key0 + r*W0, rk[2r+1] = key1 + r*W1
     int fog_enabled;
     float fog_density, fog_r, fog_g, fog_b;
+    // sky extension: a ray that leaves the scene returns AtmosphereConfig.GetSkyColor(direction) (atmosphere.go:100-135) instead
+    // of black; sky[] = the 27 config values of gort_scene_desc::sky_params
+    int sky_enabled;
+    float sky[27];
     // Upper bound on |emitted + w * direct| x |throughput growth| of any further bounce per unit of
     // throughput (host, float64, deliberately loose): used by the exact dead-path test in trace_kernel
     // (a path is dropped once every add it could still make rounds to zero in the fixed-point accumulator).

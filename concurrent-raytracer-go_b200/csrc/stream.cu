@@ -318,12 +318,22 @@ __global__ void __launch_bounds__(128, GORT_POOL_MINB) pool_trace_kernel(const _
                         V.qb[nxt][slot0 + my] = make_float4(q.dx, q.dy, q.dz, q.tbest);
                     } else {
                         store_w(V.qa[nxt] + slot0 + my, kDeadPrim);  // traceRay: miss -> black (renderer.go:171-173)
+                        if (P.sky_enabled) {  // sky extension: ... or the sky
+                            const float3 c = sky_color(P.sky, q.dx, q.dy, q.dz);
+                            add_radiance(P, V.qd[nxt][slot0 + my].y, c.x, c.y, c.z);
+                        }
                     }
                 } else if (SRC == SRC_EXT) {
                     if (q.found) {
                         V.qa[nxt][my] = make_float4(fmaf(q.tbest, q.dx, q.ox), fmaf(q.tbest, q.dy, q.oy), fmaf(q.tbest, q.dz, q.oz), __int_as_float(q.best));
                     } else {
                         store_w(V.qa[nxt] + my, kDeadPrim);
+                        if (P.sky_enabled) {  // sky extension: traceRay(scattered) = sky colour, seen through the path's throughput
+                            const float3 c = sky_color(P.sky, q.dx, q.dy, q.dz);
+                            const float4 T = V.qc[nxt][my];
+                            const float k = P.fog_enabled ? 1.0f - V.qb[nxt][my].w : 1.0f;
+                            add_radiance(P, V.qd[nxt][my].y, T.x * c.x * k, T.y * c.y * k, T.z * c.z * k);
+                        }
                         if (STATS) {
                             const uint32_t dd = __float_as_uint(V.qc[nxt][my].w) >> 16;  // already depth + 1
                             if (dd >= 5) stat_add<STATS>(st, kStatDepth5);

@@ -206,7 +206,10 @@ int gort_scene_upload(gort_ctx* ctx, const gort_scene_desc* desc);
 /* Host mirror of scene.LoadFromFile + GetHittables (scene.go:45-90,104-190) for hosts that are not
  * the Go program: parses the reference's scene JSON, applies its defaults, expands cubes, uploads.
  * options: bit0 = load "triangularPrism" objects (extension; reference skips them, scene.go:80-82)
- *          bit1 = honour the "fog" block (extension; reference ignores it) */
+ *          bit1 = honour the "fog" block (extension; reference ignores it)
+ *          bit2 = honour a "sky" block (extension): {"enabled": true, "preset": "default"|"white"|"sunset"|"night", and any of
+ *                 skyColorTop skyColorBottom sunDirection sunColor sunIntensity sunSize rayleighScattering mieScattering
+ *                 atmosphericDepth fogDensity fogColor hazeIntensity timeOfDay} -> gort_scene_desc::sky_params */
 int gort_scene_load_json(gort_ctx* ctx, const char* json_text, size_t json_len, uint32_t options);
 int gort_scene_load_file(gort_ctx* ctx, const char* path, uint32_t options);
 /* Introspection of the uploaded scene (flattened, reference scan order). */

@@ -25,7 +25,7 @@
 //     mapping with the same distribution as the reference's rejection loop (see Rng).  rng_mode=MT is a sequential mt19937_64 per worker
 //     thread (the reference's global math/rand stream is not reproducible either).
 //   * NaN after tone-map -> 0 (Go leaves uint8(NaN) implementation-defined).
-//   * camera_mode=LOOKAT, triangularPrism objects, exponential fog: SURVEY §8(f).
+//   * camera_mode=LOOKAT, triangularPrism objects, exponential fog, sky gradient: SURVEY §8(f).
 //
 #include <cmath>
 #include <cstdint>
@@ -475,7 +475,45 @@ struct Scene {
     int fog_enabled = 0;
     double fog_density = 0;
     V3 fog_color;
+    // sky extension: AtmosphereConfig (atmosphere/atmosphere.go:8-26); a ray that leaves the scene returns
+    // GetSkyColor(direction) instead of black
+    // oracle-side BVH (use_accel), built on first use and kept while the primitive counts do not change
+    mutable std::shared_ptr<void> accel_cache;
+    mutable size_t accel_cache_spheres = 0, accel_cache_tris = 0;
+    int sky_enabled = 0;
+    V3 sky_top, sky_bottom, sun_dir, sun_color, rayleigh, mie, sky_fog_color;
+    double sun_intensity = 0, sun_size = 0, atm_depth = 0, sky_fog_density = 0, haze = 0, time_of_day = 0;
 };
+
+// FastVec3Lerp is called by atmosphere.go but defined nowhere in the reference: the plain a(1-t) + bt
+static inline V3 lerp3(V3 a, V3 b, double t) { return add(muls(a, 1.0 - t), muls(b, t)); }
+
+// AtmosphereConfig.GetSkyColor — atmosphere/atmosphere.go:100-135
+static V3 sky_color(const Scene& sc, V3 dir) {
+    V3 u = normalize(dir);
+    double t = 0.5 * (u.y + 1.0);
+    V3 sky = lerp3(sc.sky_bottom, sc.sky_top, t);
+    double depth = go_max(0.0, u.y);
+    double atmospheric = std::exp(-depth * sc.atm_depth);
+    V3 scat = lerp3(sc.rayleigh, sc.mie, atmospheric);
+    sky = lerp3(sky, scat, 0.25);
+    double sunDot = dot(u, sc.sun_dir);
+    if (sunDot > (1.0 - sc.sun_size)) {
+        double si = std::pow((sunDot - (1.0 - sc.sun_size)) / sc.sun_size, 1.5);
+        si = go_min(si, 1.0);
+        sky = lerp3(sky, sc.sun_color, si * sc.sun_intensity * 0.9);
+    }
+    double tf = sc.time_of_day;
+    if (tf > 0.5) tf = 1.0 - tf;
+    tf *= 2.0;
+    double darkness = 1.0 - tf * 0.3;
+    sky = muls(sky, darkness);
+    if (sc.sky_fog_density > 0.0) {
+        double ff = std::exp(-sc.sky_fog_density);
+        sky = lerp3(sc.sky_fog_color, sky, ff);
+    }
+    return clamp(sky, 0.1, 0.98);
+}
 
 static void add_mesh_triangle(Scene& s, V3 v0, V3 v1, V3 v2, int mat) {   // NewTriangle triangle.go:13-20
     Triangle t;
@@ -658,7 +696,8 @@ struct Tracer {
     V3 trace_ray(const Ray& ray, int depth, double* primary_t) {
         if (depth >= p.max_depth) return V3{};
         HitRecord hit;
-        if (!hit_world(ray, 0.001, std::numeric_limits<double>::infinity(), hit)) return V3{0.0, 0.0, 0.0};
+        if (!hit_world(ray, 0.001, std::numeric_limits<double>::infinity(), hit))
+            return sc.sky_enabled ? sky_color(sc, ray.d) : V3{0.0, 0.0, 0.0};   // renderer.go:171-173 (sky: extension)
         if (primary_t) *primary_t = hit.t * length(ray.d);   // fog extension: world-space distance
         rng.bounce = (uint32_t)depth;
         const Material& m = sc.mats[hit.material];
@@ -908,11 +947,17 @@ static void render(const Scene& sc, const Params& p, uint8_t* rgba, double* radi
     std::atomic<int> next{0};
     int nthreads = std::max(1, p.threads);
     std::vector<Counters> cnts(nthreads);
-    std::unique_ptr<AccelFull> af;
+    std::shared_ptr<AccelFull> af;
     if (p.use_accel) {
-        af.reset(new AccelFull());
-        af->a.build(sc);
-        af->rank = build_order_rank(sc);
+        if (!sc.accel_cache || sc.accel_cache_spheres != sc.spheres.size() || sc.accel_cache_tris != sc.tris.size()) {
+            std::shared_ptr<AccelFull> fresh(new AccelFull());
+            fresh->a.build(sc);
+            fresh->rank = build_order_rank(sc);
+            sc.accel_cache = fresh;
+            sc.accel_cache_spheres = sc.spheres.size();
+            sc.accel_cache_tris = sc.tris.size();
+        }
+        af = std::static_pointer_cast<AccelFull>(sc.accel_cache);
     }
     auto worker = [&](int tid) {
         Tracer tr(sc, p, af ? reinterpret_cast<const Accel*>(af.get()) : nullptr);
@@ -1049,6 +1094,22 @@ void orc_scene_set_fog(void* sp, int enabled, double density, const double* colo
     s->fog_enabled = enabled;
     s->fog_density = density;
     s->fog_color = V3{color[0], color[1], color[2]};
+}
+// params27: the AtmosphereConfig fields in declaration order (atmosphere.go:8-26)
+void orc_scene_set_sky(void* sp, int enabled, const double* q) {
+    Scene* s = (Scene*)sp;
+    s->sky_enabled = enabled;
+    s->sky_top = V3{q[0], q[1], q[2]}; s->sky_bottom = V3{q[3], q[4], q[5]};
+    s->sun_dir = V3{q[6], q[7], q[8]}; s->sun_color = V3{q[9], q[10], q[11]};
+    s->sun_intensity = q[12]; s->sun_size = q[13];
+    s->rayleigh = V3{q[14], q[15], q[16]}; s->mie = V3{q[17], q[18], q[19]};
+    s->atm_depth = q[20]; s->sky_fog_density = q[21]; s->sky_fog_color = V3{q[22], q[23], q[24]};
+    s->haze = q[25]; s->time_of_day = q[26];
+}
+void orc_sky_color(void* sp, const double* dir, double* out) {
+    Scene* s = (Scene*)sp;
+    V3 c = sky_color(*s, V3{dir[0], dir[1], dir[2]});
+    out[0] = c.x; out[1] = c.y; out[2] = c.z;
 }
 int orc_scene_counts(void* sp, int* n_spheres, int* n_tris, int* n_hittables, int* n_lights) {
     Scene* s = (Scene*)sp;

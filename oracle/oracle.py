@@ -86,6 +86,8 @@ def lib() -> C.CDLL:
         L.orc_scene_add_mesh.argtypes = [C.c_void_p, dp, C.c_int, C.POINTER(OrcMaterial)]
         L.orc_scene_add_light.argtypes = [C.c_void_p, dp, dp, C.c_double]
         L.orc_scene_set_fog.argtypes = [C.c_void_p, C.c_int, C.c_double, dp]
+        L.orc_scene_set_sky.argtypes = [C.c_void_p, C.c_int, dp]
+        L.orc_sky_color.argtypes = [C.c_void_p, dp, dp]
         ip = C.POINTER(C.c_int)
         L.orc_scene_counts.argtypes = [C.c_void_p, ip, ip, ip, ip]
         L.orc_scene_get_triangle.argtypes = [C.c_void_p, C.c_int, dp, ip]
@@ -151,10 +153,34 @@ def make_material(md: dict) -> OrcMaterial:
     return m
 
 
+# NewDefaultAtmosphere / NewWhiteAtmosphere / NewSunsetAtmosphere / NewNightAtmosphere (atmosphere/atmosphere.go:28-98), fields in
+# declaration order: SkyColorTop SkyColorBottom SunDirection SunColor SunIntensity SunSize RayleighScattering MieScattering
+# AtmosphericDepth FogDensity FogColor HazeIntensity TimeOfDay
+SKY_PRESETS = {
+    "default": [0.6, 0.8, 1.0, 0.9, 0.95, 1.0, 0.0, 0.8, -0.6, 1.0, 0.98, 0.95, 1.2, 0.015, 0.6, 0.8, 1.0, 1.0, 0.98, 0.95, 0.3, 0.0, 0.9, 0.92, 0.95, 0.05, 0.6],
+    "white": [0.98, 0.98, 1.0, 0.92, 0.92, 0.95, 0.0, 0.8, -0.6, 1.0, 0.99, 0.97, 0.8, 0.012, 0.9, 0.9, 0.95, 0.95, 0.95, 0.98, 0.2, 0.0, 0.95, 0.95, 0.98, 0.02, 0.6],
+    "sunset": [1.0, 0.4, 0.2, 1.0, 0.8, 0.6, 0.0, 0.3, -0.9, 1.0, 0.6, 0.3, 1.2, 0.03, 1.0, 0.4, 0.2, 1.0, 0.8, 0.6, 0.8, 0.1, 1.0, 0.8, 0.6, 0.3, 0.8],
+    "night": [0.1, 0.1, 0.3, 0.2, 0.2, 0.4, 0.0, -0.7, -0.7, 0.8, 0.8, 1.0, 0.3, 0.005, 0.1, 0.1, 0.3, 0.8, 0.8, 1.0, 0.2, 0.0, 0.1, 0.1, 0.2, 0.0, 0.0],
+}
+_SKY_FIELDS = (("skyColorTop", 0, 3), ("skyColorBottom", 3, 3), ("sunDirection", 6, 3), ("sunColor", 9, 3), ("sunIntensity", 12, 1),
+               ("sunSize", 13, 1), ("rayleighScattering", 14, 3), ("mieScattering", 17, 3), ("atmosphericDepth", 20, 1),
+               ("fogDensity", 21, 1), ("fogColor", 22, 3), ("hazeIntensity", 25, 1), ("timeOfDay", 26, 1))
+
+
+def sky_params(block: dict):
+    """the scene JSON's "sky" block (extension) -> the 27 AtmosphereConfig values: a preset, then per-field overrides"""
+    q = list(SKY_PRESETS[block.get("preset", "default")])
+    for name, off, n in _SKY_FIELDS:
+        if name in block:
+            v = block[name]
+            q[off:off + n] = [float(x) for x in v] if n == 3 else [float(v)]
+    return q
+
+
 class Scene:
     """Oracle-side scene built from a parsed scene JSON dict (scene.go:12-39 schema)."""
 
-    def __init__(self, desc: dict, prisms: bool = False, fog: bool = False):
+    def __init__(self, desc: dict, prisms: bool = False, fog: bool = False, sky: bool = False):
         L = lib()
         self.h = C.c_void_p(L.orc_scene_new())
         cam = desc.get("camera", {})
@@ -181,6 +207,14 @@ class Scene:
         fg = desc.get("fog") or {}
         if fog and fg.get("enabled"):
             L.orc_scene_set_fog(self.h, 1, float(fg.get("density", 0.0)), _d3(_vec3(fg.get("color"))))
+        sk = desc.get("sky") or {}
+        if sky and sk.get("enabled"):
+            L.orc_scene_set_sky(self.h, 1, (C.c_double * 27)(*sky_params(sk)))
+
+    def sky_color(self, direction):
+        out = (C.c_double * 3)()
+        lib().orc_sky_color(self.h, _d3(direction), out)
+        return [out[0], out[1], out[2]]
 
     @classmethod
     def from_flat(cls, camera: dict, materials, spheres, triangles, lights, fog=None) -> "Scene":

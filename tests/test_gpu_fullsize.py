@@ -141,7 +141,7 @@ def test_c5_one_million_primitives(gort, oracle):
         assert (q[..., :3].sum(-1) > 0).mean() > 0.5
         assert Cm.within_one(p, q) >= bar, (depth, Cm.within_one(p, q))
     W, H = 160, 90
-    small = (W // 2 - 12, H // 2 - 8, W // 2 + 12, H // 2 + 8)
+    small = (W // 2 - 5, H // 2 - 3, W // 2 + 5, H // 2 + 3)  # 60 pixels x 1024 spp x depth 32 in float64: ~30 s of oracle time
     x0, y0, x1, y1 = small
     r.SetSamples(1024); r.SetMaxDepth(32); r.SetSoftShadows(True); r.SetAntiAliasing(True); r.SetSeed(3)
     img = r.Render(flat, W, H)

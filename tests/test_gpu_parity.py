@@ -254,6 +254,34 @@ def test_fog_extension(gort, oracle, renderer):
     assert (plain != img).any()
 
 
+@pytest.mark.parametrize("path", ["queue", "stream"])
+def test_sky_extension(gort, oracle, renderer, path):
+    """Sky gradient: a ray that leaves the scene returns AtmosphereConfig.GetSkyColor(direction)
+    (atmosphere/atmosphere.go:100-135) instead of black — primary rays and every bounce — through both BVH render paths,
+    alone and together with the fog extension; off unless the loader is asked for it."""
+    d = all_materials_scene()
+    d["sky"] = {"enabled": True, "preset": "sunset", "sunSize": 0.2, "timeOfDay": 0.3}
+    d["fog"] = {"enabled": True, "density": 0.03, "color": [0.3, 0.3, 0.35], "type": "exponential"}
+    os.environ["GORT_PATH"] = path
+    try:
+        for opts, fog in ((gort.LOAD_SKY, False), (gort.LOAD_SKY | gort.LOAD_FOG, True)):
+            configure(renderer, 3, 8, seed=31)
+            img = renderer.Render(gort.SceneFromDict(d, opts), 480, 300)
+            assert renderer.lastStats.render_path == (1 if path == "queue" else 2)
+            ref, _, _ = oracle.Scene(d, fog=fog, sky=True).render(480, 300, samples=3, max_depth=8, rng_mode=oracle.RNG_PHILOX, seed=31)
+            assert (ref[..., :3].min(-1) > 0).mean() > 0.99  # no black pixel is left
+            check(img, ref)
+        plain = renderer.Render(gort.SceneFromDict(d), 480, 300)
+        assert (plain[..., :3].sum(-1) == 0).mean() > 0.2  # reference behaviour: a miss is black
+        # nothing but sky: an empty scene (no BVH at all)
+        e = {"camera": d["camera"], "objects": [], "lights": [], "sky": {"enabled": True}}
+        img = renderer.Render(gort.SceneFromDict(e, gort.LOAD_SKY), 200, 120)
+        ref, _, _ = oracle.Scene(e, sky=True).render(200, 120, samples=3, max_depth=8, rng_mode=oracle.RNG_PHILOX, seed=31)
+        check(img, ref)
+    finally:
+        del os.environ["GORT_PATH"]
+
+
 def test_c1_golden_fixture(gort, renderer):
     """C1-view 200x150, 4 spp, Philox seed 1 against the committed oracle image and radiance samples."""
     import os

@@ -318,3 +318,24 @@ def test_trace_ray_known_radiance(oracle):
     _, rad, _ = oracle.Scene(d).render(8, 8, samples=1, max_depth=5, jitter=False, want_radiance=True)
     assert np.allclose(rad[4, 4], (0.6, 0.35, 2.1))
     assert rad[0, 0].tolist() == [0, 0, 0]  # miss -> black, not skyColor (renderer.go:171-173)
+
+
+def test_sky_gradient_known_answers(oracle):
+    """GetSkyColor (atmosphere/atmosphere.go:100-135) with NewDefaultAtmosphere (:28-44), hand-derived: straight down
+    t = 0 -> SkyColorBottom, atmospheric = 1 -> MieScattering, 0.75/0.25 blend, no sun, TimeOfDay 0.6 -> darkness 0.76."""
+    s = oracle.Scene({"camera": {"position": [0, 0, 5], "aspectRatio": 1.5}, "objects": [], "lights": [], "sky": {"enabled": True}}, sky=True)
+    down = s.sky_color([0, -2, 0])  # (the direction is normalised first)
+    want = [0.76 * (0.75 * b + 0.25 * m) for b, m in zip((0.9, 0.95, 1.0), (1.0, 0.98, 0.95))]
+    assert np.allclose(down, want, atol=1e-12)
+    # into the sun: sunDot = 1 > 1 - SunSize -> intensity min(1, 1^1.5) * 1.2 * 0.9 = 1.08 (an extrapolating lerp), then the clamp to 0.98
+    sun = s.sky_color([0, 0.8, -0.6])
+    assert max(sun) <= 0.98 and min(sun) >= 0.1
+    # night preset: TimeOfDay 0 -> darkness 1; straight up: t = 1 -> top, atmospheric = exp(-0.2)
+    n = oracle.Scene({"camera": {}, "objects": [], "lights": [], "sky": {"enabled": True, "preset": "night"}}, sky=True)
+    a = np.exp(-0.2)
+    up = n.sky_color([0, 1, 0])
+    want = [max(0.1, 0.75 * t + 0.25 * (r * (1 - a) + m * a)) for t, r, m in zip((0.1, 0.1, 0.3), (0.1, 0.1, 0.3), (0.8, 0.8, 1.0))]
+    assert np.allclose(up, want, atol=1e-12)
+    # off by default: a miss is black (renderer.go:171-173)
+    img, _, _ = oracle.Scene({"camera": {"position": [0, 0, 5], "aspectRatio": 1.5}, "objects": [], "lights": [], "sky": {"enabled": True}}).render(8, 8, samples=1, max_depth=2)
+    assert (img[..., :3] == 0).all()
