@@ -316,6 +316,30 @@ inline float as_float(int32_t i) {
 
 }  // namespace
 
+void pack_sphere(const HostSphere& s, F4& geom, I2& meta) {
+    geom = F4{(float)s.c[0], (float)s.c[1], (float)s.c[2], (float)s.r};
+    meta = I2{s.mat, s.order};
+}
+
+void pack_triangle(const HostTriangle& t, F4 o[4]) {
+    double e1[3], e2[3], nrm[3];
+    for (int a = 0; a < 3; a++) {
+        e1[a] = t.v[1][a] - t.v[0][a];
+        e2[a] = t.v[2][a] - t.v[0][a];
+    }
+    // calculateNormal (triangle.go:30-34): normalize(e1 x e2), zero-safe (vector.go:61-67)
+    nrm[0] = e1[1] * e2[2] - e1[2] * e2[1];
+    nrm[1] = e1[2] * e2[0] - e1[0] * e2[2];
+    nrm[2] = e1[0] * e2[1] - e1[1] * e2[0];
+    double len = std::sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
+    if (len == 0) nrm[0] = nrm[1] = nrm[2] = 0;
+    else for (int a = 0; a < 3; a++) nrm[a] /= len;
+    o[0] = F4{(float)t.v[0][0], (float)t.v[0][1], (float)t.v[0][2], as_float(t.mat)};
+    o[1] = F4{(float)e1[0], (float)e1[1], (float)e1[2], as_float(t.order)};
+    o[2] = F4{(float)e2[0], (float)e2[1], (float)e2[2], 0.f};
+    o[3] = F4{(float)nrm[0], (float)nrm[1], (float)nrm[2], 0.f};
+}
+
 void build_bvh(const HostScene& scene, FlatBvh& out) {
     auto t0 = std::chrono::steady_clock::now();
     {
@@ -499,32 +523,9 @@ void build_bvh(const HostScene& scene, FlatBvh& out) {
 
     auto emit_leaf = [&](const BNode& leaf, uint32_t start) -> int32_t {
         if (leaf.type == 0) {
-            for (int i = 0; i < leaf.count; i++) {
-                const HostSphere& s = scene.spheres[prims_storage[leaf.first + i].idx];
-                out.spheres[start + i] = F4{(float)s.c[0], (float)s.c[1], (float)s.c[2], (float)s.r};
-                out.sphere_meta[start + i] = I2{s.mat, s.order};
-            }
+            for (int i = 0; i < leaf.count; i++) pack_sphere(scene.spheres[prims_storage[leaf.first + i].idx], out.spheres[start + i], out.sphere_meta[start + i]);
         } else {
-            for (int i = 0; i < leaf.count; i++) {
-                const HostTriangle& t = scene.tris[prims_storage[leaf.first + i].idx];
-                double e1[3], e2[3], nrm[3];
-                for (int a = 0; a < 3; a++) {
-                    e1[a] = t.v[1][a] - t.v[0][a];
-                    e2[a] = t.v[2][a] - t.v[0][a];
-                }
-                // calculateNormal (triangle.go:30-34): normalize(e1 x e2), zero-safe (vector.go:61-67)
-                nrm[0] = e1[1] * e2[2] - e1[2] * e2[1];
-                nrm[1] = e1[2] * e2[0] - e1[0] * e2[2];
-                nrm[2] = e1[0] * e2[1] - e1[1] * e2[0];
-                double len = std::sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
-                if (len == 0) nrm[0] = nrm[1] = nrm[2] = 0;
-                else for (int a = 0; a < 3; a++) nrm[a] /= len;
-                F4* o = &out.tris[4 * (size_t)(start + i)];
-                o[0] = F4{(float)t.v[0][0], (float)t.v[0][1], (float)t.v[0][2], as_float(t.mat)};
-                o[1] = F4{(float)e1[0], (float)e1[1], (float)e1[2], as_float(t.order)};
-                o[2] = F4{(float)e2[0], (float)e2[1], (float)e2[2], 0.f};
-                o[3] = F4{(float)nrm[0], (float)nrm[1], (float)nrm[2], 0.f};
-            }
+            for (int i = 0; i < leaf.count; i++) pack_triangle(scene.tris[prims_storage[leaf.first + i].idx], &out.tris[4 * (size_t)(start + i)]);
         }
         uint32_t v = (start & kLeafStartMask) | ((uint32_t)(leaf.count - 1) << kLeafCountShift) | ((uint32_t)leaf.type << kLeafTypeBit);
         return (int32_t)~v;

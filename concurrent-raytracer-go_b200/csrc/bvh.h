@@ -53,6 +53,10 @@ struct FlatBvh {
     double build_ms = 0;
 };
 
+// The device records of one primitive (the layout above), shared by the host builder's leaves and the device builder's input.
+void pack_sphere(const HostSphere& s, F4& geom, I2& meta);
+void pack_triangle(const HostTriangle& t, F4 out[4]);
+
 // Binned-SAH build (16 bins, all 3 axes), leaves of <= kMaxLeafPrims primitives of one type.
 void build_bvh(const HostScene& scene, FlatBvh& out);
 

@@ -10,12 +10,14 @@
 #include <fstream>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/gort.h"
 #include "bvh.h"
 #include "host_scene.h"
 #include "kernels.h"
+#include "lbvh.h"
 #include "stream.h"
 
 using namespace gort;
@@ -61,6 +63,8 @@ struct DeviceState {
     // cull pass, under the trace kernel; only the kept blocks wait for the end
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_cull = nullptr, ev_aux = nullptr;
+    uint8_t* d_build = nullptr;   // device BVH build: primitive arrays in scene order + scratch
+    size_t build_bytes = 0;
     cudaEvent_t ev_tc = nullptr;  // end of the cull pass (timing): trace_ms starts here
     // global-queue wavefront pipeline (stream.cu): path / record / pair queues of one batch, counter ring, readback
     uint8_t* d_stream = nullptr;
@@ -87,6 +91,10 @@ struct gort_ctx {
     bool peer_direct = false;  // multi-device ctx: all devices can store into the lead device's memory
     std::string err;
     double upload_ms = 0, bvh_ms = 0;
+    size_t bvh_bytes = 0;     // node + primitive arrays on the device
+    bool bvh_on_device = false;  // built by lbvh.cu: ctx->bvh holds the counts and the grid only
+    uint8_t* h_build = nullptr;  // page-locked staging of the device builder's input (primitives, materials, lights), kept across uploads
+    size_t h_build_bytes = 0;
     // last render (for gort_read_radiance)
     int last_w = 0, last_h = 0, last_samples = 0, last_rank = 0, last_count = 1;
     std::vector<int> last_local_tiles;  // per device
@@ -210,6 +218,133 @@ void pack_material(const HostMaterial& m, F4 out[4]) {
     out[3] = F4{(float)spec_power, (float)f0, (float)fs, (float)mf};
 }
 
+// Large scenes: the BVH is built on the device (lbvh.cu).  The host packs the primitives in scene order (parallel), one H2D
+// copy per array, and the builder writes the node / primitive arrays the kernels read.  Returns GORT_OK, an error, or
+// 1 = "use the host builder" (tree deeper than the traversal stack: many coincident centroids).
+int upload_scene_device_bvh(gort_ctx* ctx) {
+    const double t0 = now_ms();
+    const HostScene& hs = ctx->scene;
+    const size_t nS = hs.spheres.size(), nT = hs.tris.size(), n = nS + nT;
+    const bool times = getenv("GORT_BVH_TIMES") != nullptr;
+    auto lap = [&](const char* what) {
+        if (times) fprintf(stderr, "[gort lbvh] %-28s %8.2f ms\n", what, now_ms() - t0);
+    };
+    // everything the device needs is packed straight into page-locked memory (kept across uploads): no staging copy, and the
+    // H2D copies run at PCIe speed
+    auto a256 = [](size_t v) { return (v + 255) / 256 * 256; };
+    const size_t nM = hs.mats.size(), nL = hs.lights.size();
+    const size_t off_sph = 0, off_meta = off_sph + a256(nS * 16), off_tri = off_meta + a256(nS * 8), in_bytes = off_tri + a256(nT * 64);
+    const size_t off_mats = in_bytes, off_lights = off_mats + a256(nM * 64), stage_bytes = off_lights + a256(nL * 32);
+    if (ctx->h_build_bytes < stage_bytes) {
+        if (ctx->h_build) CUDA_TRY(ctx, cudaFreeHost(ctx->h_build));
+        ctx->h_build = nullptr; ctx->h_build_bytes = 0;
+        CUDA_TRY(ctx, cudaHostAlloc(&ctx->h_build, stage_bytes, cudaHostAllocPortable));
+        ctx->h_build_bytes = stage_bytes;
+    }
+    F4* sph = reinterpret_cast<F4*>(ctx->h_build + off_sph);
+    I2* meta = reinterpret_cast<I2*>(ctx->h_build + off_meta);
+    F4* tri = reinterpret_cast<F4*>(ctx->h_build + off_tri);
+    F4* mats = reinterpret_cast<F4*>(ctx->h_build + off_mats);
+    F4* lights = reinterpret_cast<F4*>(ctx->h_build + off_lights);
+    lap("staging buffer");
+    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<double> lo(hw * 3, 1e300), hi(hw * 3, -1e300);
+    auto work = [&](unsigned t) {
+        double* l = &lo[t * 3];
+        double* h = &hi[t * 3];
+        for (size_t i = nS * t / hw; i < nS * (t + 1) / hw; i++) {
+            pack_sphere(hs.spheres[i], sph[i], meta[i]);
+            const double r = std::fabs(hs.spheres[i].r);
+            for (int a = 0; a < 3; a++) { l[a] = std::min(l[a], hs.spheres[i].c[a] - r); h[a] = std::max(h[a], hs.spheres[i].c[a] + r); }
+        }
+        for (size_t i = nT * t / hw; i < nT * (t + 1) / hw; i++) {
+            pack_triangle(hs.tris[i], &tri[4 * i]);
+            for (int k = 0; k < 3; k++)
+                for (int a = 0; a < 3; a++) { l[a] = std::min(l[a], hs.tris[i].v[k][a]); h[a] = std::max(h[a], hs.tris[i].v[k][a]); }
+        }
+        for (size_t i = nM * t / hw; i < nM * (t + 1) / hw; i++) pack_material(hs.mats[i], &mats[4 * i]);
+    };
+    {
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < hw; t++) pool.emplace_back(work, t);
+        work(0);
+        for (auto& th : pool) th.join();
+    }
+    for (size_t i = 0; i < nL; i++) {
+        const HostLight& l = hs.lights[i];
+        lights[2 * i] = F4{(float)l.pos[0], (float)l.pos[1], (float)l.pos[2], (float)l.intensity};
+        lights[2 * i + 1] = F4{(float)l.color[0], (float)l.color[1], (float)l.color[2], 0.f};
+    }
+    lap("primitives + materials packed");
+    double wlo[3] = {1e300, 1e300, 1e300}, whi[3] = {-1e300, -1e300, -1e300};
+    for (unsigned t = 0; t < hw; t++)
+        for (int a = 0; a < 3; a++) { wlo[a] = std::min(wlo[a], lo[t * 3 + a]); whi[a] = std::max(whi[a], hi[t * 3 + a]); }
+    LbvhIn in;
+    memset(&in, 0, sizeof(in));
+    in.n_spheres = (uint32_t)nS; in.n_tris = (uint32_t)nT;
+    double extent = 0;
+    for (int a = 0; a < 3; a++) extent = std::max(extent, std::max(std::fabs(wlo[a]), std::fabs(whi[a])));
+    const double pad = 4e-7 * std::max(1.0, extent);  // as bvh.cpp
+    in.pad = (float)pad;
+    FlatBvh& b = ctx->bvh;
+    b = FlatBvh();
+    for (int a = 0; a < 3; a++) {
+        in.world_lo[a] = (float)wlo[a]; in.world_hi[a] = (float)whi[a];
+        const double l = wlo[a] - 4.0 * pad, h = whi[a] + 4.0 * pad;  // (the device pads in fp32: a little more room than the host grid)
+        const double qc = std::max((h - l) / 65520.0, 1e-30);
+        b.qcell[a] = (float)qc;
+        b.qorigin[a] = (float)(l - 8.0 * qc);
+        in.qcell[a] = b.qcell[a]; in.qorigin[a] = b.qorigin[a];
+    }
+    b.n_nodes = (int32_t)(n - 1);
+    int max_depth = 0;
+    for (size_t i = 0; i < ctx->devs.size(); i++) {
+        DeviceState& d = ctx->devs[i];
+        CUDA_TRY(ctx, cudaSetDevice(d.dev));
+        cudaStream_t st = stream_of(ctx, (int)i);
+        if (d.blob_in_use) {
+            d.d_nodes = d.d_spheres = d.d_tris = d.d_mats = d.d_lights = nullptr;
+            d.d_meta = nullptr;
+            d.cap_nodes = d.cap_spheres = d.cap_meta = d.cap_tris = d.cap_mats = d.cap_lights = 0;
+            d.blob_in_use = false;
+        }
+        const size_t scratch = lbvh_scratch_bytes((uint32_t)n);
+        if (int rc = ensure(ctx, d.d_build, d.build_bytes, in_bytes + scratch)) return rc;
+        float4* d_sph_in = (float4*)(d.d_build + off_sph);
+        int2* d_meta_in = (int2*)(d.d_build + off_meta);
+        float4* d_tri_in = (float4*)(d.d_build + off_tri);
+        CUDA_TRY(ctx, cudaMemcpyAsync(d.d_build, ctx->h_build, in_bytes, cudaMemcpyHostToDevice, st));  // the three primitive arrays at once
+        if (int rc = ensure(ctx, d.d_nodes, d.cap_nodes, (n - 1) * 6 * sizeof(F4))) return rc;
+        if (int rc = ensure(ctx, d.d_spheres, d.cap_spheres, nS * sizeof(F4))) return rc;
+        if (int rc = ensure(ctx, d.d_meta, d.cap_meta, nS * sizeof(I2))) return rc;
+        if (int rc = ensure(ctx, d.d_tris, d.cap_tris, nT * 4 * sizeof(F4))) return rc;
+        if (int rc = ensure(ctx, d.d_mats, d.cap_mats, nM * 4 * sizeof(F4))) return rc;
+        if (int rc = ensure(ctx, d.d_lights, d.cap_lights, nL * 2 * sizeof(F4))) return rc;
+        if (nM) CUDA_TRY(ctx, cudaMemcpyAsync(d.d_mats, mats, nM * 4 * sizeof(F4), cudaMemcpyHostToDevice, st));
+        if (nL) CUDA_TRY(ctx, cudaMemcpyAsync(d.d_lights, lights, nL * 2 * sizeof(F4), cudaMemcpyHostToDevice, st));
+        in.spheres = d_sph_in; in.sphere_meta = d_meta_in; in.tris = d_tri_in;
+        LbvhOut out;
+        out.nodes = d.d_nodes; out.spheres = d.d_spheres; out.sphere_meta = d.d_meta; out.tris = d.d_tris;
+        int depth_i = 0;
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        lap("buffers + H2D");
+        CUDA_TRY(ctx, lbvh_build(in, out, d.d_build + in_bytes, scratch, &depth_i, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        lap("device build");
+        max_depth = std::max(max_depth, depth_i);
+    }
+    if (times) fprintf(stderr, "[gort lbvh] %zu primitives, %zu inner nodes, depth %d%s\n", n, n - 1, max_depth, max_depth > 62 ? " -> host builder" : "");
+    if (max_depth > 62) return 1;
+    b.max_depth = max_depth;
+    ctx->bvh_on_device = true;
+    ctx->bvh_bytes = (n - 1) * 6 * sizeof(F4) + nS * (sizeof(F4) + sizeof(I2)) + nT * 4 * sizeof(F4);
+    ctx->has_scene = true;
+    ctx->bvh_ms = now_ms() - t0;  // pack + H2D + device build
+    b.build_ms = ctx->bvh_ms;
+    ctx->upload_ms = 0;
+    return GORT_OK;
+}
+
 int upload_scene(gort_ctx* ctx) {
     const double t0 = now_ms();
     // limits of the device code: a leaf's first primitive is a 26-bit index per primitive type; the walks keep a 64-entry stack
@@ -217,8 +352,23 @@ int upload_scene(gort_ctx* ctx) {
         ctx->has_scene = false;
         return fail(ctx, GORT_ERR_INVALID, "scene too large: at most 2^26 spheres and 2^26 triangles");
     }
+    {
+        // which builder: binned SAH on the host (better trees, ~0.45 s per million primitives) or LBVH on the device (a few ms)
+        const size_t n_prims = ctx->scene.spheres.size() + ctx->scene.tris.size();
+        const char* which = getenv("GORT_BVH");
+        const char* mn = getenv("GORT_BVH_DEVICE_MIN");
+        const size_t device_min = mn ? (size_t)atoll(mn) : (size_t)200000;
+        const bool on_device = n_prims >= 2 && (which ? !strcmp(which, "device") : n_prims >= device_min);
+        ctx->bvh_on_device = false;
+        if (on_device) {
+            const int rc = upload_scene_device_bvh(ctx);
+            if (rc != 1) return rc;
+        }
+    }
     build_bvh(ctx->scene, ctx->bvh);
     ctx->bvh_ms = ctx->bvh.build_ms;
+    ctx->bvh_bytes = ctx->bvh.nodes.size() * sizeof(F4) + ctx->bvh.spheres.size() * sizeof(F4) + ctx->bvh.sphere_meta.size() * sizeof(I2) +
+                     ctx->bvh.tris.size() * sizeof(F4);
     if (ctx->bvh.max_depth > 62) {
         ctx->has_scene = false;
         return fail(ctx, GORT_ERR_INVALID, "BVH deeper than the traversal stack (62 levels): degenerate geometry");
@@ -614,6 +764,12 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     tp.fog_enabled = ctx->scene.fog_enabled;
     tp.fog_density = (float)ctx->scene.fog_density;
     tp.fog_r = (float)ctx->scene.fog_color[0]; tp.fog_g = (float)ctx->scene.fog_color[1]; tp.fog_b = (float)ctx->scene.fog_color[2];
+    {
+        const double ex = 65520.0 * ctx->bvh.qcell[0], ey = 65520.0 * ctx->bvh.qcell[1], ez = 65520.0 * ctx->bvh.qcell[2];
+        const double vol = ex * ey * ez;
+        const double n_prims = (double)(ctx->scene.spheres.size() + ctx->scene.tris.size());
+        tp.cone_skip = (vol > 0 && !getenv("GORT_NO_CONE_SKIP")) ? (float)(n_prims / vol * 0.010578) : 0.f;
+    }
     tp.sky_enabled = ctx->scene.sky_enabled;
     for (int k = 0; k < 27; k++) tp.sky[k] = (float)ctx->scene.sky_params[k];
     CUDA_TRY(ctx, launch_cull(tp, d.d_active, d.d_counter + 1, st));
@@ -661,8 +817,7 @@ int collect_stats(gort_ctx* ctx, const gort_render_params* p, gort_stats* s, dou
     s->upload_ms = ctx->upload_ms;
     s->bvh_build_ms = ctx->bvh_ms;
     s->bvh_nodes = (uint64_t)ctx->bvh.n_nodes;
-    s->bvh_bytes = ctx->bvh.nodes.size() * sizeof(F4) + ctx->bvh.spheres.size() * sizeof(F4) + ctx->bvh.sphere_meta.size() * sizeof(I2) +
-                   ctx->bvh.tris.size() * sizeof(F4);
+    s->bvh_bytes = ctx->bvh_bytes;
     unsigned long long tot[kStatCount] = {0};
     int64_t pixels = 0;
     const int tiles_x = (p->width + kTile - 1) / kTile;
@@ -818,10 +973,11 @@ void gort_destroy(gort_ctx* ctx) {
         if (d.ev_aux) cudaEventDestroy(d.ev_aux);
         if (d.ev_tc) cudaEventDestroy(d.ev_tc);
         if (d.ev_count) cudaEventDestroy(d.ev_count);
-        cudaFree(d.d_stream); cudaFree(d.d_ctl);
+        cudaFree(d.d_stream); cudaFree(d.d_ctl); cudaFree(d.d_build);
         if (d.h_count) cudaFreeHost(d.h_count);
         if (d.own_stream) cudaStreamDestroy(d.own_stream);
     }
+    if (ctx->h_build) cudaFreeHost(ctx->h_build);
     delete ctx;
 }
 

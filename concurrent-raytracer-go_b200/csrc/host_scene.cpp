@@ -6,6 +6,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <thread>
+#include <vector>
 
 #include "json.h"
 
@@ -328,8 +330,22 @@ std::string scene_from_desc(const gort_scene_desc& d, HostScene& out) {
     memcpy(out.cam_up, d.cam_up, sizeof(out.cam_up));
     out.cam_fov = d.cam_fov;
     out.cam_aspect = d.cam_aspect;
+    // large scenes (10^5..10^6 primitives, one material per object): the copies below run on all host threads
+    const int64_t n_prims = (int64_t)d.n_spheres + d.n_triangles;
+    const unsigned hw = (n_prims + d.n_materials) >= 100000 ? std::max(1u, std::min(16u, std::thread::hardware_concurrency())) : 1u;
+    std::vector<const char*> errs(hw, nullptr);
+    auto parallel = [&](int64_t count, auto&& body) {
+        std::vector<std::thread> pool;
+        auto run = [&](unsigned t) {
+            for (int64_t i = count * t / hw; i < count * (t + 1) / hw && !errs[t]; i++)
+                if (const char* e = body(i)) errs[t] = e;
+        };
+        for (unsigned t = 1; t < hw; t++) pool.emplace_back(run, t);
+        run(0);
+        for (auto& th : pool) th.join();
+    };
     out.mats.resize(d.n_materials);
-    for (int i = 0; i < d.n_materials; i++) {
+    parallel(d.n_materials, [&](int64_t i) -> const char* {
         HostMaterial& m = out.mats[i];
         m.type = d.mat_type[i];
         if (m.type < GORT_MAT_LAMBERTIAN || m.type > GORT_MAT_DIFFUSELIGHT) return "unknown material type";
@@ -340,16 +356,15 @@ std::string scene_from_desc(const gort_scene_desc& d, HostScene& out) {
         m.ior = d.mat_ior[i];
         if (m.type == GORT_MAT_PERFECTMIRROR) m.metallic = 1.0;  // GetMetallic advanced_materials.go:165
         if (m.type == GORT_MAT_DIELECTRIC) m.color[0] = m.color[1] = m.color[2] = 1.0;  // GetAlbedo material.go:266
-    }
-    const int64_t n_prims = (int64_t)d.n_spheres + d.n_triangles;
-    std::vector<char> seen((size_t)n_prims, 0);
-    auto check_order = [&](int32_t o) -> bool {
-        if (o < 0 || o >= n_prims || seen[o]) return false;
-        seen[o] = 1;
-        return true;
+        return nullptr;
+    });
+    std::vector<unsigned char> seen((size_t)n_prims, 0);
+    auto check_order = [&](int32_t o) -> bool {  // every scan position taken exactly once (atomic: the loops run on several threads)
+        if (o < 0 || o >= n_prims) return false;
+        return __atomic_exchange_n(&seen[o], (unsigned char)1, __ATOMIC_RELAXED) == 0;
     };
     out.spheres.resize(d.n_spheres);
-    for (int i = 0; i < d.n_spheres; i++) {
+    parallel(d.n_spheres, [&](int64_t i) -> const char* {
         HostSphere& s = out.spheres[i];
         memcpy(s.c, d.sphere_center + 3 * i, sizeof(s.c));
         s.r = d.sphere_radius[i];
@@ -357,16 +372,20 @@ std::string scene_from_desc(const gort_scene_desc& d, HostScene& out) {
         s.order = d.sphere_order[i];
         if (s.mat < 0 || s.mat >= d.n_materials) return "sphere material index out of range";
         if (!check_order(s.order)) return "sphere_order is not a permutation of the scan order";
-    }
+        return nullptr;
+    });
     out.tris.resize(d.n_triangles);
-    for (int i = 0; i < d.n_triangles; i++) {
+    parallel(d.n_triangles, [&](int64_t i) -> const char* {
         HostTriangle& t = out.tris[i];
         memcpy(t.v, d.tri_vertices + 9 * i, sizeof(t.v));
         t.mat = d.tri_material[i];
         t.order = d.tri_order[i];
         if (t.mat < 0 || t.mat >= d.n_materials) return "triangle material index out of range";
         if (!check_order(t.order)) return "tri_order is not a permutation of the scan order";
-    }
+        return nullptr;
+    });
+    for (const char* e : errs)
+        if (e) return e;
     out.lights.resize(d.n_lights);
     for (int i = 0; i < d.n_lights; i++) {
         HostLight& l = out.lights[i];

@@ -94,6 +94,10 @@ struct TraceParams {
     // of black; sky[] = the 27 config values of gort_scene_desc::sky_params
     int sky_enabled;
     float sky[27];
+    // wavefront pipeline: primitives per unit volume of the world box x the volume factor of a shadow cone (pi/3 tan^2(asin 0.1)).
+    // A lit pair whose cone is expected to hold far more primitives than a candidate list takes skips its cone walk and sends
+    // its 16 rays through the BVH at once (same answers either way; 0 = always walk the cone)
+    float cone_skip;
     // Upper bound on |emitted + w * direct| x |throughput growth| of any further bounce per unit of
     // throughput (host, float64, deliberately loose): used by the exact dead-path test in trace_kernel
     // (a path is dropped once every add it could still make rounds to zero in the fixed-point accumulator).

@@ -664,7 +664,18 @@ __global__ void __launch_bounds__(128, GORT_POOL_MINB) pool_cone_kernel(const __
                     tmax = dist2 * inv_d;
                     nx = nn.x; ny = nn.y; nz = nn.z;
                     thr = tangent_threshold(dot3(nx, ny, nz, ax, ay, az), ox, oy, oz);
-                    if (P.no_cone_cull) {  // test switch: every pair's rays walk the BVH
+                    bool skip = P.no_cone_cull != 0;  // test switch: every pair's rays walk the BVH
+                    if (!skip && P.cone_skip > 0.f) {
+                        // how many primitives does the cone hold, at the scene's mean density, up to where its axis leaves the world
+                        // box (or reaches the light)?  Far more than a candidate list takes: do not walk the cone at all
+                        const float wlx = fmaf(8.0f, S.qcx, S.qox), wly = fmaf(8.0f, S.qcy, S.qoy), wlz = fmaf(8.0f, S.qcz, S.qoz);
+                        const float tx = ((ax > 0.f ? fmaf(65520.0f, S.qcx, wlx) : wlx) - ox) * rcp_fast(fabsf(ax) > 1e-12f ? ax : 1e-12f);
+                        const float ty = ((ay > 0.f ? fmaf(65520.0f, S.qcy, wly) : wly) - oy) * rcp_fast(fabsf(ay) > 1e-12f ? ay : 1e-12f);
+                        const float tz = ((az > 0.f ? fmaf(65520.0f, S.qcz, wlz) : wlz) - oz) * rcp_fast(fabsf(az) > 1e-12f ? az : 1e-12f);
+                        const float L = fmaxf(0.f, fminf(fminf(tx, ty), fminf(tz, tmax)));
+                        skip = P.cone_skip * L * L * L > 8.0f * (float)kMaxCand;
+                    }
+                    if (skip) {
                         cg::coalesced_group g = cg::coalesced_threads();
                         uint32_t wb = 0;
                         if (g.thread_rank() == 0) wb = atomicAdd(V.ctl + cb + kCtlWalk, g.size());
