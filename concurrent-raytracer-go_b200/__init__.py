@@ -80,6 +80,7 @@ class RenderParams(C.Structure):
         ("anti_aliasing", C.c_int32), ("recursive_reflections", C.c_int32), ("soft_shadows", C.c_int32),
         ("camera_mode", C.c_int32), ("shard_rank", C.c_int32), ("shard_count", C.c_int32), ("collect_stats", C.c_int32),
         ("seed", C.c_uint64),
+        ("crop_x0", C.c_int32), ("crop_y0", C.c_int32), ("crop_x1", C.c_int32), ("crop_y1", C.c_int32),
     ]
 
 
@@ -368,6 +369,7 @@ class ParallelRenderer:
         self.seed = 0
         self.shardRank, self.shardCount = 0, 1
         self.collectStats = False
+        self.crop = (0, 0, 0, 0)
         self._scene_token = None
         self.lastStats: Optional[Stats] = None
         self._bench_raw = None
@@ -385,6 +387,10 @@ class ParallelRenderer:
     def SetSeed(self, seed: int): self.seed = int(seed)
     def SetShard(self, rank: int, count: int): self.shardRank, self.shardCount = int(rank), int(count)
     def SetCollectStats(self, v: bool): self.collectStats = bool(v)
+
+    def SetCrop(self, x0: int = 0, y0: int = 0, x1: int = 0, y1: int = 0):
+        """region render (RenderChunk): only [x0, x1) x [y0, y1) is traced, the rest of the frame is black; () = whole frame"""
+        self.crop = (int(x0), int(y0), int(x1), int(y1))
 
     def GetStats(self) -> dict:  # settings.go:27-37
         return {"workers": self.numWorkers, "samples": self.samples, "maxDepth": self.maxDepth,
@@ -424,7 +430,7 @@ class ParallelRenderer:
 
     def _params(self, width: int, height: int) -> RenderParams:
         key = (width, height, self.samples, self.maxDepth, self.antiAliasing, self.recursiveReflections, self.softShadows,
-               self.cameraMode, self.shardRank, self.shardCount, self.collectStats, self.seed)
+               self.cameraMode, self.shardRank, self.shardCount, self.collectStats, self.seed, self.crop)
         if self._params_cache is not None and self._params_cache[0] == key:
             return self._params_cache[1]
         p = RenderParams()
@@ -437,6 +443,7 @@ class ParallelRenderer:
         p.shard_rank, p.shard_count = self.shardRank, self.shardCount
         p.collect_stats = int(self.collectStats)
         p.seed = self.seed
+        p.crop_x0, p.crop_y0, p.crop_x1, p.crop_y1 = self.crop
         self._params_cache = (key, p)
         return p
 

@@ -538,6 +538,8 @@ int validate(gort_ctx* ctx, const gort_render_params* p) {
     const int sc = p->shard_count <= 0 ? 1 : p->shard_count;
     if (p->shard_rank < 0 || p->shard_rank >= sc) return fail(ctx, GORT_ERR_INVALID, "shard_rank out of range");
     if (p->camera_mode != GORT_CAMERA_REFERENCE && p->camera_mode != GORT_CAMERA_LOOKAT) return fail(ctx, GORT_ERR_INVALID, "camera_mode");
+    if (p->crop_x1 > p->crop_x0 && (p->crop_x0 < 0 || p->crop_y0 < 0 || p->crop_x1 > p->width || p->crop_y1 > p->height || p->crop_y1 <= p->crop_y0))
+        return fail(ctx, GORT_ERR_INVALID, "crop rectangle outside the frame");
     return GORT_OK;
 }
 
@@ -737,6 +739,7 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     tp.jitter = p->anti_aliasing ? 1 : 0; tp.recursive = p->recursive_reflections ? 1 : 0; tp.soft = p->soft_shadows ? 1 : 0;
     tp.tiles_x = tiles_x; tp.tiles_y = tiles_y;
     tp.shard_rank = eff_rank; tp.shard_count = eff_count; tp.n_local_tiles = n_local;
+    tp.crop_x0 = p->crop_x0; tp.crop_y0 = p->crop_y0; tp.crop_x1 = p->crop_x1; tp.crop_y1 = p->crop_y1;
     // work units = (sample batch, active 8x4 block), sized on the device: aim for >= 16 per resident warp
     {
         // work units per resident warp.  Measured 4 / 8 / 16 / 32 / 64: C2-view 0.777 / 0.709 / 0.667 / 0.667 / 0.665 ms

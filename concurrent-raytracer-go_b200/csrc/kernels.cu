@@ -797,6 +797,8 @@ __global__ void __launch_bounds__(128) cull_kernel(const __grid_constant__ Trace
     const uint32_t x0 = tx * kTile + ((block & 3u) << 3), y0 = ty * kTile + ((block >> 2) << 2);
     if (x0 >= (uint32_t)P.width || y0 >= (uint32_t)P.height) return;
     const uint32_t x1 = min(x0 + 8u, (uint32_t)P.width), y1 = min(y0 + 4u, (uint32_t)P.height);
+    // region render (RenderChunk): a block that does not touch the region is not traced
+    if (P.crop_x1 > P.crop_x0 && ((int)x1 <= P.crop_x0 || (int)x0 >= P.crop_x1 || (int)y1 <= P.crop_y0 || (int)y0 >= P.crop_y1)) return;
     // (u,v) rectangle of every sample of the block, widened by a rounding margin
     const float u0 = ((float)x0 - 1e-3f) / (float)P.width, u1 = ((float)x1 + 1e-3f) / (float)P.width;
     const float v0 = ((float)y0 - 1e-3f) / (float)P.height, v1 = ((float)y1 + 1e-3f) / (float)P.height;

@@ -77,6 +77,7 @@ struct TraceParams {
     int jitter, recursive, soft;
     int tiles_x, tiles_y;
     int shard_rank, shard_count, n_local_tiles;
+    int crop_x0, crop_y0, crop_x1, crop_y1;  // region render: blocks outside are not traced (crop_x1 <= crop_x0: whole frame)
     uint32_t target_units;           // desired number of work units (dynamic balance), see trace_kernel
     const uint32_t* active_list;     // pixel blocks kept by the cull pass: (local tile << 5) | block;
                                      // [0, n_deep) from the front, n_norm more from the back of [0, 32*n_local_tiles)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GORT_ABI_VERSION 3u /* 3: sky extension in gort_scene_desc; gort_stats: cull_ms, primary_generated, render_path, kernel_launches */
+#define GORT_ABI_VERSION 3u /* 3: sky extension in gort_scene_desc; gort_stats: cull_ms, primary_generated, render_path, kernel_launches; gort_render_params: crop */
 #define GORT_MAX_DEVICES 8
 #define GORT_TILE 32 /* createRenderTasks tileSize, renderer.go:401 */
 
@@ -141,6 +141,10 @@ typedef struct gort_render_params {
     int32_t shard_count;           /*   tile_id % shard_count == shard_rank (0/1 = whole frame)  */
     int32_t collect_stats;         /* 1 = also count ray segments / node visits / primitive tests (slower kernel variant) */
     uint64_t seed;                 /* Philox key; the image is a pure function of (scene, params, seed) */
+    /* Region render (the reference's RenderChunk, internal/distributed/distributed_renderer.go:29-39): only the pixel blocks that
+     * touch [crop_x0, crop_x1) x [crop_y0, crop_y1) are traced; every other pixel of the frame is written black.  Pixels inside
+     * the region are bit-identical to the full frame's.  crop_x1 <= crop_x0 (all zero): the whole frame. */
+    int32_t crop_x0, crop_y0, crop_x1, crop_y1;
 } gort_render_params;
 
 typedef struct gort_stats {
