@@ -239,7 +239,9 @@ int gort_render(gort_ctx* ctx, const gort_render_params* params, uint8_t* rgba_o
 int gort_host_alloc(size_t bytes, void** out);
 void gort_host_free(void* p);
 /* Same frame, but the row-major RGBA8 image stays in device memory (device_ids[0]); d_rgba is a
- * device pointer with width*height*4 bytes.  Asynchronous on the ctx stream unless stats_out != NULL. */
+ * device pointer with width*height*4 bytes.  Stream-ordered on the ctx stream; returns without waiting for the frame unless
+ * stats_out != NULL — except for large scenes (render_path 2), whose bounce loop is driven from the host and has finished all
+ * but the resolve pass when the call returns. */
 int gort_render_device(gort_ctx* ctx, const gort_render_params* params, void* d_rgba, size_t rgba_bytes,
                        gort_stats* stats_out);
 /* Multi-process sharding (one process per GPU): render only this shard's tiles into a TILE-MAJOR
