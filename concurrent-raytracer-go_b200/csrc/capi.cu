@@ -549,7 +549,7 @@ int validate(gort_ctx* ctx, const gort_render_params* p) {
 // GORT_PATH=queue|stream overrides the size rule (tests render the same scene through both).
 enum RenderPath { kPathSmall = 0, kPathQueue = 1, kPathStream = 2 };
 
-int choose_path(const gort_ctx* ctx) {
+int choose_path(const gort_ctx* ctx, const gort_render_params* p) {
     const HostScene& hs = ctx->scene;
     const size_t n_prims = hs.spheres.size() + hs.tris.size();
     const bool small_ok = hs.tris.empty() && !hs.spheres.empty() && (int)hs.spheres.size() <= kSmallMax && (int)hs.mats.size() <= kSmallMax &&
@@ -559,9 +559,14 @@ int choose_path(const gort_ctx* ctx) {
     if (force && !strcmp(force, "stream") && stream_ok) return kPathStream;
     if (force && !strcmp(force, "queue")) return small_ok ? kPathSmall : kPathQueue;
     if (small_ok) return kPathSmall;
+    // The pipeline pays ~10 launches per bounce whatever the frame holds: it wins once a frame has enough rays to fill them.
+    // Measured crossover (profiles/README.md): C4 (depth 16) ~8 M primary samples per frame, C5 (depth 32) ~12 M.
     const char* mp = getenv("GORT_STREAM_MIN_PRIMS");
+    const char* ms = getenv("GORT_STREAM_MIN_SAMPLES");
     const size_t min_prims = mp ? (size_t)atoll(mp) : 4096;
-    return (stream_ok && n_prims >= min_prims) ? kPathStream : kPathQueue;
+    const int64_t min_samples = ms ? (int64_t)atoll(ms) : (int64_t)12 << 20;
+    const int64_t frame_samples = (int64_t)p->width * p->height * p->samples;
+    return (stream_ok && n_prims >= min_prims && frame_samples >= min_samples) ? kPathStream : kPathQueue;
 }
 
 // The wavefront pipeline for one device's share of the frame: batches of samples, one bounce at a time (stream.h).
@@ -699,7 +704,7 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     tp.inv_w = 1.0f / (float)p->width; tp.inv_h = 1.0f / (float)p->height;
     // tiny sphere-only scenes: the spheres ride in the kernel parameters, in scan order
     tp.small_n = 0;
-    const int path = choose_path(ctx);
+    const int path = choose_path(ctx, p);
     d.last_path = path;
     d.last_launches = 0;
     if (path == kPathSmall) {
