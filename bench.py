@@ -282,13 +282,13 @@ def main():
             return launches_per_frame[0]  # libgort kernels (memsets and the L2 flush are not counted)
         if link is not None:
             r.RenderLinked(W, H, link)
-            return 5  # (release | -) + cull + trace + (- | wait) + resolve + (wait | signal)
+            return launches_per_frame[0] + 2  # + (release | -) + (wait | signal)
         r.RenderShardDevice(W, H, slab.data_ptr())
         dist.all_gather_into_tensor(gathered, slab)
         if rank == 0:
             r.UnswizzleDevice(gathered.data_ptr(), world, W, H, frame.data_ptr())
-            return 4  # + unswizzle (the all-gather is NCCL's)
-        return 3
+            return launches_per_frame[0] + 1  # + unswizzle (the all-gather is NCCL's)
+        return launches_per_frame[0]
 
     def step_e2e():
         """public API with host buffers: scene upload (host flatten + BVH + H2D) and frame D2H inside the step"""
@@ -322,6 +322,9 @@ def main():
     barrier()
     if world == 1:
         launches_per_frame[0] = int(r.RenderDevice(W, H, frame.data_ptr(), want_stats=True).kernel_launches)
+    else:
+        launches_per_frame[0] = int(r.RenderShardDevice(W, H, slab.data_ptr(), want_stats=True).kernel_launches)
+        barrier()
 
     # ---- timed: K steps, device events per step, L2 flushed between steps (outside the events) ----
     sampler = ClockSampler(local_rank)
