@@ -63,6 +63,7 @@ struct DeviceState {
     // cull pass, under the trace kernel; only the kept blocks wait for the end
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_cull = nullptr, ev_aux = nullptr;
+    uint64_t wide_serial = 0;     // scene_serial whose tree the 4-wide nodes behind d_nodes were collapsed from
     uint8_t* d_build = nullptr;   // device BVH build: primitive arrays in scene order + scratch
     size_t build_bytes = 0;
     cudaEvent_t ev_tc = nullptr;  // end of the cull pass (timing): trace_ms starts here
@@ -92,6 +93,7 @@ struct gort_ctx {
     std::string err;
     double upload_ms = 0, bvh_ms = 0;
     size_t bvh_bytes = 0;     // node + primitive arrays on the device
+    uint64_t scene_serial = 0;   // bumped by every scene upload (the 4-wide collapse of the tree is derived per upload, on first use)
     bool bvh_on_device = false;  // built by lbvh.cu: ctx->bvh holds the counts and the grid only
     uint8_t* h_build = nullptr;  // page-locked staging of the device builder's input (primitives, materials, lights), kept across uploads
     size_t h_build_bytes = 0;
@@ -314,7 +316,7 @@ int upload_scene_device_bvh(gort_ctx* ctx) {
         int2* d_meta_in = (int2*)(d.d_build + off_meta);
         float4* d_tri_in = (float4*)(d.d_build + off_tri);
         CUDA_TRY(ctx, cudaMemcpyAsync(d.d_build, ctx->h_build, in_bytes, cudaMemcpyHostToDevice, st));  // the three primitive arrays at once
-        if (int rc = ensure(ctx, d.d_nodes, d.cap_nodes, (n - 1) * 6 * sizeof(F4))) return rc;
+        if (int rc = ensure(ctx, d.d_nodes, d.cap_nodes, (n - 1) * 10 * sizeof(F4))) return rc;
         if (int rc = ensure(ctx, d.d_spheres, d.cap_spheres, nS * sizeof(F4))) return rc;
         if (int rc = ensure(ctx, d.d_meta, d.cap_meta, nS * sizeof(I2))) return rc;
         if (int rc = ensure(ctx, d.d_tris, d.cap_tris, nT * 4 * sizeof(F4))) return rc;
@@ -337,6 +339,7 @@ int upload_scene_device_bvh(gort_ctx* ctx) {
     if (max_depth > 62) return 1;
     b.max_depth = max_depth;
     ctx->bvh_on_device = true;
+    ctx->scene_serial++;
     ctx->bvh_bytes = (n - 1) * 6 * sizeof(F4) + nS * (sizeof(F4) + sizeof(I2)) + nT * 4 * sizeof(F4);
     ctx->has_scene = true;
     ctx->bvh_ms = now_ms() - t0;  // pack + H2D + device build
@@ -384,12 +387,13 @@ int upload_scene(gort_ctx* ctx) {
     }
     const FlatBvh& b = ctx->bvh;
     const void* src[6] = {b.nodes.data(), b.spheres.data(), b.sphere_meta.data(), b.tris.data(), mats.data(), lights.data()};
+    const size_t nodes_cap = (size_t)b.n_nodes * 10 * sizeof(F4);  // 4 fp32 + 2 quantised float4 per node from the host, room for the 4-wide collapse
     const size_t len[6] = {b.nodes.size() * sizeof(F4), b.spheres.size() * sizeof(F4), b.sphere_meta.size() * sizeof(I2),
                            b.tris.size() * sizeof(F4), mats.size() * sizeof(F4), lights.size() * sizeof(F4)};
     size_t off[6], total = 0;
     for (int k = 0; k < 6; k++) {
         off[k] = total;
-        total += (std::max<size_t>(len[k], 16) + 255) / 256 * 256;
+        total += (std::max<size_t>(k == 0 ? nodes_cap : len[k], 16) + 255) / 256 * 256;
     }
     constexpr size_t kBlobMax = 1u << 20;
     for (size_t i = 0; i < ctx->devs.size(); i++) {
@@ -438,6 +442,7 @@ int upload_scene(gort_ctx* ctx) {
             if (bytes) CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
             return GORT_OK;
         };
+        if (int rc = ensure(ctx, d.d_nodes, d.cap_nodes, nodes_cap)) return rc;
         if (int rc = up(d.d_nodes, d.cap_nodes, b.nodes.data(), b.nodes.size() * sizeof(F4))) return rc;
         if (int rc = up(d.d_spheres, d.cap_spheres, b.spheres.data(), b.spheres.size() * sizeof(F4))) return rc;
         if (int rc = up(d.d_meta, d.cap_meta, b.sphere_meta.data(), b.sphere_meta.size() * sizeof(I2))) return rc;
@@ -447,6 +452,7 @@ int upload_scene(gort_ctx* ctx) {
         CUDA_TRY(ctx, cudaStreamSynchronize(st));  // host vectors go out of scope: the copies must be done
     }
     ctx->has_scene = true;
+    ctx->scene_serial++;
     ctx->upload_ms = now_ms() - t0 - ctx->bvh_ms;
     return GORT_OK;
 }
@@ -579,6 +585,14 @@ int run_stream(gort_ctx* ctx, DeviceState& d, const TraceParams& tp, const gort_
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     const uint32_t n_deep = d.h_count[0], n_active = d.h_count[0] + d.h_count[1];
     if (n_active == 0) return GORT_OK;
+    if (stream_wants_wide_nodes() && d.wide_serial != ctx->scene_serial) {
+        // the traversal kernel walks the 4-wide collapse of the tree: derived on the device, once per uploaded scene
+        const size_t need = bvh_collapse_scratch_bytes(ctx->bvh.n_nodes);
+        if (int rc = ensure(ctx, d.d_build, d.build_bytes, need)) return rc;
+        CUDA_TRY(ctx, bvh_collapse_wide(d.d_nodes, ctx->bvh.n_nodes, d.d_nodes + 6 * (size_t)ctx->bvh.n_nodes, ctx->bvh.qorigin, ctx->bvh.qcell, d.d_build,
+                                        d.build_bytes, st));
+        d.wide_serial = ctx->scene_serial;
+    }
     const uint64_t per_sample = (uint64_t)n_active * 32u;
     const uint64_t prim_total = per_sample * (uint64_t)p->samples;
     // path slots: every launch works on (up to) this many paths; the queue is topped up with new primary rays each iteration

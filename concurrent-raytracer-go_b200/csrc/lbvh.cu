@@ -227,6 +227,109 @@ size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------
+// 4-wide collapse (lbvh.h)
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void wide_parent_kernel(const float4* __restrict__ nodes, int n2, int* __restrict__ parent) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n2) return;
+    const float4 l = nodes[4 * (size_t)i + 3];
+    const int c0 = __float_as_int(l.x), c1 = __float_as_int(l.y);
+    if (c0 >= 0) parent[c0] = i;
+    if (c1 >= 0 && c1 != c0) parent[c1] = i;
+    if (i == 0) parent[0] = -1;
+}
+
+__global__ void wide_mark_kernel(const int* __restrict__ parent, int n2, uint32_t* __restrict__ mark) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n2) return;
+    int d = 0;
+    for (int p = parent[i]; p >= 0; p = parent[p]) d++;
+    mark[i] = (d & 1) ? 0u : 1u;
+}
+
+struct QGrid {
+    float o[3], c[3];
+};
+
+__device__ __forceinline__ uint32_t quantise(float lo, float hi, float o, float c) {
+    const double ql = floor(((double)lo - (double)o) / (double)c) - 2.0, qh = ceil(((double)hi - (double)o) / (double)c) + 2.0;
+    return (uint32_t)fmin(65535.0, fmax(0.0, ql)) | ((uint32_t)fmin(65535.0, fmax(0.0, qh)) << 16);
+}
+
+__global__ void wide_emit_kernel(const float4* __restrict__ nodes, int n2, const uint32_t* __restrict__ mark, const uint32_t* __restrict__ widx,
+                                 const QGrid g, float4* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n2 || !mark[i]) return;
+    uint32_t w[16];
+#pragma unroll
+    for (int k = 0; k < 12; k++) w[k] = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; k++) w[12 + k] = (uint32_t)kWideNoChild;
+    int n = 0;
+    auto add = [&](float lox, float hix, float loy, float hiy, float loz, float hiz, int link) {
+        w[3 * n + 0] = quantise(lox, hix, g.o[0], g.c[0]);
+        w[3 * n + 1] = quantise(loy, hiy, g.o[1], g.c[1]);
+        w[3 * n + 2] = quantise(loz, hiz, g.o[2], g.c[2]);
+        w[12 + n] = link >= 0 ? widx[link] : (uint32_t)link;  // an inner grandchild sits at even depth: it is a wide node itself
+        n++;
+    };
+    const float4* np = nodes + 4 * (size_t)i;
+    const float4 n0 = np[0], n1 = np[1], n2v = np[2], n3 = np[3];
+    const int c[2] = {__float_as_int(n3.x), __float_as_int(n3.y)};
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        if (k == 1 && c[1] == c[0]) break;  // (the single-primitive scene references its leaf from both slots)
+        if (c[k] >= 0) {
+            const float4* cp = nodes + 4 * (size_t)c[k];
+            const float4 m0 = cp[0], m1 = cp[1], m2 = cp[2], m3 = cp[3];
+            const int g0 = __float_as_int(m3.x), g1 = __float_as_int(m3.y);
+            add(m0.x, m0.y, m0.z, m0.w, m2.x, m2.y, g0);
+            if (g1 != g0) add(m1.x, m1.y, m1.z, m1.w, m2.z, m2.w, g1);
+        } else if (k == 0) {
+            add(n0.x, n0.y, n0.z, n0.w, n2v.x, n2v.y, c[0]);
+        } else {
+            add(n1.x, n1.y, n1.z, n1.w, n2v.z, n2v.w, c[1]);
+        }
+    }
+    float4* o = out + 4 * (size_t)widx[i];
+#pragma unroll
+    for (int k = 0; k < 4; k++) o[k] = make_float4(__uint_as_float(w[4 * k]), __uint_as_float(w[4 * k + 1]), __uint_as_float(w[4 * k + 2]), __uint_as_float(w[4 * k + 3]));
+}
+
+}  // namespace
+
+size_t bvh_collapse_scratch_bytes(int n2) {
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, n2);
+    return align256(scan_bytes) + 3 * align256((size_t)n2 * 4) + 1024;
+}
+
+cudaError_t bvh_collapse_wide(const float4* nodes2, int n2, float4* wide_out, const float* qorigin3, const float* qcell3, void* scratch, size_t scratch_bytes,
+                              cudaStream_t st) {
+    if (n2 <= 0) return cudaSuccess;
+    if (scratch_bytes < bvh_collapse_scratch_bytes(n2)) return cudaErrorInvalidValue;
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, n2);
+    uint8_t* p = (uint8_t*)scratch;
+    auto take = [&](size_t bytes) { uint8_t* r = p; p += align256(bytes); return r; };
+    void* cub_tmp = take(scan_bytes);
+    int* parent = (int*)take((size_t)n2 * 4);
+    uint32_t* mark = (uint32_t*)take((size_t)n2 * 4);
+    uint32_t* widx = (uint32_t*)take((size_t)n2 * 4);
+    const int T = 256, G = (n2 + T - 1) / T;
+    wide_parent_kernel<<<G, T, 0, st>>>(nodes2, n2, parent);
+    wide_mark_kernel<<<G, T, 0, st>>>(parent, n2, mark);
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(cub_tmp, scan_bytes, mark, widx, n2, st);
+    if (e != cudaSuccess) return e;
+    QGrid g;
+    for (int a = 0; a < 3; a++) { g.o[a] = qorigin3[a]; g.c[a] = qcell3[a]; }
+    wide_emit_kernel<<<G, T, 0, st>>>(nodes2, n2, mark, widx, g, wide_out);
+    return cudaGetLastError();
+}
+
 size_t lbvh_scratch_bytes(uint32_t n) {
     size_t sort_bytes = 0, scan_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);

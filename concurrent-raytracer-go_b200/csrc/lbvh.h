@@ -28,4 +28,13 @@ size_t lbvh_scratch_bytes(uint32_t n_prims);
 // Enqueues the build on `st`; *max_depth_out (host, pinned or pageable) is valid after the stream has been synchronised.
 cudaError_t lbvh_build(const LbvhIn& in, const LbvhOut& out, void* scratch, size_t scratch_bytes, int* max_depth_out, cudaStream_t st);
 
+// 4-wide collapse of a flat BVH2 (bvh.h layout, either builder) for the wavefront pipeline's walk: every inner node at even depth
+// becomes a 64-byte node holding its (up to four) grandchildren: word 3k + a = child k's box on axis a as lo | hi << 16 on the
+// quantisation grid (rounded outward by two cells), word 12 + k = child k's link (>= 0 wide node, < 0 leaf as in bvh.h,
+// kWideNoChild = empty slot).  One visit = two 256-bit loads and four slab tests: half the dependent node fetches of the binary walk.
+constexpr int kWideNoChild = 0x7FFFFFFF;
+size_t bvh_collapse_scratch_bytes(int n_nodes2);
+cudaError_t bvh_collapse_wide(const float4* nodes2, int n_nodes2, float4* wide_out, const float* qorigin3, const float* qcell3, void* scratch,
+                              size_t scratch_bytes, cudaStream_t st);
+
 }  // namespace gort

@@ -8,6 +8,7 @@
 #include <cooperative_groups.h>
 
 #include "device.cuh"
+#include "lbvh.h"
 
 namespace gort {
 
@@ -20,6 +21,9 @@ constexpr uint32_t kDeadPrim = 0x7FFFFFFFu;  // qa.w of a path that ended (miss,
 #endif
 #ifndef GORT_POOL_QNODES
 #define GORT_POOL_QNODES 1
+#endif
+#ifndef GORT_POOL_WIDE
+#define GORT_POOL_WIDE 1  // the traversal kernel walks the 4-wide collapse of the tree (0: the quantised binary nodes)
 #endif
 #ifndef GORT_POOL_MINB
 #define GORT_POOL_MINB 10
@@ -97,7 +101,9 @@ __global__ void __launch_bounds__(128, GORT_POOL_MINB) pool_trace_kernel(const _
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t chunk = total >= n_warps * kPoolChunk ? kPoolChunk : max(32u, ((total / n_warps) + 31u) & ~31u);
 
-#if GORT_POOL_QNODES
+#if GORT_POOL_WIDE
+    const float4* __restrict__ nodes = S.nodes + 6 * (size_t)S.n_nodes;  // the 4-wide collapse (lbvh.h): 64 bytes per wide node
+#elif GORT_POOL_QNODES
     const float4* __restrict__ nodes = S.nodes + 4 * (size_t)S.n_nodes;  // the quantised copy: 32 bytes per node
 #else
     const float4* __restrict__ nodes = S.nodes;
@@ -112,7 +118,11 @@ __global__ void __launch_bounds__(128, GORT_POOL_MINB) pool_trace_kernel(const _
     RayQuery q;
     q.ox = q.oy = q.oz = q.dx = q.dy = q.dz = 0.f; q.a = 1.f; q.inv_a = 1.f; q.tmin = 0.001f; q.tbest = 0.f; q.best = 0; q.found = false;
     float idx = 0.f, idy = 0.f, idz = 0.f, oodx = 0.f, oody = 0.f, oodz = 0.f;
+#if GORT_POOL_WIDE
+    int stack[96];  // up to three pushes per wide level, (depth <= 62) / 2 levels
+#else
     int stack[64];
+#endif
     int sp = 0, node = 0;
 
     for (;;) {
@@ -242,6 +252,58 @@ __global__ void __launch_bounds__(128, GORT_POOL_MINB) pool_trace_kernel(const _
         }
         if (have) {
             bool fin = false;
+#if GORT_POOL_WIDE
+            if (node >= 0) {
+                // one 4-wide node: two 256-bit loads, four slab tests (two binary visits' worth of boxes in one dependent fetch)
+                stat_add<STATS>(st, kStatNodes, 2);
+                stat_add<STATS>(st, kStatWalkLane0 + SRC);
+                float4 A, B, C, D;
+                ldg8(nodes + 4 * (size_t)node, A, B);
+                ldg8(nodes + 4 * (size_t)node + 2, C, D);
+                const uint32_t magic = 0x4B000000u;  // 2^23
+#define GORT_QLO(w) __uint_as_float((__float_as_uint(w) & 0xffffu) | magic)
+#define GORT_QHI(w) __uint_as_float(__byte_perm(__float_as_uint(w), magic, 0x7632))
+#define GORT_SLAB(wx, wy, wz, tn, tf)                                                                                        \
+    {                                                                                                                        \
+        const float lx = fmaf(GORT_QLO(wx), idx, -oodx), hx = fmaf(GORT_QHI(wx), idx, -oodx);                               \
+        const float ly = fmaf(GORT_QLO(wy), idy, -oody), hy = fmaf(GORT_QHI(wy), idy, -oody);                               \
+        const float lz = fmaf(GORT_QLO(wz), idz, -oodz), hz = fmaf(GORT_QHI(wz), idz, -oodz);                               \
+        tn = fmaxf(fmaxf(fminf(lx, hx), fminf(ly, hy)), fmaxf(fminf(lz, hz), q.tmin));                                      \
+        tf = fminf(fminf(fmaxf(lx, hx), fmaxf(ly, hy)), fminf(fmaxf(lz, hz), q.tbest));                                     \
+    }
+                float tn0, tf0, tn1, tf1, tn2, tf2, tn3, tf3;
+                GORT_SLAB(A.x, A.y, A.z, tn0, tf0)
+                GORT_SLAB(A.w, B.x, B.y, tn1, tf1)
+                GORT_SLAB(B.z, B.w, C.x, tn2, tf2)
+                GORT_SLAB(C.y, C.z, C.w, tn3, tf3)
+#undef GORT_SLAB
+#undef GORT_QLO
+#undef GORT_QHI
+                const int l0 = __float_as_int(D.x), l1 = __float_as_int(D.y), l2 = __float_as_int(D.z), l3 = __float_as_int(D.w);
+                // (1 + 2^-22 widening of the far side keeps the fp32 slab test conservative)
+                const bool h0 = tn0 <= tf0 * 1.0000002f && l0 != kWideNoChild, h1 = tn1 <= tf1 * 1.0000002f && l1 != kWideNoChild;
+                const bool h2 = tn2 <= tf2 * 1.0000002f && l2 != kWideNoChild, h3 = tn3 <= tf3 * 1.0000002f && l3 != kWideNoChild;
+                // the nearest hit child is walked next (closest-hit rays; shadow rays take the first), the others wait on the stack
+                int next = kWideNoChild;
+                float tnext = 0.f;
+#define GORT_PUSH(l, tn) { stack[sp++] = l; }  // (keeping the waiting children nearest-on-top was measured: no gain)
+#define GORT_TAKE(h, l, tn)                                              \
+    if (h) {                                                             \
+        if (next == kWideNoChild) { next = l; tnext = tn; }              \
+        else if (!ANY && tn < tnext) { GORT_PUSH(next, tnext) next = l; tnext = tn; } \
+        else GORT_PUSH(l, tn)                                            \
+    }
+                GORT_TAKE(h0, l0, tn0)
+                GORT_TAKE(h1, l1, tn1)
+                GORT_TAKE(h2, l2, tn2)
+                GORT_TAKE(h3, l3, tn3)
+#undef GORT_TAKE
+#undef GORT_PUSH
+                if (next != kWideNoChild) node = next;
+                else if (sp == 0) fin = true;
+                else node = stack[--sp];
+            } else {
+#else
             if (node >= 0) {
                 stat_add<STATS>(st, kStatNodes);
                 stat_add<STATS>(st, kStatWalkLane0 + SRC);
@@ -298,6 +360,7 @@ __global__ void __launch_bounds__(128, GORT_POOL_MINB) pool_trace_kernel(const _
                     else node = stack[--sp];
                 }
             } else {
+#endif
                 const uint32_t v = ~(uint32_t)node;
                 const uint32_t start = v & 0x3FFFFFFu;
                 const int cnt = (int)((v >> 26) & 15u) + 1;
@@ -940,6 +1003,8 @@ cudaError_t stream_launch_plan(const StreamView& v, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
+bool stream_wants_wide_nodes() { return GORT_POOL_WIDE != 0; }
+
 size_t stream_bytes_per_slot() {
     return 2 * (3 * sizeof(float4) + sizeof(uint2)) + 4 * sizeof(float4) + sizeof(uint2) + kLC * (1 + 4 + 4 + 4 + 4 + 32);
 }

@@ -82,6 +82,7 @@ struct StreamView {
 };
 
 size_t stream_bytes_per_slot();
+bool stream_wants_wide_nodes();  // the traversal kernel of this build walks the 4-wide collapse (lbvh.h)
 // geom: 1 spheres only, 2 triangles only, 3 both (template specialisation, like the per-warp-queue kernel)
 // plan: how many primary rays join the next queue this iteration (fills it up to `cap`), 1 thread
 cudaError_t stream_launch_plan(const StreamView& v, cudaStream_t st);
