@@ -31,6 +31,10 @@ constexpr uint32_t kDeadPrim = 0x7FFFFFFFu;  // qa.w of a path that ended (miss,
 constexpr int kPoolRefill = GORT_POOL_REFILL;      // pool_trace refills as soon as this many lanes of a warp are idle
 constexpr uint32_t kPoolChunk = GORT_POOL_CHUNK;   // rays a warp takes from the global cursor at a time
 constexpr int kLC = kStreamLightChunk;
+#ifndef GORT_CONE_BUDGET
+#define GORT_CONE_BUDGET 16
+#endif
+constexpr int kConeBudget = GORT_CONE_BUDGET;  // node visits of one shadow-cone walk before the pair is sent to the walk list instead
 
 enum PoolSrc { SRC_PRIMARY = 0, SRC_EXT = 1, SRC_HARD = 2, SRC_SOFT = 3 };
 
@@ -695,6 +699,7 @@ __global__ void __launch_bounds__(128, GORT_POOL_MINB) pool_cone_kernel(const __
     uint32_t n = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
     int stack[64];
     int sp = 0, node = 0;
+    int budget = 0;  // node visits this pair's cone walk may still make (see kConeBudget)
 
     for (;;) {
         const unsigned act = __ballot_sync(FULL_MASK, have);
@@ -745,6 +750,7 @@ __global__ void __launch_bounds__(128, GORT_POOL_MINB) pool_cone_kernel(const __
                         V.walk_list[g.shfl(wb, 0) + g.thread_rank()] = e;
                     } else {
                         n = 0; sp = 0; node = 0;
+                        budget = kConeBudget;
                         have = true;
                     }
                 }
@@ -756,7 +762,12 @@ __global__ void __launch_bounds__(128, GORT_POOL_MINB) pool_cone_kernel(const __
 
         if (have) {
             bool fin = false, over = false;
-            if (node >= 0) {
+            if (node >= 0 && --budget < 0) {
+                // A cone walk is one lane's sequential work while the pair's 16 rays walk in parallel: a cone that has not been
+                // settled within the budget goes to the walk list like an overflowing one (same answers, bounded latency)
+                over = true;
+                fin = true;
+            } else if (node >= 0) {
                 stat_add<STATS>(st, kStatConeTests, 2);
                 const float4* np = nodes + 4 * (size_t)node;
                 float4 n0, n1, n2, n3;
