@@ -25,12 +25,20 @@ constexpr uint32_t kDeadPrim = 0x7FFFFFFFu;  // qa.w of a path that ended (miss,
 #ifndef GORT_POOL_WIDE
 #define GORT_POOL_WIDE 1  // the traversal kernel walks the 4-wide collapse of the tree (0: the quantised binary nodes)
 #endif
+#ifndef GORT_POOL_DEFER
+#define GORT_POOL_DEFER 1  // leaf tests deferred and run per warp in batches (4-wide walk only)
+#endif
+#ifndef GORT_LEAF_BATCH
+#define GORT_LEAF_BATCH 8
+#endif
 #ifndef GORT_POOL_MINB
 #define GORT_POOL_MINB 10
 #endif
 constexpr int kPoolRefill = GORT_POOL_REFILL;      // pool_trace refills as soon as this many lanes of a warp are idle
 constexpr uint32_t kPoolChunk = GORT_POOL_CHUNK;   // rays a warp takes from the global cursor at a time
 constexpr int kLC = kStreamLightChunk;
+[[maybe_unused]] constexpr int kLeafBatch = GORT_LEAF_BATCH;     // deferred leaf tests run once this many lanes of a warp have a parked leaf
+[[maybe_unused]] constexpr int kDoneNode = (int)0x80000000;      // "nothing left to walk" (not a valid leaf link: 2^26 - 1 primitives from start 2^26 - 1)
 #ifndef GORT_CONE_BUDGET
 #define GORT_CONE_BUDGET 16
 #endif
@@ -128,6 +136,9 @@ __global__ void __launch_bounds__(128, GORT_POOL_MINB) pool_trace_kernel(const _
     int stack[64];
 #endif
     int sp = 0, node = 0;
+#if GORT_POOL_WIDE && GORT_POOL_DEFER
+    int pend = 0;  // a leaf this lane has reached but not tested yet (leaf links are negative; 0 = none)
+#endif
 
     for (;;) {
         const unsigned act = __ballot_sync(FULL_MASK, have);
@@ -255,7 +266,7 @@ __global__ void __launch_bounds__(128, GORT_POOL_MINB) pool_trace_kernel(const _
             if (lane == 0 && vm) st.v[kStatWalkWarp0 + SRC] += 32u;
         }
         if (have) {
-            bool fin = false;
+            [[maybe_unused]] bool fin = false;
 #if GORT_POOL_WIDE
             if (node >= 0) {
                 // one 4-wide node: two 256-bit loads, four slab tests (two binary visits' worth of boxes in one dependent fetch)
@@ -304,9 +315,40 @@ __global__ void __launch_bounds__(128, GORT_POOL_MINB) pool_trace_kernel(const _
 #undef GORT_TAKE
 #undef GORT_PUSH
                 if (next != kWideNoChild) node = next;
+#if GORT_POOL_DEFER
+                else node = sp ? stack[--sp] : kDoneNode;
+            }
+            // Leaf tests are deferred: a lane that reaches a leaf parks it and walks on, and the warp tests its parked leaves
+            // together — when kLeafBatch lanes have one, or when no lane can go on without it.  Tested on the spot, a leaf costs
+            // the whole warp ~45 instructions for the two or three lanes that happen to be at one (a quarter of all issue slots
+            // at 8 % lane efficiency).  The closest hit / the occlusion answer is the same; tbest shrinks a few visits later.
+            if (node < 0 && node != kDoneNode && pend == 0) {
+                pend = node;
+                node = sp ? stack[--sp] : kDoneNode;
+            }
+        }
+        {
+            const unsigned pm = __ballot_sync(FULL_MASK, have && pend != 0), nm = __ballot_sync(FULL_MASK, have && node >= 0);
+            if (pm != 0u && (__popc(pm) >= kLeafBatch || nm == 0u) && have && pend != 0) {
+                const uint32_t v = ~(uint32_t)pend;
+                const uint32_t start = v & 0x3FFFFFFu;
+                const int cnt = (int)((v >> 26) & 15u) + 1;
+                if (GEOM == 1) test_spheres<STATS, GEOM>(S, spheres, q, start, cnt, st);
+                else if (GEOM == 2) test_tris<STATS, GEOM>(S, tris, q, start, cnt, st);
+                else if (((v >> 30) & 1u) == 0) test_spheres<STATS, GEOM>(S, spheres, q, start, cnt, st);
+                else test_tris<STATS, GEOM>(S, tris, q, start, cnt, st);
+                pend = 0;
+                if (ANY && q.found) { node = kDoneNode; sp = 0; }
+            }
+        }
+        if (have) {
+            bool fin = node == kDoneNode && pend == 0;
+            if (false) {
+#else
                 else if (sp == 0) fin = true;
                 else node = stack[--sp];
             } else {
+#endif
 #else
             if (node >= 0) {
                 stat_add<STATS>(st, kStatNodes);
