@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B200 render hot path (contract in the task brief).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c1_view|c1_ref|c2_view|c3|c4|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c1_view|c1_ref|c2_view|c2_faithful|c3|c4|c5|c5_spp32]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 A "step" is one full frame of the workload.  Default workload = the configuration BASELINE.json's metric is
@@ -42,6 +42,8 @@ WORKLOADS = {
     "c1_view": ("c1_view", 800, 600, 100, 50, 0, "sphere_reflections_light 800x600 100spp depth50 soft-shadows jitter, camera z mirrored to +8 (C1-view)"),
     "c1_ref": ("c1_ref", 800, 600, 100, 50, 0, "sphere_reflections_light 800x600 100spp depth50, committed camera (scene behind viewer: black frame)"),
     "c2_view": ("c2_view", 1200, 900, 100, 50, 1, "final_silver_prism_purple_cube 1200x900 100spp depth50, camera z mirrored to +25, prism extension on"),
+    # the same scene as the reference's own loader sees it: triangularPrism objects are unknown to it and skipped (scene/scene.go:69-83)
+    "c2_faithful": ("c2_view", 1200, 900, 100, 50, 0, "final_silver_prism_purple_cube 1200x900 100spp depth50, camera z mirrored to +25, prisms skipped as the reference's loader does"),
     "c3": ("c3", 800, 600, 1, 8, 0, "two_red_cubes 800x600 1spp depth8 no-jitter hard-shadows (deterministic correctness config)"),
     "c4": ("c4", 1920, 1080, 64, 16, 0, "synthetic 100k random spheres 1920x1080 64spp depth16 3 lights"),
     "c5": ("c5", 3840, 2160, 256, 32, 2, "synthetic 1M-primitive sphere/box scene 3840x2160 256spp depth32 fog on"),
@@ -282,7 +284,9 @@ def main():
             return launches_per_frame[0]  # libgort kernels (memsets and the L2 flush are not counted)
         if link is not None:
             r.RenderLinked(W, H, link)
-            return launches_per_frame[0] + 2  # + (release | -) + (wait | signal)
+            # rank 0 owns the frame: + the wait for the peers' arrivals (its release rides in the cull pass; a peer's wait and
+            # signal ride in its resolve kernel).  GORT_LINK_UNFUSED=1: one-thread kernels, + release + wait
+            return launches_per_frame[0] + (2 if os.environ.get("GORT_LINK_UNFUSED") else 1)
         r.RenderShardDevice(W, H, slab.data_ptr())
         dist.all_gather_into_tensor(gathered, slab)
         if rank == 0:
@@ -407,7 +411,8 @@ def main():
         # capture (tools/gpu_round.sh writes profiles/flops.json: fadd + fmul + 2 ffma per launch)
         measured = None
         try:
-            measured = json.load(open(os.path.join(ROOT, "profiles", "flops.json"))).get(args.workload)
+            # a whole frame's count: only comparable with the kernel time when one GPU renders the whole frame
+            measured = json.load(open(os.path.join(ROOT, "profiles", "flops.json"))).get(args.workload) if world == 1 else None
         except (OSError, ValueError):
             pass
         h2d = int(st.bvh_bytes + flat.desc.n_materials * 64 + flat.desc.n_lights * 32)
@@ -445,6 +450,7 @@ def main():
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
                          "traffic": traffic,
                          "kernel": "trace_kernel" if st.render_path != 2 else "wavefront pipeline (pool_trace / pool_cone / scatter / shade kernels of one frame)",
+                         "scope": "whole frame" if world == 1 else "rank 0's tiles (1/%d of the frame): counters and kernel time of that rank" % world,
                          "kernel_ms": tr, "cull_ms": st.cull_ms, "algorithmic_flops_per_launch": st.algorithmic_flops,
                          "flops_model": "SURVEY 8d per-operation costs x device counters of the same frame; ray generation only for the "
                                         "%d of %d primary samples that were generated (the rest sit in pixel blocks the cull pass proved empty); no tone-map term" % (st.primary_generated, st.primary_rays),

@@ -47,7 +47,11 @@ struct DeviceState {
     // per-frame buffers
     unsigned long long* d_accum = nullptr;
     size_t accum_tiles = 0;
-    unsigned int* d_counter = nullptr;  // [0] work counter, [1] deep active blocks, [2] other active blocks
+    // two banks of {work counter, deep active blocks, other active blocks, -}: a frame uses one and its cull pass clears the
+    // other for the next frame; behind them the resolve kernel's count of finished CTAs (frame link)
+    unsigned int* d_counter = nullptr;
+    int bank = 0;                       // the bank the LAST enqueued frame used
+    unsigned int* counters() const { return d_counter + 4 * bank; }
     uint32_t* d_active = nullptr;       // active pixel-block list
     size_t active_bytes = 0;
     unsigned long long* d_stats = nullptr;
@@ -99,6 +103,9 @@ struct gort_ctx {
     size_t h_build_bytes = 0;
     // last render (for gort_read_radiance)
     int last_w = 0, last_h = 0, last_samples = 0, last_rank = 0, last_count = 1;
+    // the call wants gort_stats: timing events are recorded between the kernels of the frame.  Without them the frame is
+    // cull -> trace -> resolve back to back, chained by programmatic dependent launches.
+    bool timing = false;
     std::vector<int> last_local_tiles;  // per device
 };
 
@@ -581,7 +588,7 @@ int choose_path(const gort_ctx* ctx, const gort_render_params* p) {
 int run_stream(gort_ctx* ctx, DeviceState& d, const TraceParams& tp, const gort_render_params* p, cudaStream_t st) {
     const bool stats = p->collect_stats != 0;
     const int geom = (tp.scene.n_spheres > 0 ? 1 : 0) | (tp.scene.n_tris > 0 ? 2 : 0);
-    CUDA_TRY(ctx, cudaMemcpyAsync(d.h_count, d.d_counter + 1, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d.h_count, d.counters() + 1, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     const uint32_t n_deep = d.h_count[0], n_active = d.h_count[0] + d.h_count[1];
     if (n_active == 0) return GORT_OK;
@@ -672,6 +679,8 @@ struct ResolveHooks {
     unsigned int wait_target = 0;
     unsigned int* timed_out = nullptr;        // set by a wait that gave up
     unsigned int* signal_flag = nullptr;      // after resolve: fence.sys + atomicAdd(*signal_flag, 1)
+    unsigned int* store_flag = nullptr;       // first thing in the frame: *store_flag = store_value (system scope)
+    unsigned int store_value = 0;
 };
 
 int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_rank, int eff_count, int slab_mode, uint8_t* out_override,
@@ -696,9 +705,21 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
         out = d.d_out;
     }
 
-    CUDA_TRY(ctx, cudaEventRecord(d.ev[0], st));
-    // the accumulators are cleared block by block in the cull pass (kept blocks only), not wholesale
-    CUDA_TRY(ctx, cudaMemsetAsync(d.d_counter, 0, 4 * sizeof(unsigned int), st));
+    const bool timing = ctx->timing;
+    // frame-link handshake folded into the cull and resolve kernels (GORT_LINK_UNFUSED=1: one-thread kernels around them)
+    static const bool link_unfused = getenv("GORT_LINK_UNFUSED") != nullptr;
+    static const bool no_pdl = getenv("GORT_NO_PDL") != nullptr;
+    if (timing) CUDA_TRY(ctx, cudaEventRecord(d.ev[0], st));
+    // the accumulators are cleared block by block in the cull pass (kept blocks only), not wholesale; the counters come
+    // cleared from the previous frame's cull pass (two banks)
+    if (hooks && hooks->store_flag && (link_unfused || n_local == 0)) CUDA_TRY(ctx, launch_link_store(hooks->store_flag, hooks->store_value, st));
+    CullExtras cx;
+    if (n_local > 0) {
+        cx.zero_bank = d.counters();  // the last frame's
+        d.bank ^= 1;
+        if (hooks && hooks->store_flag && !link_unfused) { cx.store_flag = hooks->store_flag; cx.store_value = hooks->store_value; }
+    }
+    unsigned int* const counters = d.counters();
     // active-block list (uint32 per block) followed by the kept/culled byte of every block
     if (int rc = ensure(ctx, d.d_active, d.active_bytes, (size_t)n_local * 32 * (sizeof(uint32_t) + 1))) return rc;
     if (p->collect_stats) CUDA_TRY(ctx, cudaMemsetAsync(d.d_stats, 0, kStatCount * sizeof(unsigned long long), st));
@@ -767,11 +788,11 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
         const int k = upw ? std::max(1, atoi(upw)) : 16;
         tp.target_units = (uint32_t)k * (uint32_t)d.sm_count * 32u;
     }
-    tp.active_list = d.d_active; tp.active_count = d.d_counter + 1;
+    tp.active_list = d.d_active; tp.active_count = counters + 1;
     tp.block_active = reinterpret_cast<uint8_t*>(d.d_active + (size_t)n_local * 32);
 
     tp.debug_times = d.d_debug;
-    tp.accum = d.d_accum; tp.work_counter = d.d_counter; tp.stats = p->collect_stats ? d.d_stats : nullptr;
+    tp.accum = d.d_accum; tp.work_counter = counters; tp.stats = p->collect_stats ? d.d_stats : nullptr;
     const uint32_t k0 = (uint32_t)p->seed, k1 = (uint32_t)(p->seed >> 32);
     for (int r = 0; r < 10; r++) {
         tp.rk[2 * r] = k0 + (uint32_t)r * 0x9E3779B9u;
@@ -794,9 +815,10 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     }
     tp.sky_enabled = ctx->scene.sky_enabled;
     for (int k = 0; k < 27; k++) tp.sky[k] = (float)ctx->scene.sky_params[k];
-    CUDA_TRY(ctx, launch_cull(tp, d.d_active, d.d_counter + 1, st));
-    CUDA_TRY(ctx, cudaEventRecord(d.ev_tc, st));
+    CUDA_TRY(ctx, launch_cull(tp, d.d_active, counters + 1, st, cx));
+    if (timing) CUDA_TRY(ctx, cudaEventRecord(d.ev_tc, st));
     ResolveParams rp;
+    memset(&rp, 0, sizeof(rp));
     rp.block_active = tp.block_active;
     rp.accum = d.d_accum; rp.n_local_tiles = n_local; rp.shard_rank = eff_rank; rp.shard_count = eff_count;
     rp.tiles_x = tiles_x; rp.width = p->width; rp.height = p->height; rp.samples = p->samples;
@@ -815,18 +837,26 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
         CUDA_TRY(ctx, cudaEventRecord(d.ev_aux, d.aux_stream));
         rp.part = 2;
     }
+    // programmatic dependent launches: only between kernels that follow each other directly on the stream
+    bool chained = false;
     if (path == kPathStream) {
         if (int rc = run_stream(ctx, d, tp, p, st)) return rc;
     } else {
-        CUDA_TRY(ctx, launch_trace(tp, p->collect_stats != 0, d.sm_count, st));
+        chained = !no_pdl && n_local > 0;
+        CUDA_TRY(ctx, launch_trace(tp, p->collect_stats != 0, d.sm_count, st, chained && !timing && !early));
         d.last_launches++;
     }
     d.last_launches += 2 + (early ? 1 : 0);  // cull + resolve (+ the early pass over the culled blocks)
-    CUDA_TRY(ctx, cudaEventRecord(d.ev[1], st));
+    if (timing) CUDA_TRY(ctx, cudaEventRecord(d.ev[1], st));
 
-    if (hooks && hooks->wait_flag) CUDA_TRY(ctx, launch_link_wait(hooks->wait_flag, hooks->wait_target, hooks->timed_out, st));
-    CUDA_TRY(ctx, launch_resolve(rp, st));
-    if (hooks && hooks->signal_flag) CUDA_TRY(ctx, launch_link_signal(hooks->signal_flag, st));
+    const bool fold = !link_unfused && n_local > 0;
+    if (hooks && hooks->wait_flag) {
+        if (fold) { rp.wait_flag = hooks->wait_flag; rp.wait_target = hooks->wait_target; rp.timed_out = hooks->timed_out; }
+        else CUDA_TRY(ctx, launch_link_wait(hooks->wait_flag, hooks->wait_target, hooks->timed_out, st));
+    }
+    if (hooks && hooks->signal_flag && fold) { rp.signal_flag = hooks->signal_flag; rp.done_count = d.d_counter + 8; }
+    CUDA_TRY(ctx, launch_resolve(rp, st, 0, chained && !timing && !(hooks && hooks->wait_flag && !fold)));
+    if (hooks && hooks->signal_flag && !fold) CUDA_TRY(ctx, launch_link_signal(hooks->signal_flag, st));
     if (early) CUDA_TRY(ctx, cudaStreamWaitEvent(st, d.ev_aux, 0));
     CUDA_TRY(ctx, cudaEventRecord(d.ev[2], st));
     return GORT_OK;
@@ -950,7 +980,8 @@ int gort_create(const int* device_ids, int n_devices, gort_ctx** out) {
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_count, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaMalloc(&d.d_ctl, (2 * kCtlWords + 4) * sizeof(unsigned int));
         if (e == cudaSuccess) e = cudaMallocHost(&d.h_count, 64);
-        if (e == cudaSuccess) e = cudaMalloc(&d.d_counter, 16);
+        if (e == cudaSuccess) e = cudaMalloc(&d.d_counter, 12 * sizeof(unsigned int));
+        if (e == cudaSuccess) e = cudaMemset(d.d_counter, 0, 12 * sizeof(unsigned int));
         if (e == cudaSuccess) e = cudaMalloc(&d.d_stats, kStatCount * sizeof(unsigned long long));
         if (e == cudaSuccess && getenv("GORT_DEBUG_TIMES")) e = cudaMalloc(&d.d_debug, (1 + 16 * 148 * 64) * sizeof(unsigned long long));
         if (e != cudaSuccess) return bail(GORT_ERR_CUDA, std::string("device init: ") + cudaGetErrorString(e));
@@ -1097,6 +1128,7 @@ int gort_render_shard_device(gort_ctx* ctx, const gort_render_params* p, void* d
     const int sc = p->shard_count <= 0 ? 1 : p->shard_count;
     if (!d_slab || slab_bytes != gort_shard_slab_bytes(p->width, p->height, sc)) return fail(ctx, GORT_ERR_INVALID, "slab pointer/size mismatch");
     ctx->last_w = p->width; ctx->last_h = p->height; ctx->last_samples = p->samples; ctx->last_rank = p->shard_rank; ctx->last_count = sc;
+    ctx->timing = stats_out != nullptr;
     if (int rc = enqueue_device(ctx, 0, p, p->shard_rank, sc, 1, (uint8_t*)d_slab, slab_bytes)) return rc;
     if (stats_out) return collect_stats(ctx, p, stats_out, t0, 1);
     return GORT_OK;
@@ -1171,6 +1203,7 @@ int gort_render_device(gort_ctx* ctx, const gort_render_params* p, void* d_rgba,
     const double t0 = now_ms();
     if (int rc = validate(ctx, p)) return rc;
     if (!d_rgba || rgba_bytes != (size_t)p->width * p->height * 4) return fail(ctx, GORT_ERR_INVALID, "d_rgba pointer/size mismatch");
+    ctx->timing = stats_out != nullptr;
     return render_frame_device(ctx, p, (uint8_t*)d_rgba, t0, stats_out, false);
 }
 
@@ -1179,6 +1212,7 @@ int gort_render(gort_ctx* ctx, const gort_render_params* p, uint8_t* rgba_out, s
     if (int rc = validate(ctx, p)) return rc;
     const size_t frame_bytes = (size_t)p->width * p->height * 4;
     if (!rgba_out || rgba_bytes != frame_bytes) return fail(ctx, GORT_ERR_INVALID, "rgba_out pointer/size mismatch (want width*height*4)");
+    ctx->timing = stats_out != nullptr;
     DeviceState& lead = ctx->devs[0];
     CUDA_TRY(ctx, cudaSetDevice(lead.dev));
     const int sc = p->shard_count <= 0 ? 1 : p->shard_count;
@@ -1401,9 +1435,10 @@ int gort_render_linked(gort_ctx* ctx, const gort_render_params* p, gort_link* l,
     CUDA_TRY(ctx, cudaSetDevice(ctx->devs[0].dev));
     cudaStream_t st = stream_of(ctx, 0);
     ResolveHooks hk;
+    ctx->timing = stats_out != nullptr;
     if (l->owner) {
-        // everything this stream did with frame k-1 is done when this runs: the peers may overwrite it
-        CUDA_TRY(ctx, launch_link_store(l->ctrl + 1, k - 1, st));
+        // everything this stream did with frame k-1 is done when the frame's first kernel runs: the peers may overwrite it
+        hk.store_flag = l->ctrl + 1; hk.store_value = k - 1;
         if (l->has_local_peers) {
             // Ranks that share this GPU cannot run concurrently with a kernel that waits for them: the peers must have rendered
             // (and finished) frame k already.  Checked on the host instead of enqueuing a wait that could only time out.
@@ -1415,7 +1450,7 @@ int gort_render_linked(gort_ctx* ctx, const gort_render_params* p, gort_link* l,
                 return fail(ctx, GORT_ERR_INVALID, "frame link on one GPU: render every peer rank's frame before the owner's");
             }
         }
-        if (int rc = enqueue_device(ctx, 0, p, 0, l->n_ranks, 0, l->base, 0, nullptr)) return rc;
+        if (int rc = enqueue_device(ctx, 0, p, 0, l->n_ranks, 0, l->base, 0, &hk)) return rc;
         if (l->n_ranks > 1 && !l->has_local_peers) CUDA_TRY(ctx, launch_link_wait(l->ctrl + 0, k * (unsigned int)(l->n_ranks - 1), l->ctrl + 2, st));
     } else {
         // (a local alias renders before its owner and on the same GPU: there is no one to wait for)

@@ -95,6 +95,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel
         for (int i = 0; i < kStatCount; i++) st.v[i] = 0;
     }
 
+    // Programmatic dependent launch (launch_trace(dependent)): this grid's CTAs may have become resident while the cull pass
+    // was still running, and resolve_kernel's CTAs may take the slots this grid's CTAs leave.  Nothing of the cull pass is
+    // read before the wait; a launch without the attribute passes straight through both instructions.
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // Work units are sized on the device from the number of pixel blocks the cull pass kept:
     // enough units for dynamic balance (target_units), at most 16 samples each.
     const uint32_t n_deep = P.active_count[0], n_norm = P.active_count[1];
@@ -783,8 +788,19 @@ __device__ __forceinline__ bool beam_box_outside(const Beam& B, float lox, float
 }
 
 __global__ void __launch_bounds__(128) cull_kernel(const __grid_constant__ TraceParams P, uint32_t* __restrict__ active_list,
-                                                    unsigned int* __restrict__ active_count) {
+                                                    unsigned int* __restrict__ active_count, const CullExtras X) {
+    // the trace kernel's CTAs may become resident while this pass runs (they wait for its end with griddepcontrol.wait)
+    asm volatile("griddepcontrol.launch_dependents;");
     const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id == 0) {
+        // the other counter bank is the next frame's: cleared here instead of by a memset node in front of every frame
+        if (X.zero_bank) *reinterpret_cast<uint4*>(X.zero_bank) = make_uint4(0u, 0u, 0u, 0u);
+        // owner of a frame link: everything this stream did with the previous frame is done, the peers may overwrite it
+        if (X.store_flag) {
+            asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(X.store_flag), "r"(X.store_value) : "memory");
+            __threadfence_system();
+        }
+    }
     if (id >= (uint32_t)P.n_local_tiles * 32u) return;
     const SceneView& S = P.scene;
     const uint32_t ltile = id >> 5, block = id & 31u;
@@ -913,16 +929,28 @@ __global__ void __launch_bounds__(128) cull_kernel(const __grid_constant__ Trace
     else if (active) active_list[(uint32_t)P.n_local_tiles * 32u - 1u - atomicAdd(active_count + 1, 1u)] = id;
 }
 
-cudaError_t launch_cull(const TraceParams& p, uint32_t* active_list, unsigned int* active_count, cudaStream_t stream) {
+cudaError_t launch_cull(const TraceParams& p, uint32_t* active_list, unsigned int* active_count, cudaStream_t stream, const CullExtras& x) {
     const unsigned int n = (unsigned int)p.n_local_tiles * 32u;
     if (n == 0) return cudaSuccess;
-    cull_kernel<<<(n + 127) / 128, 128, 0, stream>>>(p, active_list, active_count);
+    cull_kernel<<<(n + 127) / 128, 128, 0, stream>>>(p, active_list, active_count, x);
     return cudaGetLastError();
+}
+
+// launch with or without the programmatic-dependent-launch attribute (kernels.h)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_maybe_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, bool dependent, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = dependent ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 
 template <bool STATS, bool SMALL, int GEOM, bool SKY = false>
-static cudaError_t launch_trace_variant(const TraceParams& p, int sm_count, cudaStream_t stream) {
+static cudaError_t launch_trace_variant(const TraceParams& p, int sm_count, cudaStream_t stream, bool dependent) {
     // persistent grid: as many CTAs as fit on the chip at once (occupancy is register-bound)
     static int ctas_per_sm = 0;
     if (ctas_per_sm == 0) {
@@ -967,28 +995,28 @@ static cudaError_t launch_trace_variant(const TraceParams& p, int sm_count, cuda
         }
         return cudaGetLastError();
     }
-    trace_kernel<STATS, SMALL, GEOM, SKY><<<sm_count * ctas_per_sm, kWarpsPerCta * 32, 0, stream>>>(p);
-    return cudaGetLastError();
+    return launch_maybe_dependent(trace_kernel<STATS, SMALL, GEOM, SKY>, dim3(sm_count * ctas_per_sm), dim3(kWarpsPerCta * 32), stream, dependent, p);
 }
 
 template <bool STATS, bool SKY>
-static cudaError_t launch_trace_bvh(const TraceParams& p, int geom, int sm_count, cudaStream_t stream) {
+static cudaError_t launch_trace_bvh(const TraceParams& p, int geom, int sm_count, cudaStream_t stream, bool dependent) {
     switch (geom) {
-        case 1: return launch_trace_variant<STATS, false, 1, SKY>(p, sm_count, stream);
-        case 2: return launch_trace_variant<STATS, false, 2, SKY>(p, sm_count, stream);
-        default: return launch_trace_variant<STATS, false, 3, SKY>(p, sm_count, stream);
+        case 1: return launch_trace_variant<STATS, false, 1, SKY>(p, sm_count, stream, dependent);
+        case 2: return launch_trace_variant<STATS, false, 2, SKY>(p, sm_count, stream, dependent);
+        default: return launch_trace_variant<STATS, false, 3, SKY>(p, sm_count, stream, dependent);
     }
 }
 
-cudaError_t launch_trace(const TraceParams& p, bool stats, int sm_count, cudaStream_t stream) {
+cudaError_t launch_trace(const TraceParams& p, bool stats, int sm_count, cudaStream_t stream, bool dependent) {
     if (p.n_local_tiles == 0) return cudaSuccess;
     // kernel variant: tiny sphere scenes scan the parameter bank (an empty scene without sky is the degenerate case of that);
     // BVH scenes run the kernel specialised for what they hold
     const int geom = (p.scene.n_spheres > 0 ? 1 : 0) | (p.scene.n_tris > 0 ? 2 : 0);
     if (p.small_n > 0 || (geom == 0 && !p.sky_enabled))
-        return stats ? launch_trace_variant<true, true, 1>(p, sm_count, stream) : launch_trace_variant<false, true, 1>(p, sm_count, stream);
-    if (p.sky_enabled) return stats ? launch_trace_bvh<true, true>(p, geom, sm_count, stream) : launch_trace_bvh<false, true>(p, geom, sm_count, stream);
-    return stats ? launch_trace_bvh<true, false>(p, geom, sm_count, stream) : launch_trace_bvh<false, false>(p, geom, sm_count, stream);
+        return stats ? launch_trace_variant<true, true, 1>(p, sm_count, stream, dependent) : launch_trace_variant<false, true, 1>(p, sm_count, stream, dependent);
+    if (p.sky_enabled)
+        return stats ? launch_trace_bvh<true, true>(p, geom, sm_count, stream, dependent) : launch_trace_bvh<false, true>(p, geom, sm_count, stream, dependent);
+    return stats ? launch_trace_bvh<true, false>(p, geom, sm_count, stream, dependent) : launch_trace_bvh<false, false>(p, geom, sm_count, stream, dependent);
 }
 
 int trace_kernel_regs(bool stats) {
@@ -1009,7 +1037,37 @@ __device__ __forceinline__ uint8_t tone_map_u8(long long fixed, double inv_scale
     return (uint8_t)(c * 255.0);                   // truncating conversion
 }
 
+// spin (with back-off) until *flag >= target; a flag written from ANOTHER GPU.  20 s without it: a rank died — never hang the
+// GPU, flag it and let the host report.
+__device__ __forceinline__ void link_wait(const unsigned int* flag, unsigned int target, unsigned int* timed_out) {
+    unsigned int ns = 100;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        unsigned int v;
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int)(v - target) >= 0) break;
+        __nanosleep(ns);
+        if (ns < 2000) ns *= 2;
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > 20000000000ull) {
+            atomicExch_system(timed_out, 1u);
+            break;
+        }
+    }
+    __threadfence_system();
+}
+
 __global__ void __launch_bounds__(256) resolve_kernel(const ResolveParams R) {
+    // launched as a programmatic dependent of the trace kernel, the CTAs sit here while the last paths of the frame finish
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (R.wait_flag) {
+        // frame link, peer side: the owner must have consumed the previous frame before these tiles overwrite it.  The flag
+        // was stored when the owner STARTED this frame, a whole trace pass ago: the loop is left at its first read.
+        if (threadIdx.x == 0) link_wait(R.wait_flag, R.wait_target, R.timed_out);
+        __syncthreads();
+    }
     const int n = R.n_local_tiles * kTilePixels;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int lt = i / kTilePixels, p = i % kTilePixels;
@@ -1033,14 +1091,26 @@ __global__ void __launch_bounds__(256) resolve_kernel(const ResolveParams R) {
         if (R.slab_mode) out[i] = px;
         else if (inside) out[(size_t)y * R.width + x] = px;
     }
+    if (R.signal_flag) {
+        // frame link, peer side: "my tiles of this frame are in the owner's memory", told by the last CTA to finish
+        __threadfence_system();  // every thread: its stores are visible system-wide before its CTA counts itself done
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int done = atomicAdd(R.done_count, 1u);
+            if (done == gridDim.x - 1) {
+                *R.done_count = 0;  // for the next launch on this stream
+                __threadfence_system();
+                atomicAdd_system(R.signal_flag, 1u);
+            }
+        }
+    }
 }
 
-cudaError_t launch_resolve(const ResolveParams& p, cudaStream_t stream, int max_blocks) {
+cudaError_t launch_resolve(const ResolveParams& p, cudaStream_t stream, int max_blocks, bool dependent) {
     const int n = p.n_local_tiles * kTilePixels;
     if (n == 0) return cudaSuccess;
-    if (max_blocks > 0) resolve_kernel<<<std::min(max_blocks, (n + 127) / 128), 128, 0, stream>>>(p);
-    else resolve_kernel<<<(n + 255) / 256, 256, 0, stream>>>(p);
-    return cudaGetLastError();
+    if (max_blocks > 0) return launch_maybe_dependent(resolve_kernel, dim3(std::min(max_blocks, (n + 127) / 128)), dim3(128), stream, dependent, p);
+    return launch_maybe_dependent(resolve_kernel, dim3((n + 255) / 256), dim3(256), stream, dependent, p);
 }
 
 // rank-major concatenation of tile-major shard slabs -> row-major frame
@@ -1085,25 +1155,7 @@ __global__ void link_store_kernel(unsigned int* flag, unsigned int value) {
     asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
     __threadfence_system();
 }
-__global__ void link_wait_kernel(const unsigned int* flag, unsigned int target, unsigned int* timed_out) {
-    unsigned int ns = 100;
-    unsigned long long t0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    for (;;) {
-        unsigned int v;
-        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-        if ((int)(v - target) >= 0) break;
-        __nanosleep(ns);
-        if (ns < 2000) ns *= 2;
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        if (t - t0 > 20000000000ull) {  // 20 s: a rank died; never hang the GPU — flag it and let the host report
-            atomicExch_system(timed_out, 1u);
-            break;
-        }
-    }
-    __threadfence_system();
-}
+__global__ void link_wait_kernel(const unsigned int* flag, unsigned int target, unsigned int* timed_out) { link_wait(flag, target, timed_out); }
 cudaError_t launch_link_signal(unsigned int* flag, cudaStream_t stream) {
     link_signal_kernel<<<1, 1, 0, stream>>>(flag);
     return cudaGetLastError();

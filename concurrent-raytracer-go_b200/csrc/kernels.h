@@ -124,13 +124,31 @@ struct ResolveParams {
     uint8_t* out;      // row-major frame (slab_mode 0) or tile-major slab (slab_mode 1)
     int slab_mode;
     int part;          // 0 every pixel; 1 only the culled blocks (black; needs nothing but the cull pass); 2 only the kept blocks
+    // frame link, folded into this kernel (all null / 0 otherwise): every CTA waits until *wait_flag >= wait_target before its
+    // first store (the owner has consumed the previous frame); the last CTA to finish adds 1 to *signal_flag (system scope)
+    const unsigned int* wait_flag;
+    unsigned int wait_target;
+    unsigned int* timed_out;
+    unsigned int* signal_flag;
+    unsigned int* done_count;  // device-local, zero between launches
+};
+
+// frame-link work folded into the cull pass and per-frame counter upkeep: its first thread zeroes the counter bank of the
+// NEXT frame (four words) and, on the owner of a frame link, publishes "frame store_value consumed" (system scope)
+struct CullExtras {
+    unsigned int* zero_bank = nullptr;
+    unsigned int* store_flag = nullptr;
+    unsigned int store_value = 0;
 };
 
 // All launchers enqueue on `stream` and return the launch error (no synchronisation).
-cudaError_t launch_cull(const TraceParams& p, uint32_t* active_list, unsigned int* active_count, cudaStream_t stream);
-cudaError_t launch_trace(const TraceParams& p, bool stats, int sm_count, cudaStream_t stream);
+// `dependent` (trace, resolve): programmatic dependent launch — the kernel directly before it on the stream lets this one's CTAs
+// become resident while it drains (cull -> trace -> resolve of a frame), and this one waits for it with griddepcontrol.wait.
+// Only valid when the previous operation on the stream IS that kernel (no event record, copy or memset in between).
+cudaError_t launch_cull(const TraceParams& p, uint32_t* active_list, unsigned int* active_count, cudaStream_t stream, const CullExtras& x = CullExtras());
+cudaError_t launch_trace(const TraceParams& p, bool stats, int sm_count, cudaStream_t stream, bool dependent = false);
 // max_blocks > 0: a small grid-stride launch (co-resident with the persistent trace grid)
-cudaError_t launch_resolve(const ResolveParams& p, cudaStream_t stream, int max_blocks = 0);
+cudaError_t launch_resolve(const ResolveParams& p, cudaStream_t stream, int max_blocks = 0, bool dependent = false);
 // Frame link (one process per GPU, the owner's frame mapped into every peer): system-scope flag handshake in
 // the owner's memory.  signal: fence + atomicAdd(flag, 1); store: flag = value; wait: spin until flag >= target
 // (gives up after 20 s and sets *timed_out instead of hanging the GPU when a rank has died).
