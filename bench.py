@@ -284,8 +284,8 @@ def main():
             return launches_per_frame[0]  # libgort kernels (memsets and the L2 flush are not counted)
         if link is not None:
             r.RenderLinked(W, H, link)
-            # rank 0 owns the frame: + the wait for the peers' arrivals (its release rides in the cull pass; a peer's wait and
-            # signal ride in its resolve kernel).  GORT_LINK_UNFUSED=1: one-thread kernels, + release + wait
+            # rank 0 owns the frame: + the wait for the peers' arrivals (its release rides in the cull pass; a peer launches
+            # a wait and a signal around its resolve pass).  GORT_LINK_UNFUSED=1: + a release kernel
             return launches_per_frame[0] + (2 if os.environ.get("GORT_LINK_UNFUSED") else 1)
         r.RenderShardDevice(W, H, slab.data_ptr())
         dist.all_gather_into_tensor(gathered, slab)

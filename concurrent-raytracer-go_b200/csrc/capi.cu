@@ -71,6 +71,10 @@ struct DeviceState {
     uint8_t* d_build = nullptr;   // device BVH build: primitive arrays in scene order + scratch
     size_t build_bytes = 0;
     cudaEvent_t ev_tc = nullptr;  // end of the cull pass (timing): trace_ms starts here
+    // per-warp-queue path: the kernels stamp %globaltimer instead (TraceParams::stamps), so that a frame whose caller wants
+    // gort_stats is the same chain of dependent launches as one whose caller does not
+    unsigned long long* h_stamps = nullptr;  // page-locked host memory the kernels store into (no copy to read them back)
+    bool stamped = false;         // the last enqueued frame was timed by stamps, not by ev_tc / ev[1]
     // global-queue wavefront pipeline (stream.cu): path / record / pair queues of one batch, counter ring, readback
     uint8_t* d_stream = nullptr;
     size_t stream_bytes = 0;
@@ -83,6 +87,25 @@ struct DeviceState {
 double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
+
+// GORT_HOST_TIMES=1: where the HOST time of the upload and render calls goes (accumulated per phase, printed by gort_destroy)
+enum { kLapDesc, kLapBvh, kLapPack, kLapH2D, kLapPre, kLapEnqueue, kLapSync, kLapStats, kLapEnqSetup, kLapEnqLaunch, kLapCount };
+const char* const kLapNames[kLapCount] = {"upload: desc -> host scene", "upload: BVH build", "upload: pack + stage", "upload: H2D enqueue",
+                                          "render: validate + pointer attributes", "render: enqueue", "render: wait for the GPU", "render: stats",
+                                          "  enqueue: parameters", "  enqueue: launches"};
+double g_lap_us[kLapCount];
+unsigned long long g_lap_n[kLapCount];
+const bool g_laps = getenv("GORT_HOST_TIMES") != nullptr;
+struct Lap {
+    double t;
+    Lap() : t(g_laps ? now_ms() : 0.0) {}
+    void mark(int k) {
+        if (!g_laps) return;
+        const double n = now_ms();
+        if (g_lap_n[k]++ >= 8) g_lap_us[k] += (n - t) * 1e3;  // the first calls pay for module load and allocations
+        t = n;
+    }
+};
 
 }  // namespace
 
@@ -375,7 +398,9 @@ int upload_scene(gort_ctx* ctx) {
             if (rc != 1) return rc;
         }
     }
+    Lap lap;
     build_bvh(ctx->scene, ctx->bvh);
+    lap.mark(kLapBvh);
     ctx->bvh_ms = ctx->bvh.build_ms;
     ctx->bvh_bytes = ctx->bvh.nodes.size() * sizeof(F4) + ctx->bvh.spheres.size() * sizeof(F4) + ctx->bvh.sphere_meta.size() * sizeof(I2) +
                      ctx->bvh.tris.size() * sizeof(F4);
@@ -427,8 +452,10 @@ int upload_scene(gort_ctx* ctx) {
             CUDA_TRY(ctx, cudaEventSynchronize(d.ev_upload));
             for (int k = 0; k < 6; k++)
                 if (len[k]) memcpy(d.h_stage + off[k], src[k], len[k]);
+            lap.mark(kLapPack);
             CUDA_TRY(ctx, cudaMemcpyAsync(d.d_blob, d.h_stage, total, cudaMemcpyHostToDevice, st));
             CUDA_TRY(ctx, cudaEventRecord(d.ev_upload, st));
+            lap.mark(kLapH2D);
             d.d_nodes = reinterpret_cast<float4*>(d.d_blob + off[0]);
             d.d_spheres = reinterpret_cast<float4*>(d.d_blob + off[1]);
             d.d_meta = reinterpret_cast<int2*>(d.d_blob + off[2]);
@@ -685,6 +712,7 @@ struct ResolveHooks {
 
 int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_rank, int eff_count, int slab_mode, uint8_t* out_override,
                    size_t slab_bytes, const ResolveHooks* hooks = nullptr) {
+    Lap lap;
     DeviceState& d = ctx->devs[di];
     CUDA_TRY(ctx, cudaSetDevice(d.dev));
     cudaStream_t st = stream_of(ctx, di);
@@ -705,11 +733,16 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
         out = d.d_out;
     }
 
-    const bool timing = ctx->timing;
-    // frame-link handshake folded into the cull and resolve kernels (GORT_LINK_UNFUSED=1: one-thread kernels around them)
+    const int path = choose_path(ctx, p);
+    // gort_stats wanted: the wavefront pipeline (host round trips between its launches anyway) is timed by events between
+    // the kernels, the per-warp-queue frame by stamps the kernels write
+    const bool events = ctx->timing && (path == kPathStream || n_local == 0);
+    const bool timing = events;
+    d.stamped = ctx->timing && !events;
+    // the owner's release of a frame link rides in the cull pass (GORT_LINK_UNFUSED=1: a one-thread kernel in front of it)
     static const bool link_unfused = getenv("GORT_LINK_UNFUSED") != nullptr;
     static const bool no_pdl = getenv("GORT_NO_PDL") != nullptr;
-    if (timing) CUDA_TRY(ctx, cudaEventRecord(d.ev[0], st));
+    if (ctx->timing) CUDA_TRY(ctx, cudaEventRecord(d.ev[0], st));
     // the accumulators are cleared block by block in the cull pass (kept blocks only), not wholesale; the counters come
     // cleared from the previous frame's cull pass (two banks)
     if (hooks && hooks->store_flag && (link_unfused || n_local == 0)) CUDA_TRY(ctx, launch_link_store(hooks->store_flag, hooks->store_value, st));
@@ -739,7 +772,6 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     tp.inv_w = 1.0f / (float)p->width; tp.inv_h = 1.0f / (float)p->height;
     // tiny sphere-only scenes: the spheres ride in the kernel parameters, in scan order
     tp.small_n = 0;
-    const int path = choose_path(ctx, p);
     d.last_path = path;
     d.last_launches = 0;
     if (path == kPathSmall) {
@@ -792,6 +824,12 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     tp.block_active = reinterpret_cast<uint8_t*>(d.d_active + (size_t)n_local * 32);
 
     tp.debug_times = d.d_debug;
+    tp.stamps = nullptr;
+    if (d.stamped) {
+        void* dp = nullptr;
+        CUDA_TRY(ctx, cudaHostGetDevicePointer(&dp, d.h_stamps, 0));
+        tp.stamps = static_cast<unsigned long long*>(dp);
+    }
     tp.accum = d.d_accum; tp.work_counter = counters; tp.stats = p->collect_stats ? d.d_stats : nullptr;
     const uint32_t k0 = (uint32_t)p->seed, k1 = (uint32_t)(p->seed >> 32);
     for (int r = 0; r < 10; r++) {
@@ -815,6 +853,7 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     }
     tp.sky_enabled = ctx->scene.sky_enabled;
     for (int k = 0; k < 27; k++) tp.sky[k] = (float)ctx->scene.sky_params[k];
+    lap.mark(kLapEnqSetup);
     CUDA_TRY(ctx, launch_cull(tp, d.d_active, counters + 1, st, cx));
     if (timing) CUDA_TRY(ctx, cudaEventRecord(d.ev_tc, st));
     ResolveParams rp;
@@ -823,7 +862,14 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     rp.accum = d.d_accum; rp.n_local_tiles = n_local; rp.shard_rank = eff_rank; rp.shard_count = eff_count;
     rp.tiles_x = tiles_x; rp.width = p->width; rp.height = p->height; rp.samples = p->samples;
     rp.out = out; rp.slab_mode = slab_mode; rp.part = 0;
-    const bool early = hooks && hooks->early_black && n_local > 0;
+    // the culled blocks of a host frame: written by the trace kernel itself (per-warp-queue path: the frame stays one chain of
+    // dependent launches), or by a small resolve pass on the aux stream beside the wavefront pipeline's kernels
+    static const bool early_aux = getenv("GORT_EARLY_AUX") != nullptr;
+    // (for a frame in device memory the trace kernel writing the culled blocks changed nothing: 0.1746 vs 0.1756 ms)
+    const bool early_any = hooks && hooks->early_black && n_local > 0 && !slab_mode;
+    const bool early_in_trace = early_any && path != kPathStream && !early_aux;
+    const bool early = early_any && !early_in_trace;
+    if (early_in_trace) { tp.early_out = out; rp.part = 2; }
     if (early) {
         if (!d.aux_stream) {
             CUDA_TRY(ctx, cudaStreamCreateWithFlags(&d.aux_stream, cudaStreamNonBlocking));
@@ -849,16 +895,20 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     d.last_launches += 2 + (early ? 1 : 0);  // cull + resolve (+ the early pass over the culled blocks)
     if (timing) CUDA_TRY(ctx, cudaEventRecord(d.ev[1], st));
 
-    const bool fold = !link_unfused && n_local > 0;
-    if (hooks && hooks->wait_flag) {
-        if (fold) { rp.wait_flag = hooks->wait_flag; rp.wait_target = hooks->wait_target; rp.timed_out = hooks->timed_out; }
-        else CUDA_TRY(ctx, launch_link_wait(hooks->wait_flag, hooks->wait_target, hooks->timed_out, st));
-    }
-    if (hooks && hooks->signal_flag && fold) { rp.signal_flag = hooks->signal_flag; rp.done_count = d.d_counter + 8; }
-    CUDA_TRY(ctx, launch_resolve(rp, st, 0, chained && !timing && !(hooks && hooks->wait_flag && !fold)));
-    if (hooks && hooks->signal_flag && !fold) CUDA_TRY(ctx, launch_link_signal(hooks->signal_flag, st));
+    // frame link, peer side: wait for the owner's release before the first store into its frame, tell it when the last one is
+    // out.  One-thread kernels around the resolve pass: folded into it (every CTA polling the owner's word, a system-scope fence
+    // per CTA before the last one signals) the two-GPU frame was 3 us slower (profiles/README.md).
+    // They join the frame's chain of dependent launches: each is resident, parked in griddepcontrol.wait, before its turn comes.
+    static const bool link_chain = getenv("GORT_LINK_NO_CHAIN") == nullptr;
+    const bool chain = chained && !timing;
+    const bool waits = hooks && hooks->wait_flag;
+    if (waits) CUDA_TRY(ctx, launch_link_wait(hooks->wait_flag, hooks->wait_target, hooks->timed_out, st, chain && link_chain));
+    rp.stamps = tp.stamps;
+    CUDA_TRY(ctx, launch_resolve(rp, st, 0, chain && (!waits || link_chain)));
+    if (hooks && hooks->signal_flag) CUDA_TRY(ctx, launch_link_signal(hooks->signal_flag, st, chain && link_chain));
     if (early) CUDA_TRY(ctx, cudaStreamWaitEvent(st, d.ev_aux, 0));
     CUDA_TRY(ctx, cudaEventRecord(d.ev[2], st));
+    lap.mark(kLapEnqLaunch);
     return GORT_OK;
 }
 
@@ -878,9 +928,20 @@ int collect_stats(gort_ctx* ctx, const gort_render_params* p, gort_stats* s, dou
         CUDA_TRY(ctx, cudaSetDevice(d.dev));
         CUDA_TRY(ctx, cudaEventSynchronize(d.ev[2]));
         float c = 0, a = 0, b = 0;
-        CUDA_TRY(ctx, cudaEventElapsedTime(&c, d.ev[0], d.ev_tc));  // memsets + cull pass
-        CUDA_TRY(ctx, cudaEventElapsedTime(&a, d.ev_tc, d.ev[1]));  // the trace kernel(s) alone
-        CUDA_TRY(ctx, cudaEventElapsedTime(&b, d.ev[1], d.ev[2]));
+        if (d.stamped) {
+            // cull pass = first cull thread -> first trace thread past its wait for the cull pass; trace = that -> first resolve
+            // thread past its wait for the trace kernel; the rest of ev[0]..ev[2] is the resolve pass (and the launch of the first)
+            const volatile unsigned long long* t = d.h_stamps;  // the frame is complete (ev[2]): the stores have landed
+            float total = 0;
+            CUDA_TRY(ctx, cudaEventElapsedTime(&total, d.ev[0], d.ev[2]));
+            c = (float)((double)(t[1] - t[0]) * 1e-6);
+            a = (float)((double)(t[2] - t[1]) * 1e-6);
+            b = std::max(0.f, total - c - a);
+        } else {
+            CUDA_TRY(ctx, cudaEventElapsedTime(&c, d.ev[0], d.ev_tc));  // memsets + cull pass
+            CUDA_TRY(ctx, cudaEventElapsedTime(&a, d.ev_tc, d.ev[1]));  // the trace kernel(s) alone
+            CUDA_TRY(ctx, cudaEventElapsedTime(&b, d.ev[1], d.ev[2]));
+        }
         s->device_ms[i] = c + a + b;
         if (i == 0) {
             s->cull_ms = c; s->trace_ms = a; s->resolve_ms = b;
@@ -980,6 +1041,7 @@ int gort_create(const int* device_ids, int n_devices, gort_ctx** out) {
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_count, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaMalloc(&d.d_ctl, (2 * kCtlWords + 4) * sizeof(unsigned int));
         if (e == cudaSuccess) e = cudaMallocHost(&d.h_count, 64);
+        if (e == cudaSuccess) e = cudaHostAlloc(&d.h_stamps, 4 * sizeof(unsigned long long), cudaHostAllocPortable | cudaHostAllocMapped);
         if (e == cudaSuccess) e = cudaMalloc(&d.d_counter, 12 * sizeof(unsigned int));
         if (e == cudaSuccess) e = cudaMemset(d.d_counter, 0, 12 * sizeof(unsigned int));
         if (e == cudaSuccess) e = cudaMalloc(&d.d_stats, kStatCount * sizeof(unsigned long long));
@@ -1012,6 +1074,11 @@ int gort_create(const int* device_ids, int n_devices, gort_ctx** out) {
 
 void gort_destroy(gort_ctx* ctx) {
     if (!ctx) return;
+    if (g_laps) {
+        for (int k = 0; k < kLapCount; k++)
+            if (g_lap_n[k] > 8) fprintf(stderr, "[gort host] %-40s %9.2f us x %llu\n", kLapNames[k], g_lap_us[k] / (double)(g_lap_n[k] - 8), g_lap_n[k] - 8);
+        memset(g_lap_us, 0, sizeof(g_lap_us)); memset(g_lap_n, 0, sizeof(g_lap_n));
+    }
     for (DeviceState& d : ctx->devs) {
         if (d.dev < 0) continue;
         cudaSetDevice(d.dev);
@@ -1019,6 +1086,7 @@ void gort_destroy(gort_ctx* ctx) {
         free_scene(d);
         cudaFree(d.d_debug); cudaFree(d.d_accum); cudaFree(d.d_active); cudaFree(d.d_counter); cudaFree(d.d_stats); cudaFree(d.d_out); cudaFree(d.d_gather);
         if (d.h_pinned) cudaFreeHost(d.h_pinned);
+        if (d.h_stamps) cudaFreeHost(d.h_stamps);
         for (auto& e : d.ev)
             if (e) cudaEventDestroy(e);
         if (d.aux_stream) { cudaStreamSynchronize(d.aux_stream); cudaStreamDestroy(d.aux_stream); }
@@ -1051,10 +1119,12 @@ int gort_set_stream(gort_ctx* ctx, void* cuda_stream) {
 int gort_scene_upload(gort_ctx* ctx, const gort_scene_desc* desc) {
     if (!ctx) return GORT_ERR_INVALID;
     if (!desc) return fail(ctx, GORT_ERR_INVALID, "desc is NULL");
+    Lap lap;
     HostScene hs;
     std::string err = scene_from_desc(*desc, hs);
     if (!err.empty()) return fail(ctx, GORT_ERR_INVALID, err);
     ctx->scene = std::move(hs);
+    lap.mark(kLapDesc);
     return upload_scene(ctx);
 }
 
@@ -1213,6 +1283,7 @@ int gort_render(gort_ctx* ctx, const gort_render_params* p, uint8_t* rgba_out, s
     const size_t frame_bytes = (size_t)p->width * p->height * 4;
     if (!rgba_out || rgba_bytes != frame_bytes) return fail(ctx, GORT_ERR_INVALID, "rgba_out pointer/size mismatch (want width*height*4)");
     ctx->timing = stats_out != nullptr;
+    Lap lap;
     DeviceState& lead = ctx->devs[0];
     CUDA_TRY(ctx, cudaSetDevice(lead.dev));
     const int sc = p->shard_count <= 0 ? 1 : p->shard_count;
@@ -1240,13 +1311,17 @@ int gort_render(gort_ctx* ctx, const gort_render_params* p, uint8_t* rgba_out, s
         if (cudaPointerGetAttributes(&pa0, target) == cudaSuccess && pa0.type == cudaMemoryTypeHost && pa0.devicePointer) {
             ResolveHooks hk;
             hk.early_black = !getenv("GORT_NO_EARLY_BLACK");
+            lap.mark(kLapPre);
             if (int rc = render_frame_device(ctx, p, (uint8_t*)pa0.devicePointer, t0, nullptr, false, &hk)) return rc;
+            lap.mark(kLapEnqueue);
             CUDA_TRY(ctx, cudaStreamSynchronize(st0));
+            lap.mark(kLapSync);
             if (staged) memcpy(rgba_out, lead.h_pinned, frame_bytes);
             if (stats_out) {
                 if (int rc = collect_stats(ctx, p, stats_out, t0, 1)) return rc;
                 stats_out->total_ms = now_ms() - t0;
             }
+            lap.mark(kLapStats);
             return GORT_OK;
         }
         cudaGetLastError();

@@ -81,6 +81,22 @@ __device__ __forceinline__ float qf(const uint32_t (*Q)[kQueueCap], int f, int s
 // is sized so that 7-8 CTAs fit.
 // SKY (BVH variants only): the sky extension's two call sites are compiled in only for scenes that enable it — the kernel is
 // bound by its code footprint (the same sites, present but never executed, cost C2-view 8 %)
+// TraceParams::early_out: black (alpha 255) for every pixel of the blocks the cull pass dropped — what resolve_kernel writes for
+// them (part 1), but from inside the trace kernel: the frame of a sparse scene is mostly such blocks, and a frame in page-locked
+// host memory takes them over PCIe while the kept blocks are still being traced.  One warp per participating CTA; a 32-pixel tile
+// row is one 128-byte store.
+static __device__ __noinline__ void fill_culled_rows(const TraceParams& P, int first, int stride) {
+    const int lane = threadIdx.x & 31;
+    uchar4* out = reinterpret_cast<uchar4*>(P.early_out);
+    for (int seg = first; seg < P.n_local_tiles * kTile; seg += stride) {
+        const int lt = seg / kTile, ly = seg % kTile;
+        if (P.block_active[lt * 32 + (ly >> 2) * 4 + (lane >> 3)]) continue;
+        const int gt = P.shard_rank + lt * P.shard_count;
+        const int x = (gt % P.tiles_x) * kTile + lane, y = (gt / P.tiles_x) * kTile + ly;
+        if (x < P.width && y < P.height) out[(size_t)y * P.width + x] = make_uchar4(0, 0, 0, 255);
+    }
+}
+
 template <bool STATS, bool SMALL, int GEOM, bool SKY = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel(const __grid_constant__ TraceParams P) {
     __shared__ WarpShared<SMALL> wsh[kWarpsPerCta];
@@ -100,6 +116,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMALL ? 8 : 7) trace_kernel
     // read before the wait; a launch without the attribute passes straight through both instructions.
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (P.stamps && blockIdx.x == 0 && threadIdx.x == 0)
+        asm volatile("{ .reg .u64 t; mov.u64 t, %%globaltimer; st.global.u64 [%0], t; }" ::"l"(P.stamps + 1) : "memory");
+    if (P.early_out && (blockIdx.x & 7u) == 0 && threadIdx.x < 32) fill_culled_rows(P, (int)(blockIdx.x >> 3), (int)((gridDim.x + 7u) >> 3));
     // Work units are sized on the device from the number of pixel blocks the cull pass kept:
     // enough units for dynamic balance (target_units), at most 16 samples each.
     const uint32_t n_deep = P.active_count[0], n_norm = P.active_count[1];
@@ -793,6 +812,7 @@ __global__ void __launch_bounds__(128) cull_kernel(const __grid_constant__ Trace
     asm volatile("griddepcontrol.launch_dependents;");
     const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id == 0) {
+        if (P.stamps) asm volatile("{ .reg .u64 t; mov.u64 t, %%globaltimer; st.global.u64 [%0], t; }" ::"l"(P.stamps) : "memory");
         // the other counter bank is the next frame's: cleared here instead of by a memset node in front of every frame
         if (X.zero_bank) *reinterpret_cast<uint4*>(X.zero_bank) = make_uint4(0u, 0u, 0u, 0u);
         // owner of a frame link: everything this stream did with the previous frame is done, the peers may overwrite it
@@ -1037,37 +1057,12 @@ __device__ __forceinline__ uint8_t tone_map_u8(long long fixed, double inv_scale
     return (uint8_t)(c * 255.0);                   // truncating conversion
 }
 
-// spin (with back-off) until *flag >= target; a flag written from ANOTHER GPU.  20 s without it: a rank died — never hang the
-// GPU, flag it and let the host report.
-__device__ __forceinline__ void link_wait(const unsigned int* flag, unsigned int target, unsigned int* timed_out) {
-    unsigned int ns = 100;
-    unsigned long long t0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    for (;;) {
-        unsigned int v;
-        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-        if ((int)(v - target) >= 0) break;
-        __nanosleep(ns);
-        if (ns < 2000) ns *= 2;
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        if (t - t0 > 20000000000ull) {
-            atomicExch_system(timed_out, 1u);
-            break;
-        }
-    }
-    __threadfence_system();
-}
-
 __global__ void __launch_bounds__(256) resolve_kernel(const ResolveParams R) {
     // launched as a programmatic dependent of the trace kernel, the CTAs sit here while the last paths of the frame finish
+    asm volatile("griddepcontrol.launch_dependents;");  // (a frame link's signal kernel)
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (R.wait_flag) {
-        // frame link, peer side: the owner must have consumed the previous frame before these tiles overwrite it.  The flag
-        // was stored when the owner STARTED this frame, a whole trace pass ago: the loop is left at its first read.
-        if (threadIdx.x == 0) link_wait(R.wait_flag, R.wait_target, R.timed_out);
-        __syncthreads();
-    }
+    if (R.stamps && blockIdx.x == 0 && threadIdx.x == 0)
+        asm volatile("{ .reg .u64 t; mov.u64 t, %%globaltimer; st.global.u64 [%0], t; }" ::"l"(R.stamps + 2) : "memory");
     const int n = R.n_local_tiles * kTilePixels;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int lt = i / kTilePixels, p = i % kTilePixels;
@@ -1090,19 +1085,6 @@ __global__ void __launch_bounds__(256) resolve_kernel(const ResolveParams R) {
         uchar4* out = reinterpret_cast<uchar4*>(R.out);
         if (R.slab_mode) out[i] = px;
         else if (inside) out[(size_t)y * R.width + x] = px;
-    }
-    if (R.signal_flag) {
-        // frame link, peer side: "my tiles of this frame are in the owner's memory", told by the last CTA to finish
-        __threadfence_system();  // every thread: its stores are visible system-wide before its CTA counts itself done
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned int done = atomicAdd(R.done_count, 1u);
-            if (done == gridDim.x - 1) {
-                *R.done_count = 0;  // for the next launch on this stream
-                __threadfence_system();
-                atomicAdd_system(R.signal_flag, 1u);
-            }
-        }
     }
 }
 
@@ -1147,7 +1129,9 @@ cudaError_t launch_unswizzle(const uint8_t* slabs, int shard_count, int width, i
 // Each kernel is one thread; a waiting kernel spins on a flag written from ANOTHER GPU (never on a kernel of
 // its own GPU), with back-off.
 // ---------------------------------------------------------------------------------------------
+// (the signal and wait kernels can be launched as programmatic dependents of the kernel before them, like the frame's own)
 __global__ void link_signal_kernel(unsigned int* flag) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // the resolve pass is complete, its stores performed
     __threadfence_system();
     atomicAdd_system(flag, 1u);
 }
@@ -1155,18 +1139,42 @@ __global__ void link_store_kernel(unsigned int* flag, unsigned int value) {
     asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
     __threadfence_system();
 }
-__global__ void link_wait_kernel(const unsigned int* flag, unsigned int target, unsigned int* timed_out) { link_wait(flag, target, timed_out); }
-cudaError_t launch_link_signal(unsigned int* flag, cudaStream_t stream) {
-    link_signal_kernel<<<1, 1, 0, stream>>>(flag);
-    return cudaGetLastError();
+// spin (with back-off) until *flag >= target; a flag written from ANOTHER GPU.  20 s without it: a rank died — never hang the
+// GPU, flag it and let the host report.
+__device__ __forceinline__ void link_wait(const unsigned int* flag, unsigned int target, unsigned int* timed_out) {
+    unsigned int ns = 100;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        unsigned int v;
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int)(v - target) >= 0) break;
+        __nanosleep(ns);
+        if (ns < 2000) ns *= 2;
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > 20000000000ull) {
+            atomicExch_system(timed_out, 1u);
+            break;
+        }
+    }
+    __threadfence_system();
+}
+
+__global__ void link_wait_kernel(const unsigned int* flag, unsigned int target, unsigned int* timed_out) {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    link_wait(flag, target, timed_out);
+}
+cudaError_t launch_link_signal(unsigned int* flag, cudaStream_t stream, bool dependent) {
+    return launch_maybe_dependent(link_signal_kernel, dim3(1), dim3(1), stream, dependent, flag);
 }
 cudaError_t launch_link_store(unsigned int* flag, unsigned int value, cudaStream_t stream) {
     link_store_kernel<<<1, 1, 0, stream>>>(flag, value);
     return cudaGetLastError();
 }
-cudaError_t launch_link_wait(const unsigned int* flag, unsigned int target, unsigned int* timed_out, cudaStream_t stream) {
-    link_wait_kernel<<<1, 1, 0, stream>>>(flag, target, timed_out);
-    return cudaGetLastError();
+cudaError_t launch_link_wait(const unsigned int* flag, unsigned int target, unsigned int* timed_out, cudaStream_t stream, bool dependent) {
+    return launch_maybe_dependent(link_wait_kernel, dim3(1), dim3(1), stream, dependent, flag, target, timed_out);
 }
 
 // ---------------------------------------------------------------------------------------------

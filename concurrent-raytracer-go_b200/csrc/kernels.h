@@ -87,6 +87,10 @@ struct TraceParams {
     unsigned long long* accum;   // [n_local_tiles][1024][3] int64 fixed point
     unsigned int* work_counter;  // zeroed before launch
     unsigned long long* stats;   // [kStatCount] or nullptr
+    uint8_t* early_out;               // nullptr, or the row-major RGBA8 frame: one warp in eight CTAs of the trace kernel first writes black
+                                      // into the pixel blocks the cull pass dropped (a page-locked host frame fills over PCIe under the trace)
+    unsigned long long* stamps;       // nullptr, or %globaltimer stamps of the frame: [0] cull pass starts, [1] trace kernel starts (cull done),
+                                      // [2] resolve starts (trace done) — the kernel split of gort_stats without event records between the kernels
     unsigned long long* debug_times;  // nullptr, or [1 + 2*n_warps]: kernel start, then per warp (end of units, end of drain) in ns
     uint32_t rk[20];             // Philox4x32-10 round keys: rk[2r] = key0 + r*W0, rk[2r+1] = key1 + r*W1
     int fog_enabled;
@@ -124,13 +128,7 @@ struct ResolveParams {
     uint8_t* out;      // row-major frame (slab_mode 0) or tile-major slab (slab_mode 1)
     int slab_mode;
     int part;          // 0 every pixel; 1 only the culled blocks (black; needs nothing but the cull pass); 2 only the kept blocks
-    // frame link, folded into this kernel (all null / 0 otherwise): every CTA waits until *wait_flag >= wait_target before its
-    // first store (the owner has consumed the previous frame); the last CTA to finish adds 1 to *signal_flag (system scope)
-    const unsigned int* wait_flag;
-    unsigned int wait_target;
-    unsigned int* timed_out;
-    unsigned int* signal_flag;
-    unsigned int* done_count;  // device-local, zero between launches
+    unsigned long long* stamps;  // see TraceParams
 };
 
 // frame-link work folded into the cull pass and per-frame counter upkeep: its first thread zeroes the counter bank of the
@@ -152,9 +150,9 @@ cudaError_t launch_resolve(const ResolveParams& p, cudaStream_t stream, int max_
 // Frame link (one process per GPU, the owner's frame mapped into every peer): system-scope flag handshake in
 // the owner's memory.  signal: fence + atomicAdd(flag, 1); store: flag = value; wait: spin until flag >= target
 // (gives up after 20 s and sets *timed_out instead of hanging the GPU when a rank has died).
-cudaError_t launch_link_signal(unsigned int* flag, cudaStream_t stream);
+cudaError_t launch_link_signal(unsigned int* flag, cudaStream_t stream, bool dependent = false);
 cudaError_t launch_link_store(unsigned int* flag, unsigned int value, cudaStream_t stream);
-cudaError_t launch_link_wait(const unsigned int* flag, unsigned int target, unsigned int* timed_out, cudaStream_t stream);
+cudaError_t launch_link_wait(const unsigned int* flag, unsigned int target, unsigned int* timed_out, cudaStream_t stream, bool dependent = false);
 cudaError_t launch_unswizzle(const uint8_t* slabs, int shard_count, int width, int height, uint8_t* rgba, cudaStream_t stream);
 cudaError_t launch_trace_rays(const SceneView& scene, int n, const float* origins, const float* dirs, float tmin, float tmax,
                               int any_hit, float* out_t, int* out_order, cudaStream_t stream);
