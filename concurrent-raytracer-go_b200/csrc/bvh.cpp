@@ -343,14 +343,16 @@ void pack_triangle(const HostTriangle& t, F4 o[4]) {
 void build_bvh(const HostScene& scene, FlatBvh& out) {
     auto t0 = std::chrono::steady_clock::now();
     {
-        const char* e = getenv("GORT_BVH_NODE_COST");
+        static const char* const e = getenv("GORT_BVH_NODE_COST");
         kNodeCost = e ? atof(e) : 1.0;
     }
     out = FlatBvh();
     Builder B;
     const int nS = (int)scene.spheres.size(), nT = (int)scene.tris.size();
     std::vector<BPrim> prims_storage((size_t)nS + nT);
-    unsigned hw = std::thread::hardware_concurrency();
+    // (asked once: the call reads /sys on every use, microseconds that a 7-sphere scene re-uploaded per frame would pay each time)
+    static const unsigned hw_cores = std::thread::hardware_concurrency();
+    unsigned hw = hw_cores;
     if (const char* e = getenv("GORT_BVH_THREADS")) hw = (unsigned)std::max(1, atoi(e));
     auto prim_boxes = [&](int lo, int hi) {
         for (int j = lo; j < hi; j++) {
@@ -402,7 +404,7 @@ void build_bvh(const HostScene& scene, FlatBvh& out) {
     const bool parallel = n >= 20000 && hw > 1;
     if (parallel) B.defer_below = std::max(1024, n / 64);
     g_node_threads = parallel ? hw : 1u;  // the top of the tree scans its large ranges in parallel chunks
-    const bool times = getenv("GORT_BVH_TIMES") != nullptr;
+    static const bool times = getenv("GORT_BVH_TIMES") != nullptr;
     auto lap = [&](const char* what) {
         if (times) fprintf(stderr, "[gort bvh] %-22s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     };

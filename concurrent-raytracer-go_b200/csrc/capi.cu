@@ -84,6 +84,10 @@ struct DeviceState {
     int last_path = 0, last_launches = 0;
 };
 
+// tuning knobs that are set for a whole process are read once (a getenv is ~0.3 us; a C1 frame is 170 us and asked a dozen).
+// The switches the tests flip between frames (GORT_PATH, GORT_BVH, GORT_NO_CONE_CULL, GORT_NO_ZERO_COPY, ...) stay live.
+#define GORT_ENV_ONCE(name) ([]() -> const char* { static const char* const v = getenv(name); return v; }())
+
 double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -257,7 +261,7 @@ int upload_scene_device_bvh(gort_ctx* ctx) {
     const double t0 = now_ms();
     const HostScene& hs = ctx->scene;
     const size_t nS = hs.spheres.size(), nT = hs.tris.size(), n = nS + nT;
-    const bool times = getenv("GORT_BVH_TIMES") != nullptr;
+    const bool times = GORT_ENV_ONCE("GORT_BVH_TIMES") != nullptr;
     auto lap = [&](const char* what) {
         if (times) fprintf(stderr, "[gort lbvh] %-28s %8.2f ms\n", what, now_ms() - t0);
     };
@@ -389,7 +393,7 @@ int upload_scene(gort_ctx* ctx) {
         // which builder: binned SAH on the host (better trees, ~0.45 s per million primitives) or LBVH on the device (a few ms)
         const size_t n_prims = ctx->scene.spheres.size() + ctx->scene.tris.size();
         const char* which = getenv("GORT_BVH");
-        const char* mn = getenv("GORT_BVH_DEVICE_MIN");
+        const char* mn = GORT_ENV_ONCE("GORT_BVH_DEVICE_MIN");
         const size_t device_min = mn ? (size_t)atoll(mn) : (size_t)200000;
         const bool on_device = n_prims >= 2 && (which ? !strcmp(which, "device") : n_prims >= device_min);
         ctx->bvh_on_device = false;
@@ -601,8 +605,8 @@ int choose_path(const gort_ctx* ctx, const gort_render_params* p) {
     if (small_ok) return kPathSmall;
     // The pipeline pays ~10 launches per bounce whatever the frame holds: it wins once a frame has enough rays to fill them.
     // Measured crossover (profiles/README.md): C4 (depth 16) ~8 M primary samples per frame, C5 (depth 32) ~12 M.
-    const char* mp = getenv("GORT_STREAM_MIN_PRIMS");
-    const char* ms = getenv("GORT_STREAM_MIN_SAMPLES");
+    const char* mp = GORT_ENV_ONCE("GORT_STREAM_MIN_PRIMS");
+    const char* ms = GORT_ENV_ONCE("GORT_STREAM_MIN_SAMPLES");
     const size_t min_prims = mp ? (size_t)atoll(mp) : 4096;
     const int64_t min_samples = ms ? (int64_t)atoll(ms) : (int64_t)12 << 20;
     const int64_t frame_samples = (int64_t)p->width * p->height * p->samples;
@@ -630,7 +634,7 @@ int run_stream(gort_ctx* ctx, DeviceState& d, const TraceParams& tp, const gort_
     const uint64_t per_sample = (uint64_t)n_active * 32u;
     const uint64_t prim_total = per_sample * (uint64_t)p->samples;
     // path slots: every launch works on (up to) this many paths; the queue is topped up with new primary rays each iteration
-    const char* be = getenv("GORT_STREAM_BATCH");
+    const char* be = GORT_ENV_ONCE("GORT_STREAM_BATCH");
     const uint64_t want = be ? std::max<uint64_t>(1024, (uint64_t)atoll(be)) : (uint64_t)16 << 20;
     const uint64_t cap = std::min<uint64_t>(std::min(want, prim_total), (uint64_t)1 << 26);
 
@@ -816,7 +820,7 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     {
         // work units per resident warp.  Measured 4 / 8 / 16 / 32 / 64: C2-view 0.777 / 0.709 / 0.667 / 0.667 / 0.665 ms
         // (finer units shorten the end of the frame), C4 and C5 flat; C1-view is at one sample per unit either way.
-        const char* upw = getenv("GORT_UNITS_PER_WARP");
+        const char* upw = GORT_ENV_ONCE("GORT_UNITS_PER_WARP");
         const int k = upw ? std::max(1, atoi(upw)) : 16;
         tp.target_units = (uint32_t)k * (uint32_t)d.sm_count * 32u;
     }
@@ -836,10 +840,10 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
         tp.rk[2 * r] = k0 + (uint32_t)r * 0x9E3779B9u;
         tp.rk[2 * r + 1] = k1 + (uint32_t)r * 0xBB67AE85u;
     }
-    tp.dead_bound = getenv("GORT_NO_DEAD_PATH") ? 0.f : dead_path_bound(ctx->scene, tp.cam, p->max_depth);
+    tp.dead_bound = GORT_ENV_ONCE("GORT_NO_DEAD_PATH") ? 0.f : dead_path_bound(ctx->scene, tp.cam, p->max_depth);
     tp.no_cone_cull = getenv("GORT_NO_CONE_CULL") ? 1 : 0;
     {
-        const char* ud = getenv("GORT_URGENT_DEPTH");
+        const char* ud = GORT_ENV_ONCE("GORT_URGENT_DEPTH");
         tp.urgent_depth = ud ? atoi(ud) : 3;
     }
     tp.fog_enabled = ctx->scene.fog_enabled;
@@ -849,7 +853,7 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
         const double ex = 65520.0 * ctx->bvh.qcell[0], ey = 65520.0 * ctx->bvh.qcell[1], ez = 65520.0 * ctx->bvh.qcell[2];
         const double vol = ex * ey * ez;
         const double n_prims = (double)(ctx->scene.spheres.size() + ctx->scene.tris.size());
-        tp.cone_skip = (vol > 0 && !getenv("GORT_NO_CONE_SKIP")) ? (float)(n_prims / vol * 0.010578) : 0.f;
+        tp.cone_skip = (vol > 0 && !GORT_ENV_ONCE("GORT_NO_CONE_SKIP")) ? (float)(n_prims / vol * 0.010578) : 0.f;
     }
     tp.sky_enabled = ctx->scene.sky_enabled;
     for (int k = 0; k < 27; k++) tp.sky[k] = (float)ctx->scene.sky_params[k];
@@ -1310,7 +1314,7 @@ int gort_render(gort_ctx* ctx, const gort_render_params* p, uint8_t* rgba_out, s
         }
         if (cudaPointerGetAttributes(&pa0, target) == cudaSuccess && pa0.type == cudaMemoryTypeHost && pa0.devicePointer) {
             ResolveHooks hk;
-            hk.early_black = !getenv("GORT_NO_EARLY_BLACK");
+            hk.early_black = !GORT_ENV_ONCE("GORT_NO_EARLY_BLACK");
             lap.mark(kLapPre);
             if (int rc = render_frame_device(ctx, p, (uint8_t*)pa0.devicePointer, t0, nullptr, false, &hk)) return rc;
             lap.mark(kLapEnqueue);

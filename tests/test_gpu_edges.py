@@ -102,6 +102,9 @@ def test_render_device_matches_host_path(gort, renderer):
     out = torch.zeros(H * W * 4, dtype=torch.uint8, device="cuda")
     st = renderer.RenderDevice(W, H, out.data_ptr(), want_stats=True)
     assert st.kernel_ms > 0 and st.primary_rays == W * H * 2
+    # the kernel split comes from stamps the kernels write (no event between them): consistent with the frame's event time
+    assert st.trace_ms > 0 and st.cull_ms > 0 and st.resolve_ms >= 0
+    assert abs(st.cull_ms + st.trace_ms + st.resolve_ms - st.kernel_ms) < 1e-3 and st.trace_ms < st.kernel_ms
     assert (out.cpu().numpy().reshape(H, W, 4) == host).all()
 
 
