@@ -746,7 +746,7 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     // the owner's release of a frame link rides in the cull pass (GORT_LINK_UNFUSED=1: a one-thread kernel in front of it)
     static const bool link_unfused = getenv("GORT_LINK_UNFUSED") != nullptr;
     static const bool no_pdl = getenv("GORT_NO_PDL") != nullptr;
-    if (ctx->timing) CUDA_TRY(ctx, cudaEventRecord(d.ev[0], st));
+    if (events || (ctx->timing && ctx->devs.size() > 1)) CUDA_TRY(ctx, cudaEventRecord(d.ev[0], st));
     // the accumulators are cleared block by block in the cull pass (kept blocks only), not wholesale; the counters come
     // cleared from the previous frame's cull pass (two banks)
     if (hooks && hooks->store_flag && (link_unfused || n_local == 0)) CUDA_TRY(ctx, launch_link_store(hooks->store_flag, hooks->store_value, st));
@@ -907,7 +907,7 @@ int enqueue_device(gort_ctx* ctx, int di, const gort_render_params* p, int eff_r
     const bool chain = chained && !timing;
     const bool waits = hooks && hooks->wait_flag;
     if (waits) CUDA_TRY(ctx, launch_link_wait(hooks->wait_flag, hooks->wait_target, hooks->timed_out, st, chain && link_chain));
-    rp.stamps = tp.stamps;
+    rp.stamps = tp.stamps; rp.done_count = d.d_counter + 8;
     CUDA_TRY(ctx, launch_resolve(rp, st, 0, chain && (!waits || link_chain)));
     if (hooks && hooks->signal_flag) CUDA_TRY(ctx, launch_link_signal(hooks->signal_flag, st, chain && link_chain));
     if (early) CUDA_TRY(ctx, cudaStreamWaitEvent(st, d.ev_aux, 0));
@@ -934,13 +934,11 @@ int collect_stats(gort_ctx* ctx, const gort_render_params* p, gort_stats* s, dou
         float c = 0, a = 0, b = 0;
         if (d.stamped) {
             // cull pass = first cull thread -> first trace thread past its wait for the cull pass; trace = that -> first resolve
-            // thread past its wait for the trace kernel; the rest of ev[0]..ev[2] is the resolve pass (and the launch of the first)
+            // thread past its wait for the trace kernel; resolve = that -> its last CTA
             const volatile unsigned long long* t = d.h_stamps;  // the frame is complete (ev[2]): the stores have landed
-            float total = 0;
-            CUDA_TRY(ctx, cudaEventElapsedTime(&total, d.ev[0], d.ev[2]));
             c = (float)((double)(t[1] - t[0]) * 1e-6);
             a = (float)((double)(t[2] - t[1]) * 1e-6);
-            b = std::max(0.f, total - c - a);
+            b = (float)((double)(t[3] - t[2]) * 1e-6);
         } else {
             CUDA_TRY(ctx, cudaEventElapsedTime(&c, d.ev[0], d.ev_tc));  // memsets + cull pass
             CUDA_TRY(ctx, cudaEventElapsedTime(&a, d.ev_tc, d.ev[1]));  // the trace kernel(s) alone

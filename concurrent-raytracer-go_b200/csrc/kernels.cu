@@ -1086,6 +1086,14 @@ __global__ void __launch_bounds__(256) resolve_kernel(const ResolveParams R) {
         if (R.slab_mode) out[i] = px;
         else if (inside) out[(size_t)y * R.width + x] = px;
     }
+    if (R.stamps) {
+        // end of the frame for gort_stats: stamped by the last CTA to get here
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(R.done_count, 1u) == gridDim.x - 1) {
+            *R.done_count = 0;  // for the next launch on this stream
+            asm volatile("{ .reg .u64 t; mov.u64 t, %%globaltimer; st.global.u64 [%0], t; }" ::"l"(R.stamps + 3) : "memory");
+        }
+    }
 }
 
 cudaError_t launch_resolve(const ResolveParams& p, cudaStream_t stream, int max_blocks, bool dependent) {

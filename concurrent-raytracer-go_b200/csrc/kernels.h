@@ -90,7 +90,7 @@ struct TraceParams {
     uint8_t* early_out;               // nullptr, or the row-major RGBA8 frame: one warp in eight CTAs of the trace kernel first writes black
                                       // into the pixel blocks the cull pass dropped (a page-locked host frame fills over PCIe under the trace)
     unsigned long long* stamps;       // nullptr, or %globaltimer stamps of the frame: [0] cull pass starts, [1] trace kernel starts (cull done),
-                                      // [2] resolve starts (trace done) — the kernel split of gort_stats without event records between the kernels
+                                      // [2] resolve starts (trace done), [3] resolve ends — the kernel times of gort_stats without event records
     unsigned long long* debug_times;  // nullptr, or [1 + 2*n_warps]: kernel start, then per warp (end of units, end of drain) in ns
     uint32_t rk[20];             // Philox4x32-10 round keys: rk[2r] = key0 + r*W0, rk[2r+1] = key1 + r*W1
     int fog_enabled;
@@ -128,7 +128,8 @@ struct ResolveParams {
     uint8_t* out;      // row-major frame (slab_mode 0) or tile-major slab (slab_mode 1)
     int slab_mode;
     int part;          // 0 every pixel; 1 only the culled blocks (black; needs nothing but the cull pass); 2 only the kept blocks
-    unsigned long long* stamps;  // see TraceParams
+    unsigned long long* stamps;  // see TraceParams; [3] = the last CTA of this pass is done
+    unsigned int* done_count;    // with stamps: device word, zero between launches
 };
 
 // frame-link work folded into the cull pass and per-frame counter upkeep: its first thread zeroes the counter bank of the
