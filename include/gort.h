@@ -148,8 +148,11 @@ typedef struct gort_render_params {
 } gort_render_params;
 
 typedef struct gort_stats {
-    double kernel_ms;    /* CUDA-event time of trace + resolve kernels, max over the ctx's devices */
-    double trace_ms;     /* the trace kernel alone (device 0) */
+    double kernel_ms;    /* device time of the frame (cull + trace + resolve), max over the ctx's devices.  Per-warp-queue path
+                            (render_path 0/1): from %globaltimer stamps the kernels write — first cull thread to last resolve CTA —
+                            so that asking for stats does not put event records between the kernels; wavefront pipeline
+                            (render_path 2) and n_devices > 1: CUDA events on the stream */
+    double trace_ms;     /* the trace kernel(s) alone (device 0) */
     double resolve_ms;   /* tone-map/quantise/pack kernel (+ gather/unswizzle when n_devices > 1) */
     double total_ms;     /* host wall clock of the whole call (launch + D2H where applicable) */
     double upload_ms;    /* last gort_scene_upload: host flatten + H2D */
