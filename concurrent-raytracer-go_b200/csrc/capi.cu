@@ -78,6 +78,9 @@ struct DeviceState {
     // global-queue wavefront pipeline (stream.cu): path / record / pair queues of one batch, counter ring, readback
     uint8_t* d_stream = nullptr;
     size_t stream_bytes = 0;
+    float4* d_top = nullptr;           // first four levels of the 4-wide tree as one block (lbvh.h: wide_top_block)
+    uint8_t* d_sort = nullptr;         // sorted mode: (key, entry) double buffers + radix-sort scratch
+    size_t sort_bytes = 0;
     unsigned int* d_ctl = nullptr;     // 2 x kCtlWords + the frame's primary cursor (64 bit)
     unsigned int* h_count = nullptr;   // pinned: {active deep, active other, first 6 counters of the iteration}
     cudaEvent_t ev_count = nullptr;
@@ -629,6 +632,10 @@ int run_stream(gort_ctx* ctx, DeviceState& d, const TraceParams& tp, const gort_
         if (int rc = ensure(ctx, d.d_build, d.build_bytes, need)) return rc;
         CUDA_TRY(ctx, bvh_collapse_wide(d.d_nodes, ctx->bvh.n_nodes, d.d_nodes + 6 * (size_t)ctx->bvh.n_nodes, ctx->bvh.qorigin, ctx->bvh.qcell, d.d_build,
                                         d.build_bytes, st));
+        // ... and the top of it as one block, for the traversal kernel's shared-memory staging (GORT_TOP)
+        size_t top_have = d.d_top ? kTopNodes * 64 : 0;
+        if (int rc = ensure(ctx, d.d_top, top_have, (size_t)kTopNodes * 64)) return rc;
+        CUDA_TRY(ctx, wide_top_block(d.d_nodes + 6 * (size_t)ctx->bvh.n_nodes, d.d_top, st));
         d.wide_serial = ctx->scene_serial;
     }
     const uint64_t per_sample = (uint64_t)n_active * 32u;
@@ -658,6 +665,19 @@ int run_stream(gort_ctx* ctx, DeviceState& d, const TraceParams& tp, const gort_
         v.cand_recs = (uint4*)take(32 * kStreamLightChunk);
         if ((size_t)(q - d.d_stream) > d.stream_bytes) return fail(ctx, GORT_ERR_INVALID, "stream buffer carve-out overflow");
     }
+    // Sorted mode (GORT_SORT=0..3): the entries of an iteration's queue are scattered in Morton order of their hit points.
+    // Queues below kSortMin entries are not worth the sort's launches.
+    const char* so = getenv("GORT_SORT");
+    const int sort_mode = so ? atoi(so) : kStreamSortDefault;  // 1: Morton order; 2: coarser cells; 3: live entries first only
+    const bool sorted = sort_mode >= 1 && sort_mode <= 3;
+    const int sort_begin_bit = sort_mode == 2 ? 8 : (sort_mode == 3 ? 23 : 0);
+    constexpr uint32_t kSortMin = 1u << 15;
+    if (sorted)
+        if (int rc = ensure(ctx, d.d_sort, d.sort_bytes, stream_sort_bytes((uint32_t)cap))) return rc;
+    // GORT_TOP=0|1: the traversal kernel stages the top of the wide tree in shared memory
+    const char* te = getenv("GORT_TOP");
+    v.top = (stream_wants_wide_nodes() && (te ? atoi(te) != 0 : kStreamTopDefault)) ? d.d_top : nullptr;
+    v.top_plain = te && atoi(te) == 2;
     v.cap = (uint32_t)cap;
     v.n_active = n_active; v.n_deep = n_deep;
     v.prim_total = prim_total;
@@ -669,13 +689,19 @@ int run_stream(gort_ctx* ctx, DeviceState& d, const TraceParams& tp, const gort_
     // next queue up with new primary rays; trace both; shade the records.  Ring of two counter blocks.
     CUDA_TRY(ctx, cudaMemsetAsync(d.d_ctl, 0, (2 * kCtlWords + 2) * sizeof(unsigned int), st));
     uint64_t generated = 0;
+    uint32_t n_cur = 0;  // entries of the current queue (= the previous iteration's kCtlNextTotal, read back below)
     for (int it = 0;; it++) {
         v.cur = it & 1;
         v.ctl = d.d_ctl + (size_t)(it & 1) * kCtlWords;
         v.ctl_prev = d.d_ctl + (size_t)((it & 1) ^ 1) * kCtlWords;
         v.chunk = 0;
+        v.order = nullptr;
         if (it > 0) {
             CUDA_TRY(ctx, cudaMemsetAsync(v.ctl, 0, kCtlWords * sizeof(unsigned int), st));
+            if (sorted && n_cur >= kSortMin) {
+                CUDA_TRY(ctx, stream_launch_sort(tp, v, n_cur, sort_begin_bit, d.d_sort, d.sort_bytes, st));
+                d.last_launches++;  // the key pass (the radix sort's passes are CUB's)
+            }
             CUDA_TRY(ctx, stream_launch_scatter(tp, v, geom, stats, d.sm_count, st));
             d.last_launches++;
         }
@@ -695,6 +721,7 @@ int run_stream(gort_ctx* ctx, DeviceState& d, const TraceParams& tp, const gort_
         }
         CUDA_TRY(ctx, cudaEventSynchronize(d.ev_count));
         generated += d.h_count[2 + kCtlNew];
+        n_cur = d.h_count[2 + kCtlNextTotal];
         if (d.h_count[2 + kCtlNextTotal] == 0 && generated >= prim_total) break;  // nothing left to scatter, nothing left to generate
     }
     return GORT_OK;
@@ -1096,7 +1123,7 @@ void gort_destroy(gort_ctx* ctx) {
         if (d.ev_aux) cudaEventDestroy(d.ev_aux);
         if (d.ev_tc) cudaEventDestroy(d.ev_tc);
         if (d.ev_count) cudaEventDestroy(d.ev_count);
-        cudaFree(d.d_stream); cudaFree(d.d_ctl); cudaFree(d.d_build);
+        cudaFree(d.d_stream); cudaFree(d.d_sort); cudaFree(d.d_top); cudaFree(d.d_ctl); cudaFree(d.d_build);
         if (d.h_count) cudaFreeHost(d.h_count);
         if (d.own_stream) cudaStreamDestroy(d.own_stream);
     }

@@ -301,6 +301,45 @@ __global__ void wide_emit_kernel(const float4* __restrict__ nodes, int n2, const
 
 }  // namespace
 
+namespace {
+
+// one thread: 85 nodes, once per uploaded scene
+__global__ void wide_top_kernel(const float4* __restrict__ wide, float4* __restrict__ top) {
+    int ids[kTopNodes];
+    unsigned char depth[kTopNodes];
+    int cnt = 1;
+    ids[0] = 0;  // the root is wide node 0
+    depth[0] = 0;
+    for (int h = 0; h < cnt; h++) {
+        const float4* np = wide + 4 * (size_t)ids[h];
+        const float4 a = np[0], b = np[1], c = np[2];
+        float4 d = np[3];
+        if (depth[h] < kTopLevels - 1) {
+            int l[4] = {__float_as_int(d.x), __float_as_int(d.y), __float_as_int(d.z), __float_as_int(d.w)};
+            for (int k = 0; k < 4; k++) {
+                if (l[k] >= 0 && l[k] != kWideNoChild && cnt < kTopNodes) {
+                    ids[cnt] = l[k];
+                    depth[cnt] = depth[h] + 1;
+                    l[k] = kTopBase + cnt;
+                    cnt++;
+                }
+            }
+            d = make_float4(__int_as_float(l[0]), __int_as_float(l[1]), __int_as_float(l[2]), __int_as_float(l[3]));
+        }
+        top[4 * h + 0] = a; top[4 * h + 1] = b; top[4 * h + 2] = c; top[4 * h + 3] = d;
+    }
+    const float4 none = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 links = make_float4(__int_as_float(kWideNoChild), __int_as_float(kWideNoChild), __int_as_float(kWideNoChild), __int_as_float(kWideNoChild));
+    for (int h = cnt; h < kTopNodes; h++) { top[4 * h + 0] = none; top[4 * h + 1] = none; top[4 * h + 2] = none; top[4 * h + 3] = links; }
+}
+
+}  // namespace
+
+cudaError_t wide_top_block(const float4* wide, float4* top_out, cudaStream_t st) {
+    wide_top_kernel<<<1, 1, 0, st>>>(wide, top_out);
+    return cudaGetLastError();
+}
+
 size_t bvh_collapse_scratch_bytes(int n2) {
     size_t scan_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, n2);

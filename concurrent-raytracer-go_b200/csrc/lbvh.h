@@ -33,6 +33,13 @@ cudaError_t lbvh_build(const LbvhIn& in, const LbvhOut& out, void* scratch, size
 // quantisation grid (rounded outward by two cells), word 12 + k = child k's link (>= 0 wide node, < 0 leaf as in bvh.h,
 // kWideNoChild = empty slot).  One visit = two 256-bit loads and four slab tests: half the dependent node fetches of the binary walk.
 constexpr int kWideNoChild = 0x7FFFFFFF;
+// Top of the wide tree as one contiguous block (wide_top_block): the nodes of the first kTopLevels wide levels (= eight binary
+// levels) in breadth-first order, kTopNodes x 64 bytes, links between them rewritten to kTopBase + position in the block; links
+// that leave the block are the global ones.  A traversal kernel stages the block in shared memory with one bulk copy.
+constexpr int kTopLevels = 4;
+constexpr int kTopNodes = 1 + 4 + 16 + 64;
+constexpr int kTopBase = 0x40000000;
+cudaError_t wide_top_block(const float4* wide, float4* top_out, cudaStream_t st);
 size_t bvh_collapse_scratch_bytes(int n_nodes2);
 cudaError_t bvh_collapse_wide(const float4* nodes2, int n_nodes2, float4* wide_out, const float* qorigin3, const float* qcell3, void* scratch,
                               size_t scratch_bytes, cudaStream_t st);

@@ -5,7 +5,12 @@
 // those of kernels.cu (trace_kernel), stage by stage; the reference lines are cited there and again here.
 #include "stream.h"
 
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
 #include <cooperative_groups.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include "device.cuh"
 #include "lbvh.h"
@@ -88,9 +93,12 @@ __device__ __forceinline__ void light_dir(const float4 L0, float ox, float oy, f
 // lanes keep their walk state: the warp's instruction stream stays filled whatever the spread of walk lengths.
 // ANY sources (shadow rays) stop at the first accepted primitive.
 // ---------------------------------------------------------------------------------------------
-template <int SRC, bool STATS, int GEOM>
+// TOP (4-wide walk only): the first four wide levels of the tree (lbvh.h: wide_top_block, 5.4 KB) are staged in shared memory
+// by one bulk copy (cp.async.bulk -> mbarrier) when the CTA starts, and visits of those nodes read them from there.
+template <int SRC, bool STATS, int GEOM, bool TOP>
 __global__ void __launch_bounds__(128, GORT_POOL_MINB) pool_trace_kernel(const __grid_constant__ TraceParams P, const __grid_constant__ StreamView V) {
     constexpr bool ANY = SRC == SRC_HARD || SRC == SRC_SOFT;
+    [[maybe_unused]] const float4* top_s = nullptr;
     const SceneView& S = P.scene;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -122,6 +130,37 @@ __global__ void __launch_bounds__(128, GORT_POOL_MINB) pool_trace_kernel(const _
 #endif
     const float4* __restrict__ spheres = GEOM != 2 ? S.spheres : nullptr;
     const float4* __restrict__ tris = GEOM != 1 ? S.tris : nullptr;
+
+    int root = 0;  // where a walk starts: wide node 0, or its copy at the head of the staged block
+    if constexpr (TOP) {
+        __shared__ __align__(128) float4 top_block[kTopNodes * 4];
+        __shared__ __align__(8) unsigned long long top_bar;
+        top_s = top_block;
+        constexpr uint32_t kTopBytes = kTopNodes * 4 * sizeof(float4);
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&top_bar), dst = (uint32_t)__cvta_generic_to_shared(top_block);
+        if (V.top_plain) {
+            // (A/B switch: the same block copied by the CTA's threads, no bulk copy, no mbarrier)
+            for (int k = threadIdx.x; k < kTopNodes * 4; k += blockDim.x) top_block[k] = __ldg(V.top + k);
+            __syncthreads();
+            root = kTopBase;
+        }
+        if (!V.top_plain && threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (!V.top_plain && threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kTopBytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(V.top), "r"(kTopBytes), "r"(bar)
+                         : "memory");
+        }
+        // every thread waits for phase 0 of the barrier (the copy's bytes); bounded, and a walk that never got its block
+        // simply starts at the global root
+        uint32_t ok = V.top_plain ? 1u : 0u;
+        for (int tries = 0; tries < (1 << 16) && !ok; tries++)
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar) : "memory");
+        if (__syncthreads_and((int)ok)) root = kTopBase;
+    }
 
     uint32_t wnext = 0, wend = 0;  // this warp's share of the pool: [wnext, wend)
     bool pool_done = false;        // warp-uniform
@@ -251,7 +290,7 @@ __global__ void __launch_bounds__(128, GORT_POOL_MINB) pool_trace_kernel(const _
                         oodx = q.ox * idx; oody = q.oy * idy; oodz = q.oz * idz;
 #endif
                         sp = 0;
-                        node = 0;
+                        node = root;
                         have = true;
                     }
                 }
@@ -273,8 +312,13 @@ __global__ void __launch_bounds__(128, GORT_POOL_MINB) pool_trace_kernel(const _
                 stat_add<STATS>(st, kStatNodes, 2);
                 stat_add<STATS>(st, kStatWalkLane0 + SRC);
                 float4 A, B, C, D;
-                ldg8(nodes + 4 * (size_t)node, A, B);
-                ldg8(nodes + 4 * (size_t)node + 2, C, D);
+                if (TOP && node >= kTopBase) {
+                    const float4* tn = top_s + 4 * (node - kTopBase);
+                    A = tn[0]; B = tn[1]; C = tn[2]; D = tn[3];
+                } else {
+                    ldg8(nodes + 4 * (size_t)node, A, B);
+                    ldg8(nodes + 4 * (size_t)node + 2, C, D);
+                }
                 const uint32_t magic = 0x4B000000u;  // 2^23
 #define GORT_QLO(w) __uint_as_float((__float_as_uint(w) & 0xffffu) | magic)
 #define GORT_QHI(w) __uint_as_float(__byte_perm(__float_as_uint(w), magic, 0x7632))
@@ -486,14 +530,17 @@ __global__ void __launch_bounds__(128) stream_scatter_kernel(const __grid_consta
     const unsigned lt_mask = (1u << lane) - 1u;
     Stats st;
     stats_zero<STATS>(st);
-    const uint32_t n_cur = V.ctl_prev[kCtlNextTotal];
+    // sorted mode: the live entries, in Morton order of their hit points (stream_launch_sort)
+    const bool sorted = V.order != nullptr;
+    const uint32_t n_cur = sorted ? V.ctl[kCtlLive] : V.ctl_prev[kCtlNextTotal];
     const int cur = V.cur, nxt = cur ^ 1;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t base = warp * 32u; base < n_cur; base += n_warps * 32u) {
-        const uint32_t i = base + lane;
+        uint32_t i = base + lane;
         float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
         bool alive = false;
         if (i < n_cur) {
+            if (sorted) i = __ldg(V.order + i);
             A = V.qa[cur][i];
             alive = __float_as_uint(A.w) != kDeadPrim;
         }
@@ -1048,6 +1095,74 @@ __global__ void stream_plan_kernel(const StreamView V) {
     *V.prim_cursor = done + n_new;
 }
 
+// ---------------------------------------------------------------------------------------------
+// sorted mode: key pass + radix sort of (key, entry) pairs.  Key = 23-bit Morton code of the entry's hit point on the
+// BVH's quantisation grid (8 + 8 + 7 bits); a dead entry (miss / ended path) gets bit 23, so the live ones come first
+// and scatter stops at their count.  The paths' arithmetic, Philox counters and accumulator adds do not depend on the
+// order they are processed in: the frame is the same.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t spread_bits3(uint32_t v) {  // 8 bits -> every third bit
+    v = (v | (v << 8)) & 0x0000F00Fu;
+    v = (v | (v << 4)) & 0x000C30C3u;
+    v = (v | (v << 2)) & 0x00249249u;
+    return v;
+}
+
+__global__ void __launch_bounds__(256) stream_sort_keys_kernel(const StreamView V, uint32_t n, float qox, float qoy, float qoz, float icx, float icy, float icz,
+                                                               uint32_t* __restrict__ keys, uint32_t* __restrict__ idx) {
+    const float4* __restrict__ qa = V.qa[V.cur];
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {  // block-uniform trip count
+        const uint32_t i = base + threadIdx.x;
+        bool live = false;
+        if (i < n) {
+            const float4 A = qa[i];
+            live = __float_as_uint(A.w) != kDeadPrim;
+            uint32_t key = 1u << 23;
+            if (live) {
+                const uint32_t gx = __float2uint_rz(fminf(fmaxf((A.x - qox) * icx, 0.f), 65535.f)) >> 8;
+                const uint32_t gy = __float2uint_rz(fminf(fmaxf((A.y - qoy) * icy, 0.f), 65535.f)) >> 8;
+                const uint32_t gz = __float2uint_rz(fminf(fmaxf((A.z - qoz) * icz, 0.f), 65535.f)) >> 8;
+                key = (spread_bits3(gx) | (spread_bits3(gy) << 1) | (spread_bits3(gz) << 2)) >> 1;
+            }
+            keys[i] = key;
+            idx[i] = i;
+        }
+        const unsigned lm = __ballot_sync(FULL_MASK, live);
+        if ((threadIdx.x & 31) == 0 && lm) atomicAdd(V.ctl + kCtlLive, (unsigned int)__popc(lm));
+    }
+}
+
+static size_t sort_temp_bytes(uint32_t cap) {
+    size_t bytes = 0;
+    cub::DoubleBuffer<uint32_t> k(nullptr, nullptr), x(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, x, (int)cap, 0, 24);
+    return (bytes + 255) / 256 * 256;
+}
+
+size_t stream_sort_bytes(uint32_t cap) { return 4 * (((size_t)cap * sizeof(uint32_t) + 255) / 256 * 256) + sort_temp_bytes(cap); }
+
+cudaError_t stream_launch_sort(const TraceParams& p, StreamView& v, uint32_t n_cur, int begin_bit, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+    v.order = nullptr;
+    if (n_cur == 0) return cudaSuccess;
+    if (n_cur > v.cap || begin_bit < 0 || begin_bit > 23 || scratch_bytes < stream_sort_bytes(v.cap)) return cudaErrorInvalidValue;
+    const size_t arr = ((size_t)v.cap * sizeof(uint32_t) + 255) / 256 * 256;
+    uint8_t* q = (uint8_t*)scratch;
+    uint32_t* k0 = (uint32_t*)q; uint32_t* k1 = (uint32_t*)(q + arr);
+    uint32_t* x0 = (uint32_t*)(q + 2 * arr); uint32_t* x1 = (uint32_t*)(q + 3 * arr);
+    void* tmp = q + 4 * arr;
+    size_t tmp_bytes = scratch_bytes - 4 * arr;
+    const SceneView& S = p.scene;
+    const int grid = (int)std::min<uint32_t>((n_cur + 255u) / 256u, 148u * 32u);
+    stream_sort_keys_kernel<<<grid, 256, 0, st>>>(v, n_cur, S.qox, S.qoy, S.qoz, 1.0f / S.qcx, 1.0f / S.qcy, 1.0f / S.qcz, k0, x0);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    cub::DoubleBuffer<uint32_t> dk(k0, k1), dx(x0, x1);
+    e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dx, (int)n_cur, begin_bit, 24, st);
+    if (e != cudaSuccess) return e;
+    v.order = dx.Current();
+    return cudaSuccess;
+}
+
 cudaError_t stream_launch_plan(const StreamView& v, cudaStream_t st) {
     stream_plan_kernel<<<1, 1, 0, st>>>(v);
     return cudaGetLastError();
@@ -1062,19 +1177,40 @@ size_t stream_bytes_per_slot() {
     return 2 * (3 * sizeof(float4) + sizeof(uint2)) + 4 * sizeof(float4) + sizeof(uint2) + kLC * (1 + 4 + 4 + 4 + 4 + 32);
 }
 
-template <int SRC, bool STATS, int GEOM>
-static cudaError_t launch_pool(const TraceParams& p, const StreamView& v, int sm_count, cudaStream_t st) {
+template <int SRC, bool STATS, int GEOM, bool TOP>
+static cudaError_t launch_pool_top(const TraceParams& p, const StreamView& v, int sm_count, cudaStream_t st) {
     static int ctas_per_sm = 0;
     if (ctas_per_sm == 0) {
-        // no shared memory in this kernel: the SM's whole carve-out is L1 for the BVH
-        cudaFuncSetAttribute(pool_trace_kernel<SRC, STATS, GEOM>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+        // no shared memory in this kernel (TOP: 5.4 KB per CTA): the rest of the SM's carve-out is L1 for the BVH
+        int carveout = TOP ? 40 : cudaSharedmemCarveoutMaxL1;
+        if (TOP) {
+            // "prefer L1" leaves room for ONE CTA's block (and the occupancy query below answers 1): ask for the carve-out
+            // that holds the blocks of all the CTAs the register file admits
+            cudaFuncAttributes fa;
+            int dev = 0, smem_sm = 0;
+            if (cudaFuncGetAttributes(&fa, pool_trace_kernel<SRC, STATS, GEOM, TOP>) == cudaSuccess && cudaGetDevice(&dev) == cudaSuccess &&
+                cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) == cudaSuccess && smem_sm > 0) {
+                const size_t need = (size_t)GORT_POOL_MINB * (fa.sharedSizeBytes + 1024);  // + the 1 KB the system reserves per CTA
+                carveout = (int)std::min<size_t>(100, (need * 100 + (size_t)smem_sm - 1) / (size_t)smem_sm + 1);
+            }
+        }
+        cudaFuncSetAttribute(pool_trace_kernel<SRC, STATS, GEOM, TOP>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
         int n = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, pool_trace_kernel<SRC, STATS, GEOM>, 128, 0);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, pool_trace_kernel<SRC, STATS, GEOM, TOP>, 128, 0);
         if (e != cudaSuccess) return e;
         ctas_per_sm = n > 0 ? n : 1;
+        if (getenv("GORT_STREAM_DEBUG")) fprintf(stderr, "pool_trace<%d,%d,%d,%d>: carve-out %d, %d CTAs/SM\n", SRC, (int)STATS, GEOM, (int)TOP, carveout, ctas_per_sm);
     }
-    pool_trace_kernel<SRC, STATS, GEOM><<<sm_count * ctas_per_sm, 128, 0, st>>>(p, v);
+    pool_trace_kernel<SRC, STATS, GEOM, TOP><<<sm_count * ctas_per_sm, 128, 0, st>>>(p, v);
     return cudaGetLastError();
+}
+
+template <int SRC, bool STATS, int GEOM>
+static cudaError_t launch_pool(const TraceParams& p, const StreamView& v, int sm_count, cudaStream_t st) {
+#if GORT_POOL_WIDE
+    if (!STATS && v.top) return launch_pool_top<SRC, false, GEOM, true>(p, v, sm_count, st);  // (a stats frame reads every node from global memory)
+#endif
+    return launch_pool_top<SRC, STATS, GEOM, false>(p, v, sm_count, st);
 }
 
 template <int SRC>

@@ -35,6 +35,8 @@ namespace gort {
 constexpr int kStreamLightChunk = 4;  // lights per shading pass
 constexpr int kStreamMaxChunks = 7;   // scenes with more than 28 lights use the per-warp-queue kernel
 constexpr int kCtlWords = 64;         // uint32 counters per iteration
+constexpr bool kStreamTopDefault = true;    // shared-memory staging of the top of the wide tree unless GORT_TOP=0
+constexpr int kStreamSortDefault = 0;     // sorted mode (stream_launch_sort) unless GORT_SORT says otherwise
 // counter block of one iteration (a ring of two; plus the frame's primary cursor behind the ring)
 enum StreamCtl {
     kCtlNext = 0,       // paths appended to the next queue by scatter == rays of pool_trace<EXT>
@@ -44,6 +46,7 @@ enum StreamCtl {
     kCtlNew = 4,        // primary rays generated this iteration (path regeneration), written by the plan kernel
     kCtlNextTotal = 5,  // kCtlNext + kCtlNew: entries of the next queue
     kCtlPrimStart = 6,  // (two words, low first) index of the first new primary ray in the frame's primary sequence
+    kCtlLive = 15,      // sorted mode: live entries of the current queue (the spare eighth word of light chunk 0's block)
     kCtlChunk0 = 8,     // per light chunk c at kCtlChunk0 + 8 c:
     kCtlHard = 0, kCtlFetchHard = 1, kCtlWalk = 2, kCtlFetchWalk = 3,
     kCtlLit = 4,        // lit pairs (hard shadow ray unoccluded) == cone walks of pool_cone
@@ -71,6 +74,12 @@ struct StreamView {
     uint32_t* walk_list;     // [cap * 4] lit pairs whose 16 rays walk the BVH themselves
     uint32_t* lit_list;      // [cap * 4] lit pairs, in the order their hard shadow rays finished
     uint4* cand_recs;        // [cap * 4] x 2: (pair, candidate count, candidates 0-1) (candidates 2-5)
+    // sorted mode (stream_launch_sort): the live entries of the current queue in Morton order of their hit points;
+    // nullptr = scatter reads the queue in the order it was written
+    const uint32_t* order;
+    // top of the wide tree as one block (lbvh.h: wide_top_block); nullptr = every node is read from global memory
+    const float4* top;
+    int top_plain;           // A/B switch: stage it with plain loads instead of the bulk copy
     unsigned int* ctl;       // this iteration's counter block
     const unsigned int* ctl_prev;  // previous iteration's block (kCtlNextTotal = entries of the current queue)
     unsigned long long* prim_cursor;  // primary rays of the frame generated so far
@@ -87,6 +96,12 @@ bool stream_wants_wide_nodes();  // the traversal kernel of this build walks the
 // plan: how many primary rays join the next queue this iteration (fills it up to `cap`), 1 thread
 cudaError_t stream_launch_plan(const StreamView& v, cudaStream_t st);
 cudaError_t stream_launch_primary(const TraceParams& p, const StreamView& v, int geom, bool stats, int sm_count, cudaStream_t st);
+// Sorted mode: order the current queue's live entries by the Morton code of their hit points before scatter reads them, so
+// that the shade records, the shadow-ray lists and the scattered rays that derive from 32 consecutive entries start close
+// together (coherent walks).  n_cur = entries of the current queue (the host has read it back); sets v.order.
+size_t stream_sort_bytes(uint32_t cap);
+// begin_bit: 0 = the full 23-bit code; 8 = 32x coarser cells (one radix pass fewer); 23 = live entries first, order kept
+cudaError_t stream_launch_sort(const TraceParams& p, StreamView& v, uint32_t n_cur, int begin_bit, void* scratch, size_t scratch_bytes, cudaStream_t st);
 cudaError_t stream_launch_scatter(const TraceParams& p, const StreamView& v, int geom, bool stats, int sm_count, cudaStream_t st);
 cudaError_t stream_launch_trace_ext(const TraceParams& p, const StreamView& v, int geom, bool stats, int sm_count, cudaStream_t st);
 cudaError_t stream_launch_shade_chunk(const TraceParams& p, const StreamView& v, int geom, bool stats, int sm_count, cudaStream_t st);

@@ -166,3 +166,27 @@ def test_stream_shards_compose(gort, renderer):
             renderer.Render(sc, 200, 136, out=out)
         renderer.SetShard(0, 1)
     assert np.array_equal(full, out)
+
+
+@pytest.mark.parametrize("objects,bvh", [(1, "host"), (3, "host"), (300, "host"), (300, "device"), (6000, "device")])
+def test_stream_switches_keep_the_frame(gort, renderer, objects, bvh):
+    """The staged top-of-tree block (GORT_TOP: the first four levels of the 4-wide tree in shared memory, one bulk copy per
+    CTA; 2 = plain loads) and the sorted mode (GORT_SORT: scatter reads the queue in Morton order of the hit points) change
+    where a node is read from and the order paths are processed in — never a path's arithmetic: the exact accumulators
+    are equal, from a one-sphere tree (top block = the root alone) to one deeper than the block."""
+    if objects <= 3:
+        d = Cm.c1_view()
+        d["objects"] = d["objects"][:objects]
+    else:
+        d = Cm.random_sphere_scene(objects, 40 + objects, cam_z=13.0 if objects < 1000 else 26.0)
+    configure(renderer, 2, 6, seed=11)
+    with forced_path("stream", GORT_BVH=bvh, GORT_TOP=0, GORT_SORT=0):
+        sc = gort.SceneFromDict(d)
+        renderer.Render(sc, 320, 240)
+        assert renderer.lastStats.render_path == 2
+        base = renderer.ReadRadiance(320, 240)
+    assert base.max() > 0
+    for env in ({"GORT_TOP": 1}, {"GORT_TOP": 2}, {"GORT_TOP": 0, "GORT_SORT": 1}, {"GORT_TOP": 1, "GORT_SORT": 1}, {"GORT_SORT": 3}):
+        with forced_path("stream", GORT_BVH=bvh, **env):
+            renderer.Render(sc, 320, 240)
+            assert np.array_equal(renderer.ReadRadiance(320, 240), base), env
