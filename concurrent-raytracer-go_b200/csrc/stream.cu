@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(128, GORT_POOL_MINB) pool_trace_kernel(const _
         // every thread waits for phase 0 of the barrier (the copy's bytes); bounded, and a walk that never got its block
         // simply starts at the global root
         uint32_t ok = V.top_plain ? 1u : 0u;
-        for (int tries = 0; tries < (1 << 16) && !ok; tries++)
+        for (int tries = 0; tries < (1 << 20) && !ok; tries++)  // (2^16 failed tries took 12 ms on a B200: the bound is ~0.2 s)
             asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar) : "memory");
         if (__syncthreads_and((int)ok)) root = kTopBase;
     }
