@@ -36,6 +36,10 @@ from typing import Callable, Optional, Sequence
 import numpy as np
 
 CHUNK_KEYS = ("id", "start_x", "end_x", "start_y", "end_y", "width", "height", "scene", "priority")
+# A node is reachable from the network: what a request may ask of it is bounded (the reference's stub renders nothing, so it
+# has no such limits to mirror).
+MAX_FRAME_PIXELS = 1 << 26   # width x height of the frame a chunk belongs to (the node allocates the frame per request)
+MAX_BODY_BYTES = 16 << 20    # POST /render body (a scene JSON sent inline is a few MB at most)
 
 
 def make_chunks(width: int, height: int, chunk_w: int, chunk_h: int, scene: str) -> list:
@@ -55,6 +59,8 @@ def validate_chunk(c: dict) -> Optional[str]:
             return "chunk field %s must be an integer" % k
     if c["width"] <= 0 or c["height"] <= 0:
         return "width/height must be positive"
+    if c["width"] > 65535 or c["height"] > 65535 or c["width"] * c["height"] > MAX_FRAME_PIXELS:
+        return "frame too large for this node (at most %d pixels)" % MAX_FRAME_PIXELS
     if not (0 <= c["start_x"] < c["end_x"] <= c["width"] and 0 <= c["start_y"] < c["end_y"] <= c["height"]):
         return "chunk rectangle outside the frame"
     if not isinstance(c.get("scene", ""), str):
@@ -82,13 +88,24 @@ def decode_pixels(result: dict, chunk: dict) -> np.ndarray:
     return rect
 
 
+def resolve_scene_path(root: str, name: str) -> str:
+    """A request names its scene file; the node opens it only inside its own scene directory (no absolute paths, no `..` or
+    symlinks that lead out of it)."""
+    root = os.path.realpath(root)
+    path = os.path.realpath(os.path.join(root, name))
+    if os.path.isabs(name) or os.path.commonpath([root, path]) != root:
+        raise ValueError("scene path outside the node's scene directory")
+    return path
+
+
 class GpuChunkRenderer:
     """RenderChunk -> [h, w, 4] uint8 through libgort (one renderer per node; calls are serialised by ChunkNode)."""
 
-    def __init__(self, samples: int = 100, max_depth: int = 50, seed: int = 0, options: int = 0, device: int = 0):
+    def __init__(self, samples: int = 100, max_depth: int = 50, seed: int = 0, options: int = 0, device: int = 0, scene_root: str = "."):
         from . import NewParallelRenderer, SceneFromDict  # noqa: F401  (raises GortError without a CUDA device: no CPU fallback)
         self._mod = __import__(__package__, fromlist=["x"])
         self.r = NewParallelRenderer(1, devices=[device])
+        self.scene_root = os.path.realpath(scene_root)  # `scene` paths of a request are resolved inside this directory only
         self.defaults = {"samples": samples, "max_depth": max_depth, "seed": seed, "options": options}
         self._scene_key = None
         self._scene = None
@@ -99,7 +116,7 @@ class GpuChunkRenderer:
             if text.lstrip().startswith("{"):
                 self._scene = self._mod.Scene(text, options)
             else:
-                self._scene = self._mod.LoadFromFile(text, options)
+                self._scene = self._mod.LoadFromFile(resolve_scene_path(self.scene_root, text), options)
             self._scene_key = key
         return self._scene
 
@@ -154,7 +171,10 @@ class ChunkNode:
                 if self.path.split("?")[0] != "/render":
                     return self._plain(404, "404 page not found")
                 try:
-                    chunk = json.loads(self.rfile.read(int(self.headers.get("Content-Length", "0"))))
+                    n = int(self.headers.get("Content-Length", "0"))
+                    if n < 0 or n > MAX_BODY_BYTES:
+                        return self._plain(413, "Request body too large")
+                    chunk = json.loads(self.rfile.read(n))
                     if not isinstance(chunk, dict):
                         raise ValueError
                 except (ValueError, json.JSONDecodeError):
@@ -302,13 +322,14 @@ def main(argv=None):
     import argparse
     ap = argparse.ArgumentParser(description="serve /render and /status (the reference's chunk-farm protocol) from this GPU")
     ap.add_argument("--port", type=int, default=8080)
-    ap.add_argument("--host", default="0.0.0.0")
+    ap.add_argument("--host", default="127.0.0.1", help="interface to listen on (0.0.0.0 to serve a dispatcher on another host)")
+    ap.add_argument("--scene-root", default=".", help="directory the `scene` paths of a request are resolved in")
     ap.add_argument("--samples", type=int, default=100)
     ap.add_argument("--max-depth", type=int, default=50)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--device", type=int, default=0)
     a = ap.parse_args(argv)
-    node = ChunkNode(GpuChunkRenderer(a.samples, a.max_depth, a.seed, 0, a.device), a.port, a.host)
+    node = ChunkNode(GpuChunkRenderer(a.samples, a.max_depth, a.seed, 0, a.device, a.scene_root), a.port, a.host)
     print("chunk node %s listening on %s:%d" % (node.node_id, a.host, node.port), flush=True)
     node.server.serve_forever()
 

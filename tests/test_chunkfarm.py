@@ -65,6 +65,29 @@ def test_http_errors_follow_the_reference_server(nodes):
     req = urllib.request.Request(base + "/render", data=json.dumps(bad).encode(), method="POST")
     res = json.loads(urllib.request.urlopen(req).read())
     assert "outside the frame" in res["error"] and res["pixels"] == []
+    # what a request may ask of a node is bounded: frame size, body size
+    huge = dict(bad, start_x=0, end_x=1, width=65535, height=65535)
+    req = urllib.request.Request(base + "/render", data=json.dumps(huge).encode(), method="POST")
+    assert "frame too large" in json.loads(urllib.request.urlopen(req).read())["error"]
+    req = urllib.request.Request(base + "/render", data=b"{}", method="POST", headers={"Content-Length": str(CF.MAX_BODY_BYTES + 1)})
+    with pytest.raises(urllib.error.HTTPError) as e:
+        urllib.request.urlopen(req)
+    assert e.value.code == 413
+
+
+def test_scene_paths_stay_inside_the_nodes_scene_directory(tmp_path):
+    """a request names its scene by path: the node opens it under its scene root only"""
+    root = tmp_path / "scenes"
+    (root / "sub").mkdir(parents=True)
+    (root / "sub" / "a.json").write_text("{}")
+    (tmp_path / "secret.json").write_text("{}")
+    assert CF.resolve_scene_path(str(root), "sub/a.json") == str((root / "sub" / "a.json").resolve())
+    for name in ("../secret.json", "sub/../../secret.json", str(tmp_path / "secret.json"), "/etc/passwd"):
+        with pytest.raises(ValueError):
+            CF.resolve_scene_path(str(root), name)
+    (root / "link.json").symlink_to(tmp_path / "secret.json")
+    with pytest.raises(ValueError):
+        CF.resolve_scene_path(str(root), "link.json")
 
 
 def test_dispatcher_assembles_the_frame_from_two_nodes(nodes):
