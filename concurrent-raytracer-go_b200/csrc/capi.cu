@@ -121,6 +121,7 @@ struct gort_ctx {
     cudaStream_t user_stream = nullptr;
     bool use_user_stream = false;
     HostScene scene;
+    HostScene scene_spare;       // the scene before the current one: gort_scene_upload builds into it and swaps
     FlatBvh bvh;
     bool has_scene = false;
     bool peer_direct = false;  // multi-device ctx: all devices can store into the lead device's memory
@@ -289,8 +290,8 @@ int upload_scene_device_bvh(gort_ctx* ctx) {
     const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     std::vector<double> lo(hw * 3, 1e300), hi(hw * 3, -1e300);
     auto work = [&](unsigned t) {
-        double* l = &lo[t * 3];
-        double* h = &hi[t * 3];
+        // (bounds in locals, stored once: the threads' slots of lo / hi share cache lines)
+        double l[3] = {1e300, 1e300, 1e300}, h[3] = {-1e300, -1e300, -1e300};
         for (size_t i = nS * t / hw; i < nS * (t + 1) / hw; i++) {
             pack_sphere(hs.spheres[i], sph[i], meta[i]);
             const double r = std::fabs(hs.spheres[i].r);
@@ -302,6 +303,7 @@ int upload_scene_device_bvh(gort_ctx* ctx) {
                 for (int a = 0; a < 3; a++) { l[a] = std::min(l[a], hs.tris[i].v[k][a]); h[a] = std::max(h[a], hs.tris[i].v[k][a]); }
         }
         for (size_t i = nM * t / hw; i < nM * (t + 1) / hw; i++) pack_material(hs.mats[i], &mats[4 * i]);
+        for (int a = 0; a < 3; a++) { lo[t * 3 + a] = l[a]; hi[t * 3 + a] = h[a]; }
     };
     {
         std::vector<std::thread> pool;
@@ -1149,10 +1151,11 @@ int gort_scene_upload(gort_ctx* ctx, const gort_scene_desc* desc) {
     if (!ctx) return GORT_ERR_INVALID;
     if (!desc) return fail(ctx, GORT_ERR_INVALID, "desc is NULL");
     Lap lap;
-    HostScene hs;
-    std::string err = scene_from_desc(*desc, hs);
+    // built in the spare scene and swapped in: a failed upload leaves the current scene alone, and the arrays of the scene
+    // before last are reused (re-uploading a 1 M-primitive scene neither maps nor unmaps its 90 MB)
+    std::string err = scene_from_desc(*desc, ctx->scene_spare);
     if (!err.empty()) return fail(ctx, GORT_ERR_INVALID, err);
-    ctx->scene = std::move(hs);
+    std::swap(ctx->scene, ctx->scene_spare);
     lap.mark(kLapDesc);
     return upload_scene(ctx);
 }

@@ -66,7 +66,7 @@ static double num_field(const json::Value* o, const char* name, double dflt) {
 
 HostMaterial make_material(const std::string& type, bool has_color, const double color[3], bool has_rough, double rough,
                            bool has_metal, double metal, bool has_spec, double spec, bool has_ior, double ior) {
-    HostMaterial m;
+    HostMaterial m = kDefaultMaterial;
     // Declared extension: a material without "color" gets (1,1,1); the reference panics
     // on the unchecked assertion at scene.go:109/113/120/127/132/141/145.
     double c[3] = {1, 1, 1};
@@ -218,7 +218,7 @@ std::string scene_from_json(const char* text, size_t len, uint32_t options, Host
             std::string type = (t && t->is_string()) ? t->str : "";
             bool prism = (type == "triangularPrism") && (options & 1u);
             if (type != "sphere" && type != "cube" && !prism) continue;  // "Unknown object type" scene.go:80-82
-            HostMaterial m;
+            HostMaterial m = kDefaultMaterial;
             if (!material_from_json(field(o, "material"), m, err)) return "object " + std::to_string(i + 1) + ": " + err;
             int32_t mi = (int32_t)out.mats.size();
             out.mats.push_back(m);
@@ -324,7 +324,15 @@ std::string scene_from_desc(const gort_scene_desc& d, HostScene& out) {
     if (d.n_spheres > 0 && (!d.sphere_center || !d.sphere_radius || !d.sphere_material || !d.sphere_order)) return "sphere arrays missing";
     if (d.n_triangles > 0 && (!d.tri_vertices || !d.tri_material || !d.tri_order)) return "triangle arrays missing";
     if (d.n_lights > 0 && (!d.light_position || !d.light_color || !d.light_intensity)) return "light arrays missing";
-    out = HostScene();
+    {
+        // `out` may be a scene built earlier: its arrays are reused (a re-upload of a scene of the same size then allocates
+        // and faults in nothing), every other field starts from the defaults
+        HostVec<HostMaterial> m = std::move(out.mats);
+        HostVec<HostSphere> s = std::move(out.spheres);
+        HostVec<HostTriangle> t = std::move(out.tris);
+        out = HostScene();
+        out.mats = std::move(m); out.spheres = std::move(s); out.tris = std::move(t);
+    }
     memcpy(out.cam_pos, d.cam_position, sizeof(out.cam_pos));
     memcpy(out.cam_look_at, d.cam_look_at, sizeof(out.cam_look_at));
     memcpy(out.cam_up, d.cam_up, sizeof(out.cam_up));

@@ -23,7 +23,7 @@ int main(int argc, char** argv) {
     const int n_sph = argc > 1 ? atoi(argv[1]) : 100000, n_cubes = argc > 2 ? atoi(argv[2]) : 0, reps = argc > 3 ? atoi(argv[3]) : 3;
     const double ext = n_sph + 12 * n_cubes > 300000 ? 200.0 : 50.0;
     HostScene hs;
-    hs.mats.push_back(HostMaterial());
+    hs.mats.push_back(kDefaultMaterial);
     uint64_t s = 20240601;
     for (int i = 0; i < n_sph; i++) {
         double p[3] = {(uni(s) * 2 - 1) * ext, (uni(s) * 2 - 1) * ext, (uni(s) * 2 - 1) * ext};
