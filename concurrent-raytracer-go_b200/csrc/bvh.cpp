@@ -133,15 +133,20 @@ static void fill_bins(const std::vector<BPrim>& prims, int first, int count, con
 static void range_bounds(const std::vector<BPrim>& prims, int first, int count, Box& b, Box& cb, bool& mixed) {
     const unsigned threads = count >= kParallelNode ? g_node_threads : 1u;
     const int32_t type0 = prims[first].type;
-    auto scan = [&prims, type0](int lo, int hi, Box& bb, Box& cc, bool& mx) {
+    auto scan = [&prims, type0](int lo, int hi, Box& bb_out, Box& cc_out, bool& mx_out) {
+        // accumulated in locals and stored once: the threads' result slots share cache lines
+        Box bb, cc;
         bb.reset();
         cc.reset();
-        mx = false;
+        bool mx = false;
         for (int i = lo; i < hi; i++) {
             bb.grow(prims[i].lo, prims[i].hi);
             cc.grow(prims[i].c, prims[i].c);
             if (prims[i].type != type0) mx = true;
         }
+        bb_out = bb;
+        cc_out = cc;
+        mx_out = mx;
     };
     if (threads <= 1) {
         scan(first, first + count, b, cb, mixed);
