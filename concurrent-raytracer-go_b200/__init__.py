@@ -38,7 +38,7 @@ EXPORTED_SYMBOLS = [
     "gort_scene_upload", "gort_scene_load_json", "gort_scene_load_file", "gort_scene_counts", "gort_scene_get_triangle",
     "gort_scene_get_material", "gort_render", "gort_render_device", "gort_shard_slab_bytes", "gort_render_shard_device",
     "gort_unswizzle_device", "gort_read_radiance", "gort_trace_rays", "gort_measure_fp32_peak",
-    "gort_host_scene_parse", "gort_host_scene_free", "gort_host_scene_counts", "gort_host_scene_get_sphere",
+    "gort_host_scene_parse", "gort_host_scene_from_desc", "gort_host_scene_free", "gort_host_scene_counts", "gort_host_scene_get_sphere",
     "gort_host_scene_get_triangle", "gort_host_scene_get_material", "gort_host_scene_get_light", "gort_host_scene_get_camera",
     "gort_host_scene_bvh_validate",
     "gort_link_create", "gort_link_open", "gort_link_close", "gort_link_frame", "gort_render_linked",
@@ -148,6 +148,7 @@ def load_library() -> C.CDLL:
     L.gort_trace_rays.argtypes = [vp, C.c_int32, dp, dp, C.c_double, C.c_double, C.c_int32, dp, ip]
     L.gort_measure_fp32_peak.argtypes = [vp, dp, dp]
     L.gort_host_scene_parse.argtypes = [C.c_char_p, C.c_size_t, C.c_uint32, C.POINTER(vp), C.c_char_p, C.c_size_t]
+    L.gort_host_scene_from_desc.argtypes = [C.POINTER(SceneDesc), C.POINTER(vp), C.c_char_p, C.c_size_t]
     L.gort_host_scene_free.argtypes = [vp]
     L.gort_host_scene_free.restype = None
     L.gort_host_scene_counts.argtypes = [vp, ip]
@@ -208,15 +209,28 @@ class HostScene:
     """Host-only parse of the reference's scene JSON by libgort's loader (no CUDA needed): the
     flattened GetHittables()/GetLights() view in the reference's scan order."""
 
-    def __init__(self, json_text: str, options: int = 0):
+    def __init__(self, json_text: Optional[str], options: int = 0):
         L = load_library()
         self._L = L
         self._h = C.c_void_p()
+        if json_text is None:  # from_desc fills it
+            return
         err = C.create_string_buffer(512)
         raw = json_text.encode()
         rc = L.gort_host_scene_parse(raw, len(raw), options, C.byref(self._h), err, len(err))
         if rc != 0:
             raise GortError(rc, err.value.decode())
+
+    @classmethod
+    def from_desc(cls, flat: "FlatScene", into: Optional["HostScene"] = None) -> "HostScene":
+        """The host side of UploadScene(FlatScene): validation + copy of a gort_scene_desc, no CUDA.  `into`: rebuild that
+        host scene in place (its arrays are reused)."""
+        hs = into if into is not None else cls(None)
+        err = C.create_string_buffer(512)
+        rc = hs._L.gort_host_scene_from_desc(C.byref(flat.desc), C.byref(hs._h), err, len(err))
+        if rc != 0:
+            raise GortError(rc, err.value.decode())
+        return hs
 
     def __del__(self):
         try:

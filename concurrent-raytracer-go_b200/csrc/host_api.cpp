@@ -39,6 +39,19 @@ int gort_host_scene_parse(const char* json_text, size_t json_len, uint32_t optio
     return GORT_OK;
 }
 
+int gort_host_scene_from_desc(const gort_scene_desc* desc, gort_host_scene** scene_inout, char* errbuf, size_t errbuf_len) {
+    if (!desc || !scene_inout) return GORT_ERR_INVALID;
+    gort_host_scene* hs = *scene_inout ? *scene_inout : new gort_host_scene();
+    std::string err = scene_from_desc(*desc, hs->s);
+    if (!err.empty()) {
+        put_err(errbuf, errbuf_len, err);
+        if (!*scene_inout) delete hs;
+        return GORT_ERR_INVALID;
+    }
+    *scene_inout = hs;
+    return GORT_OK;
+}
+
 void gort_host_scene_free(gort_host_scene* scene) { delete scene; }
 
 int gort_host_scene_counts(const gort_host_scene* scene, int32_t* c) {

@@ -292,6 +292,11 @@ typedef struct gort_host_scene gort_host_scene;
  * errbuf (may be NULL) receives the message on failure. */
 int gort_host_scene_parse(const char* json_text, size_t json_len, uint32_t options, gort_host_scene** out, char* errbuf,
                           size_t errbuf_len);
+/* The host side of gort_scene_upload (cgo: scene.Flatten() -> gort_scene_desc): the same validation and copy,
+ * kept on the host.  *scene_inout NULL: a new host scene is made; non-NULL: that one is rebuilt in place, its arrays reused
+ * (what gort_scene_upload does with the context's spare scene).  GORT_ERR_INVALID + errbuf on a bad description (the scene
+ * passed in is then unspecified but still valid to free or rebuild). */
+int gort_host_scene_from_desc(const gort_scene_desc* desc, gort_host_scene** scene_inout, char* errbuf, size_t errbuf_len);
 void gort_host_scene_free(gort_host_scene* scene);
 /* counts5 = {spheres, triangles, materials, lights, hittables} */
 int gort_host_scene_counts(const gort_host_scene* scene, int32_t* counts5);

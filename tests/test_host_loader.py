@@ -135,3 +135,56 @@ def test_parallel_bvh_build_equals_sequential(gort):
             finally:
                 del os.environ["GORT_BVH_THREADS"]
         assert infos[0] == infos[1] and infos[0]["leaves"] == infos[0]["nodes"] + 1
+
+
+def test_scene_from_desc_host_side(gort):
+    """gort_scene_upload's host half (gort_host_scene_from_desc: the same validation and copy, no device): a description of
+    > 100 000 primitives is copied by all host threads into arrays that resize() leaves untouched — every element must come
+    out as it went in —, a rebuilt scene reuses its arrays whatever the sizes, bad descriptions are refused."""
+    import synth
+    a = synth.scene_arrays(110_000, 1_500, 50.0, 5, 120.0, fog={"density": 0.01, "color": (0.2, 0.3, 0.4)})
+    flat = synth.to_gort(a)
+    hs = gort.HostScene.from_desc(flat)
+    c = hs.counts()
+    assert c == {"spheres": 110_000, "triangles": 18_000, "materials": 111_500, "lights": 3, "hittables": 110_000 + 1_500}
+    rng = np.random.default_rng(3)
+    for i in rng.integers(0, 110_000, 400).tolist() + [0, 109_999]:
+        ctr, r, m, o = hs.sphere(i)
+        assert np.array_equal(ctr, a["spheres"][i][0]) and (r, m, o) == a["spheres"][i][1:]
+    for i in rng.integers(0, 18_000, 400).tolist() + [0, 17_999]:
+        v, m, o = hs.triangle(i)
+        assert np.array_equal(v, np.asarray(a["triangles"][i][0]).reshape(-1)) and (m, o) == a["triangles"][i][1:]
+    for i in rng.integers(0, 111_500, 400).tolist() + [0, 111_499]:
+        t, v = hs.material(i)
+        want = a["materials"][i]
+        assert t == want["type"] and v[6] == want.get("ior", 1.5)
+        if t == gort.MAT_TYPES["perfectmirror"]:
+            assert v[4] == 1.0  # GetMetallic (advanced_materials.go:165)
+        if t != gort.MAT_TYPES["dielectric"]:
+            assert np.array_equal(v[:3], want.get("color", (1, 1, 1)))
+    assert np.array_equal(hs.light(2), np.array([0.0, 80.0, 0.0, 1, 1, 1, 3000.0]))
+    assert hs.bvh_validate()["nodes"] > 0
+    # rebuilt in place: smaller, then larger than ever (arrays shrink and grow), and the same answers as a fresh scene
+    small = synth.to_gort(synth.scene_arrays(50, 3, 10.0, 6, 30.0))
+    gort.HostScene.from_desc(small, into=hs)
+    assert hs.counts()["spheres"] == 50 and hs.counts()["triangles"] == 36 and hs.counts()["lights"] == 3
+    fresh = gort.HostScene.from_desc(small)
+    assert all(np.array_equal(hs.sphere(i)[0], fresh.sphere(i)[0]) for i in range(50))
+    b = synth.scene_arrays(130_000, 0, 50.0, 7, 120.0)
+    gort.HostScene.from_desc(synth.to_gort(b), into=hs)
+    assert hs.counts()["spheres"] == 130_000 and hs.counts()["triangles"] == 0
+    assert np.array_equal(hs.sphere(129_999)[0], b["spheres"][129_999][0])
+    # refused: an order that is not a permutation, a material index out of range, a missing array, another ABI
+    for field, value, msg in (("sphere_order", 1, "permutation"), ("sphere_material", 10**6, "material index")):
+        bad = synth.to_gort(synth.scene_arrays(200, 0, 10.0, 8, 30.0))
+        getattr(bad.desc, field)[7] = value
+        with pytest.raises(gort.GortError, match=msg):
+            gort.HostScene.from_desc(bad)
+    bad = synth.to_gort(synth.scene_arrays(200, 0, 10.0, 8, 30.0))
+    bad.desc.sphere_radius = None
+    with pytest.raises(gort.GortError, match="sphere arrays missing"):
+        gort.HostScene.from_desc(bad)
+    bad = synth.to_gort(synth.scene_arrays(200, 0, 10.0, 8, 30.0))
+    bad.desc.abi_version = gort.ABI_VERSION + 1
+    with pytest.raises(gort.GortError, match="abi_version"):
+        gort.HostScene.from_desc(bad)
