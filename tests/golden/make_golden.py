@@ -29,6 +29,11 @@ def main():
     json.dump({"config": "c1_view 200x150 4spp depth50 philox seed1", "counters": cnt,
                "radiance": [{"x": int(xs[i]), "y": int(ys[i]), "rgb": rad[ys[i], xs[i]].tolist()} for i in pick]},
               open(os.path.join(OUT, "c1_view_200x150_4spp_seed1.json"), "w"), indent=1)
+    # a BVH scene for both BVH render paths: the 1 500-sphere cloud (metal / glass / dielectric, 3 lights, soft shadows) at
+    # 320x180, 2 spp, depth 4, Philox seed 9
+    d = Cm.random_sphere_scene(1500, 77, cam_z=13.0)
+    img, _, _ = O.Scene(d).render(320, 180, samples=2, max_depth=4, rng_mode=O.RNG_PHILOX, seed=9, use_accel=True)
+    Image.fromarray(img, "RGBA").save(os.path.join(OUT, "sphere_cloud_1500_320x180_2spp_d4_seed9.png"), optimize=True)
 
 
 if __name__ == "__main__":

@@ -26,3 +26,13 @@ def test_oracle_reproduces_c1_fixture(oracle):
     assert cnt == meta["counters"]  # Philox mode is independent of the thread count / tile schedule
     for s in meta["radiance"]:
         assert np.allclose(rad[s["y"], s["x"]], s["rgb"], rtol=1e-12, atol=0)
+
+
+def test_oracle_reproduces_sphere_cloud_fixture(oracle):
+    ref = np.array(Image.open(os.path.join(GOLD, "sphere_cloud_1500_320x180_2spp_d4_seed9.png")).convert("RGBA"))
+    d = Cm.random_sphere_scene(1500, 77, cam_z=13.0)
+    img, _, _ = oracle.Scene(d).render(320, 180, samples=2, max_depth=4, rng_mode=oracle.RNG_PHILOX, seed=9, use_accel=True)
+    assert (img == ref).all()
+    # the oracle's own BVH answers like its linear scan (renderer.go:333-346): same image on a crop
+    lin, _, _ = oracle.Scene(d).render(320, 180, samples=2, max_depth=4, rng_mode=oracle.RNG_PHILOX, seed=9, crop=(120, 60, 200, 110))
+    assert (lin[60:110, 120:200] == ref[60:110, 120:200]).all()

@@ -190,3 +190,15 @@ def test_stream_switches_keep_the_frame(gort, renderer, objects, bvh):
         with forced_path("stream", GORT_BVH=bvh, **env):
             renderer.Render(sc, 320, 240)
             assert np.array_equal(renderer.ReadRadiance(320, 240), base), env
+
+
+@pytest.mark.parametrize("path", ["queue", "stream"])
+def test_sphere_cloud_golden_fixture(gort, renderer, path):
+    """both BVH render paths against the committed oracle image of the 1 500-sphere cloud (tests/golden/make_golden.py)"""
+    from PIL import Image
+    ref = np.array(Image.open(os.path.join(Cm.ROOT, "tests", "golden", "sphere_cloud_1500_320x180_2spp_d4_seed9.png")).convert("RGBA"))
+    configure(renderer, 2, 4, seed=9)
+    with forced_path(path):
+        img = renderer.Render(gort.SceneFromDict(Cm.random_sphere_scene(1500, 77, cam_z=13.0)), 320, 180)
+    assert (ref[..., :3].sum(-1) > 0).mean() > 0.2
+    check(img, ref, within=0.998, max_bad_lit=90)  # (the dense cloud's bar: see test_random_spheres_bvh_scene_same_stream)
