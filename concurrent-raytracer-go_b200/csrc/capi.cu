@@ -258,6 +258,8 @@ void pack_material(const HostMaterial& m, F4 out[4]) {
     out[3] = F4{(float)spec_power, (float)f0, (float)fs, (float)mf};
 }
 
+constexpr double kCoordLimit = 1e30;  // |coordinate| a scene may hold (fp32 device arithmetic squares distances)
+
 // Large scenes: the BVH is built on the device (lbvh.cu).  The host packs the primitives in scene order (parallel), one H2D
 // copy per array, and the builder writes the node / primitive arrays the kernels read.  Returns GORT_OK, an error, or
 // 1 = "use the host builder" (tree deeper than the traversal stack: many coincident centroids).
@@ -325,6 +327,10 @@ int upload_scene_device_bvh(gort_ctx* ctx) {
     in.n_spheres = (uint32_t)nS; in.n_tris = (uint32_t)nT;
     double extent = 0;
     for (int a = 0; a < 3; a++) extent = std::max(extent, std::max(std::fabs(wlo[a]), std::fabs(whi[a])));
+    if (!(extent < kCoordLimit)) {
+        ctx->has_scene = false;
+        return fail(ctx, GORT_ERR_INVALID, "scene coordinates exceed the range of the fp32 device path (|x| must stay below 1e30)");
+    }
     const double pad = 4e-7 * std::max(1.0, extent);  // as bvh.cpp
     in.pad = (float)pad;
     FlatBvh& b = ctx->bvh;
@@ -416,6 +422,14 @@ int upload_scene(gort_ctx* ctx) {
     if (ctx->bvh.max_depth > 62) {
         ctx->has_scene = false;
         return fail(ctx, GORT_ERR_INVALID, "BVH deeper than the traversal stack (62 levels): degenerate geometry");
+    }
+    for (int a = 0; a < 3; a++) {
+        // the reference computes in float64; the device path is fp32: a scene whose box leaves that range is refused, not mis-rendered
+        const double o = ctx->bvh.qorigin[a], c = ctx->bvh.qcell[a];
+        if (!(std::isfinite(o) && std::isfinite(c) && std::fabs(o) < kCoordLimit && c * 65536.0 < kCoordLimit)) {
+            ctx->has_scene = false;
+            return fail(ctx, GORT_ERR_INVALID, "scene coordinates exceed the range of the fp32 device path (|x| must stay below 1e30)");
+        }
     }
     const HostScene& hs = ctx->scene;
     std::vector<F4> mats(hs.mats.size() * 4);

@@ -54,8 +54,10 @@ class Parser {
     }
 
    private:
+    static constexpr int kMaxDepth = 1000;
     const char* p_;
     const char* end_;
+    int depth_ = 0;
     void ws() {
         while (p_ < end_ && (*p_ == ' ' || *p_ == '\t' || *p_ == '\n' || *p_ == '\r')) p_++;
     }
@@ -66,8 +68,18 @@ class Parser {
             return nullptr;
         }
         char c = *p_;
-        if (c == '{') return object(err);
-        if (c == '[') return array(err);
+        if (c == '{' || c == '[') {
+            // The parser (and the tree's destructor) recurse once per nesting level, and scene text can arrive over the
+            // network (chunk farm): bounded like Go's decoder (encoding/json stops at 10 000; a scene nests 4 deep)
+            if (depth_ >= kMaxDepth) {
+                err = "exceeded max depth";
+                return nullptr;
+            }
+            depth_++;
+            ValuePtr v = c == '{' ? object(err) : array(err);
+            depth_--;
+            return v;
+        }
         if (c == '"') {
             auto v = std::make_shared<Value>();
             v->kind = Value::String;

@@ -165,6 +165,16 @@ def test_error_codes(gort, renderer):
     with pytest.raises(gort.GortError) as e:
         r2.UploadScene(gort.Scene('{"objects": [{"type": "sphere", "material": {}}]}'))
     assert e.value.code == -6  # GORT_ERR_PARSE (the reference panics here)
+    # float64 coordinates that leave the fp32 range of the device path are refused at upload, not mis-rendered; the context
+    # has no scene afterwards
+    far = Cm.c1_view()
+    far["objects"][0]["position"] = [1e35, 0, 0]
+    with pytest.raises(gort.GortError, match="fp32") as e:
+        r2.UploadScene(gort.SceneFromDict(far))
+    assert e.value.code == -1
+    with pytest.raises(gort.GortError) as e:
+        r2.RenderDevice(16, 16, 0)
+    assert e.value.code == -4
     r2.close()
     with pytest.raises(gort.GortError):
         gort.LoadFromFile("/nonexistent/scene.json")

@@ -188,3 +188,48 @@ def test_scene_from_desc_host_side(gort):
     bad.desc.abi_version = gort.ABI_VERSION + 1
     with pytest.raises(gort.GortError, match="abi_version"):
         gort.HostScene.from_desc(bad)
+
+
+def test_loader_survives_hostile_json(gort):
+    """Scene text can come from the network (chunk farm): whatever it is, the loader answers with a scene or an error.
+    Nesting is bounded (the parser recurses per level; Go's decoder has a bound too), truncated and binary input is refused."""
+    for n, ok in ((100, True), (999, True), (1000, False), (300_000, False)):
+        text = '{"objects":' + "[" * n + "]" * n + "}"
+        if ok:
+            assert gort.HostScene(text).counts()["hittables"] == 0
+        else:
+            with pytest.raises(gort.GortError, match="exceeded max depth"):
+                gort.HostScene(text)
+    with pytest.raises(gort.GortError, match="exceeded max depth"):
+        gort.HostScene('{"a":' * 5000)
+    for text in ('{"objects":[', "[" * 50 + "1" + "]" * 49, "\x00\xff", "", '{"objects":[{"type":"sphere"', '{"lights":[{"position":"x"}]}',
+                 '{"objects":[{"type":"cube","position":[0,0,0],"size":[1,1],"material":{"type":"metal","color":[1,1,1]}}]}'):
+        with pytest.raises(gort.GortError):
+            gort.HostScene(text)
+
+    from hypothesis import given, settings, strategies as st
+
+    leaves = st.one_of(st.none(), st.booleans(), st.floats(allow_nan=False, allow_infinity=False), st.integers(-10**6, 10**6), st.text(max_size=8))
+    values = st.recursive(leaves, lambda c: st.one_of(st.lists(c, max_size=4), st.dictionaries(
+        st.sampled_from(["type", "position", "radius", "size", "material", "color", "vertices", "intensity", "x"]), c, max_size=5)), max_leaves=25)
+    scenes = st.fixed_dictionaries({}, optional={"camera": values, "objects": st.lists(values, max_size=4), "lights": st.lists(values, max_size=3),
+                                                 "fog": values, "sky": values, "renderer": values})
+
+    @settings(max_examples=300, deadline=None)
+    @given(scenes, st.integers(0, 7))
+    def structured(doc, options):
+        try:
+            gort.HostScene(json.dumps(doc), options).counts()
+        except gort.GortError:
+            pass
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.text(alphabet='{}[]":,0123456789.eE-+tfn aobjectslighpr\\u', max_size=60))
+    def soup(text):
+        try:
+            gort.HostScene(text)
+        except gort.GortError:
+            pass
+
+    structured()
+    soup()
